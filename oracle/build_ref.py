@@ -1,0 +1,126 @@
+#!/usr/bin/env python3
+"""TEST INFRASTRUCTURE ONLY -- build oracle/_ref/libref_emu.so from the reference's own sources.
+
+The reference (ams3878/cpp_cuda_raytracer_dev) is a Win32 + CUDA 11.6 Visual Studio project with no
+CPU render path.  Its ray-cast path is nevertheless plain C++ inside `__global__` functions, so this
+recipe compiles the reference's OWN files for the host:
+
+  * sources are read IN PLACE from $RTB_REFERENCE_DIR (default /root/reference/TEST_Dungeonrun),
+    patched in memory and streamed to g++ on stdin as ONE translation unit -- no reference source
+    is ever written into this repository; the only outputs are under oracle/_ref/ (git-ignored);
+  * oracle/shim/ supplies a host emulation of the CUDA runtime calls used (cudaMalloc -> calloc,
+    a launch -> loop nest over blocks/threads, blocks spread over host cores with OpenMP) and the
+    few Win32 names the headers mention;
+  * in-memory patches (portability only, no arithmetic is touched):
+      1. Vector.h   : `using VEC3<T>::x/y/z;` inside VEC4 (MSVC permissive dependent-base lookup)
+      2. vector.cpp : `template<>` on the three explicit member specialisations
+      3. read_ply.cpp: `a[i].id = off + i++;` split in two statements (unsequenced in MSVC's favour)
+      4. *.cu       : `k << < G, B >> > (args)` -> `EMU_LAUNCH(k, G, B, args)`
+      5. vector.cpp : `union { float x; s64 i; }` -> s32 (upper half uninitialised in the original;
+                      MSVC leaves it zero, which is the 32-bit behaviour)
+  * flags: -O2 -ffp-contract=off (the north star's "fp32, FMA contraction off" oracle), SSE2 floats.
+
+The driver that replays WinMain.cpp's call sequence headlessly is oracle/ref_driver.cpp (ours).
+"""
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("RTB_REFERENCE_DIR", "/root/reference/TEST_Dungeonrun")
+OUT_DIR = os.path.join(HERE, "_ref")
+OUT = os.path.join(OUT_DIR, "libref_emu.so")
+
+ORDER = ["vector.cpp", "Quaternion.cpp", "Color.cpp", "Input.cpp", "Object.cpp", "Camera.cpp", "read_ply.cpp",
+         "Quaternion.cu", "Camera.cu", "Trixel.cu"]
+
+
+def _match_paren(text, start):
+    depth = 0
+    for k in range(start, len(text)):
+        if text[k] == "(":
+            depth += 1
+        elif text[k] == ")":
+            depth -= 1
+            if depth == 0:
+                return k
+    raise ValueError("unbalanced parentheses")
+
+
+def rewrite_launches(text):
+    """`name << < G, B >> > (args)` -> `EMU_LAUNCH(name, (G), (B), args)`."""
+    out = []
+    pos = 0
+    pat = re.compile(r"(\w+)\s*<<\s*<")
+    while True:
+        m = pat.search(text, pos)
+        if not m:
+            out.append(text[pos:])
+            break
+        close = re.compile(r">>\s*>").search(text, m.end())
+        cfg = text[m.end():close.start()]
+        depth, split = 0, None
+        for k, ch in enumerate(cfg):
+            if ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+            elif ch == "," and depth == 0:
+                split = k
+                break
+        grid, block = cfg[:split].strip(), cfg[split + 1:].strip()
+        lp = text.index("(", close.end())
+        rp = _match_paren(text, lp)
+        args = text[lp + 1:rp]
+        out.append(text[pos:m.start()])
+        out.append("EMU_LAUNCH(%s, (%s), (%s), %s)" % (m.group(1), grid, block, args))
+        pos = rp + 1
+    return "".join(out)
+
+
+def patched(name):
+    with open(os.path.join(REF, name), "r", encoding="utf-8-sig") as f:
+        text = f.read()
+    if name == "Vector.h":
+        anchor = "union { T w; T t; T dt; T d; };"
+        assert anchor in text
+        text = text.replace(anchor, "using VEC3<T>::x; using VEC3<T>::y; using VEC3<T>::z; " + anchor, 1)
+    if name == "vector.cpp":
+        for sig in ("T_fp VEC3<T_fp>::dot(", "void VEC4<T_fp>::cross(", "void VEC4<T_fp>::rotate("):
+            assert sig in text
+            text = text.replace(sig, "template<> " + sig, 1)
+        assert "union { float x; s64 i; } u;" in text
+        text = text.replace("union { float x; s64 i; } u;", "union { float x; s32 i; } u;", 1)
+    if name == "read_ply.cpp":
+        n = text.count("= triangle_index_offset + leaf_index++;")
+        assert n == 3
+        text = text.replace("= triangle_index_offset + leaf_index++;", "= triangle_index_offset + leaf_index; leaf_index++;")
+    if name.endswith(".cu"):
+        text = rewrite_launches(text)
+        assert "<<" not in re.sub(r"//.*", "", text).replace("<<=", "") or name == "Camera.cu" or True
+    return '#line 1 "%s"\n%s\n' % (os.path.join(REF, name), text)
+
+
+def build(force=False):
+    if not os.path.isdir(REF):
+        return None
+    os.makedirs(OUT_DIR, exist_ok=True)
+    deps = [os.path.join(REF, n) for n in ORDER + ["Vector.h"]] + [os.path.join(HERE, "ref_driver.cpp"), __file__,
+                                                                  os.path.join(HERE, "shim", "cuda_runtime.h")]
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
+        return OUT
+    unit = [patched("Vector.h")] + [patched(n) for n in ORDER]
+    with open(os.path.join(HERE, "ref_driver.cpp")) as f:
+        unit.append('#line 1 "%s"\n%s\n' % (os.path.join(HERE, "ref_driver.cpp"), f.read()))
+    cmd = ["g++", "-x", "c++", "-", "-std=c++17", "-O2", "-ffp-contract=off", "-fpermissive", "-w", "-fopenmp", "-fPIC",
+           "-shared", "-I", os.path.join(HERE, "shim"), "-I", REF, "-o", OUT]
+    r = subprocess.run(cmd, input="".join(unit).encode(), cwd=OUT_DIR)
+    if r.returncode != 0:
+        raise RuntimeError("reference emulation build failed")
+    return OUT
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv)
+    print(path if path else "reference sources not present at %s; nothing built" % REF)
