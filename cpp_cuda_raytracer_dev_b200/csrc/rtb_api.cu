@@ -1,0 +1,638 @@
+// rtb_api.cu -- the C ABI declared in include/rtb.h: handles, device memory, launches.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rtb.h"
+#include "rtb_host.hpp"
+#include "rtb_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+thread_local int g_device = 0;
+
+int fail(rtb_status code, const std::string& what) {
+    g_error = what;
+    return (int)code;
+}
+#define RTB_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) return fail(RTB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+template <class T>
+void dfree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+}  // namespace
+
+struct rtb_mesh {
+    int device = 0;
+    int64_t n = 0;
+    std::vector<float> points;  // 9 per triangle (Trixel::h_points_init_data)
+    std::vector<float> rad;     // 3 per triangle, or empty when uniform
+    float uniform_rgb[3] = {0.1f, 0.55f, 0.2f};
+    float* d_points = nullptr;  // Trixel::d_points_init_data
+    rtb::HostTree tree;
+    bool built = false;
+};
+
+struct rtb_camera {
+    int device = 0;
+    rtb::CameraBasis basis;
+    long long pixels = 0;
+    uint32_t* d_bgra = nullptr;  // Camera::h_mem.d_color.c
+    int32_t* d_ids = nullptr;    // Camera::pixel_memory::d_rmi
+    uint32_t* h_bgra = nullptr;  // Camera::h_mem.h_color.c (pinned)
+    int32_t* h_ids = nullptr;    // pinned
+    unsigned long long* d_counters = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_render[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    // sweep ring: two chunks of device frames + pinned staging
+    uint32_t* ring_bgra[2] = {nullptr, nullptr};
+    int32_t* ring_ids[2] = {nullptr, nullptr};
+    uint32_t* stage_bgra[2] = {nullptr, nullptr};
+    int32_t* stage_ids[2] = {nullptr, nullptr};
+    int ring_frames = 0;
+    rtb_object* bound = nullptr;
+    int sm_count = 0;
+};
+
+struct rtb_object {
+    rtb_mesh* mesh = nullptr;
+    rtb_camera* cam = nullptr;
+    rtb::Transform xf;
+    bool xf_ready = false;
+    // per-(camera, mesh) device arrays: Camera::voxel_memory + Camera::trixel_memory + Trixel::trixel_memory
+    float4* d_scene = nullptr;  // nodes then triangles in ONE allocation (one L2 persisting window)
+    float4* d_nodes = nullptr;
+    float4* d_tris = nullptr;
+    float4* d_rad = nullptr;
+    size_t scene_bytes = 0;
+    float root_box[6] = {0, 0, 0, 0, 0, 0};
+    int root_ref = 0;
+    float* d_frames = nullptr;  // matrices of the frames in flight
+    float* h_frames = nullptr;  // pinned
+    int frames_capacity = 0;
+    unsigned long long* d_work = nullptr;
+};
+
+namespace {
+
+int ensure_frames(rtb_object* o, int frames) {
+    if (frames <= o->frames_capacity) return RTB_OK;
+    int cap = std::max(frames, 64);
+    if (o->d_frames) cudaFree(o->d_frames);
+    if (o->h_frames) cudaFreeHost(o->h_frames);
+    o->d_frames = nullptr; o->h_frames = nullptr; o->frames_capacity = 0;
+    RTB_CUDA(cudaMalloc(&o->d_frames, sizeof(float) * 12 * (size_t)cap));
+    RTB_CUDA(cudaMallocHost(&o->h_frames, sizeof(float) * 12 * (size_t)cap));
+    o->frames_capacity = cap;
+    return RTB_OK;
+}
+
+// Launch the persistent render kernel over `num_frames` matrices already resident in o->d_frames.
+int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, int num_frames, int tile_first, int tile_stride,
+                  uint32_t flags, uint32_t* d_bgra, int32_t* d_ids, cudaStream_t stream) {
+    using namespace rtb;
+    RenderParams P;
+    std::memset(&P, 0, sizeof P);
+    const CameraBasis& b = c->basis;
+    P.W = b.W; P.H = b.H;
+    for (int k = 0; k < 3; k++) { P.n_mod[k] = b.n_mod[k]; P.u_mod[k] = b.u_mod[k]; P.v_mod[k] = b.v_mod[k]; }
+    for (int k = 0; k < 6; k++) P.root_box[k] = o->root_box[k];
+    P.draw_distance = b.draw_distance;
+    P.background = ((uint32_t)b.background[3] << 24) | ((uint32_t)b.background[0] << 16) | ((uint32_t)b.background[1] << 8) | b.background[2];
+    P.root_ref = o->root_ref;
+    P.nodes = o->d_nodes; P.tris = o->d_tris; P.rad = o->d_rad;
+    for (int k = 0; k < 3; k++) P.uniform_rad[k] = o->mesh->uniform_rgb[k];
+    P.frames = d_frames;
+    P.num_frames = num_frames;
+    P.tiles_x = (b.W + kTile - 1) / kTile;
+    const int tiles_y = (b.H + kTile - 1) / kTile;
+    const int tiles = P.tiles_x * tiles_y;
+    if (tile_stride < 1 || tile_first < 0 || tile_first >= tile_stride) return fail(RTB_ERR_ARG, "render: bad tile_first/tile_stride");
+    P.tile_first = tile_first; P.tile_stride = tile_stride;
+    P.my_tiles = tile_first < tiles ? (tiles - tile_first + tile_stride - 1) / tile_stride : 0;
+    P.total_items = (long long)num_frames * P.my_tiles * kItemsPerTile;
+    P.out_bgra = d_bgra; P.out_ids = d_ids;
+    P.work_counter = o->d_work;
+    P.counters = c->d_counters;
+    P.cull_rel = 1e-5f;
+    if (P.total_items == 0) return RTB_OK;
+
+    const bool cull = !(flags & RTB_RENDER_NO_CULL), count = (flags & RTB_RENDER_COUNTERS) != 0;
+    void (*kern)(const RenderParams) = cull ? (count ? render_kernel<true, true> : render_kernel<true, false>)
+                                            : (count ? render_kernel<false, true> : render_kernel<false, false>);
+    int per_sm = 0;
+    RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, 0));
+    per_sm = std::max(per_sm, 1);
+    const long long warps_total = (long long)c->sm_count * per_sm * (kBlockThreads / 32);
+    long long chunk = P.total_items / (warps_total * 8);
+    chunk = std::max(1ll, std::min<long long>(chunk, kItemsPerTile));
+    P.chunk = (int)chunk;
+    const long long fetches = (P.total_items + chunk - 1) / chunk;
+    const long long blocks_needed = (fetches + (kBlockThreads / 32) - 1) / (kBlockThreads / 32);
+    const int grid = (int)std::max(1ll, std::min<long long>((long long)c->sm_count * per_sm, blocks_needed));
+    RTB_CUDA(cudaMemsetAsync(o->d_work, 0, sizeof(unsigned long long), stream));
+    kern<<<grid, kBlockThreads, 0, stream>>>(P);
+    RTB_CUDA(cudaGetLastError());
+    return RTB_OK;
+}
+
+int check_bound(rtb_object* o, rtb_camera* c, const char* who) {
+    if (!o || !c) return fail(RTB_ERR_ARG, std::string(who) + ": null handle");
+    if (o->cam != c || !o->d_scene) return fail(RTB_ERR_STATE, std::string(who) + ": object was not added to this camera (rtb_camera_add_object)");
+    return RTB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rtb_last_error(void) { return g_error.c_str(); }
+const char* rtb_version(void) { return "rtb 0.1 (sm_100a)"; }
+
+int rtb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int rtb_set_device(int device) {
+    RTB_CUDA(cudaSetDevice(device));
+    g_device = device;
+    return RTB_OK;
+}
+
+int rtb_read_ply(const char* file_name, int mode, float** points9, uint32_t* num_tri) {
+    if (!file_name || !points9 || !num_tri) return fail(RTB_ERR_ARG, "read_ply: null argument");
+    std::vector<float> pts;
+    std::string err = rtb::load_ply(file_name, mode, pts);
+    if (!err.empty()) return fail(RTB_ERR_IO, err);
+    float* out = (float*)std::malloc(sizeof(float) * std::max<size_t>(pts.size(), 1));
+    if (!out) return fail(RTB_ERR_NOMEM, "read_ply: out of memory");
+    std::memcpy(out, pts.data(), sizeof(float) * pts.size());
+    *points9 = out;
+    *num_tri = (uint32_t)(pts.size() / 9);
+    return RTB_OK;
+}
+void rtb_free(void* p) { std::free(p); }
+
+int rtb_write_ply(const char* file_name, const float* points9, uint32_t num_tri) {
+    if (!file_name || !points9) return fail(RTB_ERR_ARG, "write_ply: null argument");
+    std::string err = rtb::save_ply(file_name, points9, num_tri);
+    if (!err.empty()) return fail(RTB_ERR_IO, err);
+    return RTB_OK;
+}
+
+int rtb_mesh_geodesic(int nu, float radius, const float center[3], float displacement, uint32_t seed, float** points9,
+                      uint32_t* num_tri) {
+    if (nu < 1 || nu > 4000 || !center || !points9 || !num_tri) return fail(RTB_ERR_ARG, "mesh_geodesic: bad argument");
+    std::vector<float> pts;
+    rtb::make_geodesic(nu, radius, center, displacement, seed, pts);
+    float* out = (float*)std::malloc(sizeof(float) * pts.size());
+    if (!out) return fail(RTB_ERR_NOMEM, "mesh_geodesic: out of memory");
+    std::memcpy(out, pts.data(), sizeof(float) * pts.size());
+    *points9 = out;
+    *num_tri = (uint32_t)(pts.size() / 9);
+    return RTB_OK;
+}
+
+// ---- mesh ----------------------------------------------------------------------------------------
+
+int rtb_mesh_create(const float* points9, int64_t num_tri, const float* rad3, const float uniform_rgb[3], rtb_mesh** out) {
+    if (!points9 || num_tri <= 0 || num_tri > 0x3fffffff || !out) return fail(RTB_ERR_ARG, "mesh_create: bad argument");
+    rtb_mesh* m = new rtb_mesh();
+    m->device = g_device;
+    m->n = num_tri;
+    m->points.assign(points9, points9 + 9 * (size_t)num_tri);
+    if (rad3) m->rad.assign(rad3, rad3 + 3 * (size_t)num_tri);
+    if (uniform_rgb) std::memcpy(m->uniform_rgb, uniform_rgb, 12);
+    cudaError_t e = cudaSetDevice(m->device);
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_points, sizeof(float) * 9 * (size_t)num_tri);
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_points, points9, sizeof(float) * 9 * (size_t)num_tri, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        // like the reference, the object exists but carries the error: the tree can still be built
+        // and inspected on the host; anything that renders will fail with RTB_ERR_CUDA
+        cudaGetLastError();
+        m->d_points = nullptr;
+        g_error = std::string("mesh_create: ") + cudaGetErrorString(e);
+    }
+    *out = m;
+    return e == cudaSuccess ? RTB_OK : RTB_ERR_CUDA;
+}
+
+int rtb_mesh_build_tree(rtb_mesh* mesh) {
+    if (!mesh) return fail(RTB_ERR_ARG, "build_tree: null mesh");
+    rtb::build_tree(mesh->points.data(), mesh->n, mesh->tree, 0);
+    mesh->built = true;
+    return RTB_OK;
+}
+int64_t rtb_mesh_num_triangles(const rtb_mesh* mesh) { return mesh ? mesh->n : 0; }
+int64_t rtb_mesh_num_nodes(const rtb_mesh* mesh) { return mesh ? 2 * mesh->n - 1 : 0; }
+
+int rtb_mesh_get_tree(const rtb_mesh* mesh, int32_t* left, int32_t* right, int32_t* tri, int32_t* cut_flag, float* bounds6,
+                      float* s1, float* s2) {
+    if (!mesh || !mesh->built) return fail(RTB_ERR_STATE, "get_tree: tree not built");
+    const rtb::HostTree& T = mesh->tree;
+    for (int64_t i = 0; i < T.num_nodes; i++) {
+        if (left) left[i] = T.left[i];
+        if (right) right[i] = T.left[i] < 0 ? -1 : T.left[i] + 1;
+        if (tri) tri[i] = T.tri[i];
+        if (cut_flag) cut_flag[i] = T.cut_flag[i];
+        if (s1) s1[i] = T.s1[i];
+        if (s2) s2[i] = T.s2[i];
+    }
+    if (bounds6) std::memcpy(bounds6, T.bounds.data(), sizeof(float) * 6 * (size_t)T.num_nodes);
+    return RTB_OK;
+}
+int rtb_mesh_build_seconds(const rtb_mesh* mesh, double out3[3]) {
+    if (!mesh || !mesh->built || !out3) return fail(RTB_ERR_STATE, "build_seconds: tree not built");
+    out3[0] = mesh->tree.seconds_sort; out3[1] = mesh->tree.seconds_partition; out3[2] = out3[0] + out3[1];
+    return RTB_OK;
+}
+void rtb_mesh_destroy(rtb_mesh* mesh) {
+    if (!mesh) return;
+    if (mesh->d_points) { cudaSetDevice(mesh->device); cudaFree(mesh->d_points); }
+    delete mesh;
+}
+
+// ---- camera --------------------------------------------------------------------------------------
+
+int rtb_camera_create(int32_t r_w, int32_t r_h, float f_w, float f_h, float fclen, const float pos[3], const float look_at[3],
+                      const float up[3], rtb_camera** out) {
+    if (r_w <= 0 || r_h <= 0 || !pos || !look_at || !up || !out) return fail(RTB_ERR_ARG, "camera_create: bad argument");
+    rtb_camera* c = new rtb_camera();
+    c->device = g_device;
+    rtb::camera_basis(r_w, r_h, f_w, f_h, fclen, pos, look_at, up, c->basis);
+    c->pixels = (long long)r_w * r_h;
+    *out = c;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_bgra, sizeof(uint32_t) * (size_t)c->pixels);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_ids, sizeof(int32_t) * (size_t)c->pixels);
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_bgra, sizeof(uint32_t) * (size_t)c->pixels);
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_ids, sizeof(int32_t) * (size_t)c->pixels);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 8);
+    if (e == cudaSuccess) e = cudaMemset(c->d_counters, 0, sizeof(unsigned long long) * 8);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+        e = cudaEventCreateWithFlags(&c->ev_render[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copy[k], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
+    if (e == cudaSuccess) {
+        // init_cam_mem_cuda zeroes the frame (Camera.cu:98) and sets ids to -1 (Camera.cu:110)
+        std::memset(c->h_bgra, 0, sizeof(uint32_t) * (size_t)c->pixels);
+        for (long long i = 0; i < c->pixels; i++) c->h_ids[i] = -1;
+        e = cudaMemset(c->d_bgra, 0, sizeof(uint32_t) * (size_t)c->pixels);
+        if (e == cudaSuccess) e = cudaMemset(c->d_ids, 0xff, sizeof(int32_t) * (size_t)c->pixels);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        g_error = std::string("camera_create: ") + cudaGetErrorString(e);
+        return RTB_ERR_CUDA;  // the handle stays valid for host-side queries (basis)
+    }
+    return RTB_OK;
+}
+
+int rtb_camera_get_basis(const rtb_camera* cam, float out18[18]) {
+    if (!cam || !out18) return fail(RTB_ERR_ARG, "camera_get_basis: null argument");
+    const rtb::CameraBasis& b = cam->basis;
+    const float* src[6] = {b.n, b.v, b.u, b.n_mod, b.v_mod, b.u_mod};
+    for (int k = 0; k < 6; k++) std::memcpy(out18 + 3 * k, src[k], 12);
+    return RTB_OK;
+}
+
+int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj) {
+    if (!cam || !obj) return fail(RTB_ERR_ARG, "add_object: null handle");
+    rtb_mesh* m = obj->mesh;
+    if (!m->built) return fail(RTB_ERR_STATE, "add_object: rtb_mesh_build_tree has not been called");
+    if (!m->d_points || !cam->d_bgra) return fail(RTB_ERR_CUDA, "add_object: mesh or camera has no device memory (no usable GPU)");
+    if (m->device != cam->device) return fail(RTB_ERR_ARG, "add_object: mesh and camera live on different devices");
+    RTB_CUDA(cudaSetDevice(cam->device));
+    // Camera.cpp:131-134: faces = -camera position, identity quaternion
+    obj->xf.reset(cam->basis.pos);
+    obj->xf_ready = true;
+    obj->cam = cam;
+    cam->bound = obj;
+
+    const rtb::HostTree& T = m->tree;
+    const int64_t N = T.num_nodes, n = m->n, interior = n - 1;
+    dfree(obj->d_scene); dfree(obj->d_rad);
+    obj->d_nodes = obj->d_tris = nullptr;
+    const size_t node_bytes = sizeof(float4) * 4 * (size_t)std::max<int64_t>(interior, 1);
+    const size_t tri_bytes = sizeof(float4) * 3 * (size_t)n;
+    obj->scene_bytes = node_bytes + tri_bytes;
+    RTB_CUDA(cudaMalloc(&obj->d_scene, obj->scene_bytes));
+    obj->d_nodes = obj->d_scene;
+    obj->d_tris = obj->d_scene + node_bytes / sizeof(float4);
+    if (!obj->d_work) RTB_CUDA(cudaMalloc(&obj->d_work, sizeof(unsigned long long)));
+
+    // record index of every interior node, in node (BFS) order
+    std::vector<int32_t> record_of((size_t)N);
+    int32_t next = 0;
+    for (int64_t i = 0; i < N; i++) record_of[(size_t)i] = T.left[(size_t)i] >= 0 ? next++ : -1;
+
+    float* d_bounds = nullptr; int* d_left = nullptr; int* d_tri = nullptr; unsigned char* d_cut = nullptr; int* d_rec = nullptr;
+    cudaError_t e = cudaMalloc(&d_bounds, sizeof(float) * 6 * (size_t)N);
+    if (e == cudaSuccess) e = cudaMalloc(&d_left, sizeof(int) * (size_t)N);
+    if (e == cudaSuccess) e = cudaMalloc(&d_tri, sizeof(int) * (size_t)N);
+    if (e == cudaSuccess) e = cudaMalloc(&d_cut, (size_t)N);
+    if (e == cudaSuccess) e = cudaMalloc(&d_rec, sizeof(int) * (size_t)N);
+    if (e == cudaSuccess) e = cudaMemcpy(d_bounds, T.bounds.data(), sizeof(float) * 6 * (size_t)N, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_left, T.left.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_tri, T.tri.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_cut, T.cut_flag.data(), (size_t)N, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_rec, record_of.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice);
+    const float cx = cam->basis.pos[0], cy = cam->basis.pos[1], cz = cam->basis.pos[2];
+    if (e == cudaSuccess) {
+        rtb::pack_triangles_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cam->stream>>>(m->d_points, n, cx, cy, cz, obj->d_tris);
+        if (interior > 0)
+            rtb::pack_nodes_kernel<<<(unsigned)((N + 255) / 256), 256, 0, cam->stream>>>(d_bounds, d_left, d_tri, d_cut, d_rec, N, cx, cy, cz, obj->d_nodes);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && !m->rad.empty()) {
+        std::vector<float4> rad4((size_t)n);
+        for (int64_t i = 0; i < n; i++) rad4[(size_t)i] = make_float4(m->rad[3 * i], m->rad[3 * i + 1], m->rad[3 * i + 2], 0.0f);
+        e = cudaMalloc(&obj->d_rad, sizeof(float4) * (size_t)n);
+        if (e == cudaSuccess) e = cudaMemcpy(obj->d_rad, rad4.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cam->stream);
+    cudaFree(d_bounds); cudaFree(d_left); cudaFree(d_tri); cudaFree(d_cut); cudaFree(d_rec);
+    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, std::string("add_object: ") + cudaGetErrorString(e));
+
+    // root box, camera-relative (same arithmetic as pack_nodes_kernel; host is compiled without FMA)
+    const float* rb = T.bounds.data();
+    obj->root_box[0] = (rb[0] - cx) + 0.0f; obj->root_box[3] = (rb[1] - cx) + 0.0f;
+    obj->root_box[1] = (rb[2] - cy) + 0.0f; obj->root_box[4] = (rb[3] - cy) + 0.0f;
+    obj->root_box[2] = (rb[4] - cz) + 0.0f; obj->root_box[5] = (rb[5] - cz) + 0.0f;
+    obj->root_ref = n == 1 ? ~T.tri[0] : 0;
+
+    // pin nodes + triangles in L2 (the 800k-triangle dragon fits)
+    const char* env = std::getenv("RTB_L2_PERSIST");
+    if (!(env && env[0] == '0')) {
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cam->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, cam->device);
+        if (max_persist > 0 && max_window > 0) {
+            const size_t want = std::min<size_t>(obj->scene_bytes, (size_t)max_persist);
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                cudaStreamAttrValue attr;
+                std::memset(&attr, 0, sizeof attr);
+                attr.accessPolicyWindow.base_ptr = obj->d_scene;
+                attr.accessPolicyWindow.num_bytes = std::min<size_t>(obj->scene_bytes, (size_t)max_window);
+                attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                cudaStreamSetAttribute(cam->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+            }
+            cudaGetLastError();
+        }
+    }
+    return RTB_OK;
+}
+
+int rtb_camera_color_pixels(rtb_camera* cam, uint8_t tag) {
+    if (!cam || !cam->d_bgra) return fail(RTB_ERR_CUDA, "color_pixels: camera has no device memory");
+    RTB_CUDA(cudaSetDevice(cam->device));
+    if (tag == RTB_SET_COLOR_TAG) {
+        const rtb::CameraBasis& b = cam->basis;
+        const uint32_t bg = ((uint32_t)b.background[3] << 24) | ((uint32_t)b.background[0] << 16) | ((uint32_t)b.background[1] << 8) | b.background[2];
+        rtb::fill_kernel<<<(unsigned)((cam->pixels + 255) / 256), 256, 0, cam->stream>>>(cam->d_bgra, cam->pixels, bg);
+        rtb::fill_ids_kernel<<<(unsigned)((cam->pixels + 255) / 256), 256, 0, cam->stream>>>(cam->d_ids, cam->pixels, -1);
+        RTB_CUDA(cudaGetLastError());
+    } else if (tag != RTB_PHONG_COLOR_TAG) {
+        return fail(RTB_ERR_ARG, "color_pixels: unknown tag");
+    }
+    RTB_CUDA(cudaMemcpyAsync(cam->h_bgra, cam->d_bgra, sizeof(uint32_t) * (size_t)cam->pixels, cudaMemcpyDeviceToHost, cam->stream));
+    RTB_CUDA(cudaMemcpyAsync(cam->h_ids, cam->d_ids, sizeof(int32_t) * (size_t)cam->pixels, cudaMemcpyDeviceToHost, cam->stream));
+    RTB_CUDA(cudaStreamSynchronize(cam->stream));
+    return RTB_OK;
+}
+const uint32_t* rtb_camera_host_color(const rtb_camera* cam) { return cam ? cam->h_bgra : nullptr; }
+const int32_t* rtb_camera_host_ids(const rtb_camera* cam) { return cam ? cam->h_ids : nullptr; }
+
+int rtb_camera_counters(rtb_camera* cam, uint64_t out5[5], int reset) {
+    if (!cam || !cam->d_counters || !out5) return fail(RTB_ERR_ARG, "counters: bad argument");
+    RTB_CUDA(cudaSetDevice(cam->device));
+    unsigned long long h[8];
+    RTB_CUDA(cudaStreamSynchronize(cam->stream));
+    RTB_CUDA(cudaMemcpy(h, cam->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 5; k++) out5[k] = h[k];
+    if (reset) RTB_CUDA(cudaMemset(cam->d_counters, 0, sizeof h));
+    return RTB_OK;
+}
+
+void rtb_camera_destroy(rtb_camera* cam) {
+    if (!cam) return;
+    cudaSetDevice(cam->device);
+    if (cam->stream) cudaStreamSynchronize(cam->stream);
+    if (cam->copy_stream) cudaStreamSynchronize(cam->copy_stream);
+    dfree(cam->d_bgra); dfree(cam->d_ids); dfree(cam->d_counters);
+    if (cam->h_bgra) cudaFreeHost(cam->h_bgra);
+    if (cam->h_ids) cudaFreeHost(cam->h_ids);
+    for (int k = 0; k < 2; k++) {
+        dfree(cam->ring_bgra[k]); dfree(cam->ring_ids[k]);
+        if (cam->stage_bgra[k]) cudaFreeHost(cam->stage_bgra[k]);
+        if (cam->stage_ids[k]) cudaFreeHost(cam->stage_ids[k]);
+        if (cam->ev_render[k]) cudaEventDestroy(cam->ev_render[k]);
+        if (cam->ev_copy[k]) cudaEventDestroy(cam->ev_copy[k]);
+    }
+    if (cam->stream) cudaStreamDestroy(cam->stream);
+    if (cam->copy_stream) cudaStreamDestroy(cam->copy_stream);
+    if (cam->bound) cam->bound->cam = nullptr;
+    delete cam;
+}
+
+// ---- object --------------------------------------------------------------------------------------
+
+int rtb_object_create(rtb_mesh* mesh, rtb_object** out) {
+    if (!mesh || !out) return fail(RTB_ERR_ARG, "object_create: null argument");
+    rtb_object* o = new rtb_object();
+    o->mesh = mesh;
+    *out = o;
+    return RTB_OK;
+}
+
+int rtb_object_transform_host(rtb_object* obj, const float xyzw[4], uint8_t select, float m12_out[12]) {
+    if (!obj || !xyzw) return fail(RTB_ERR_ARG, "transform: null argument");
+    if (!obj->xf_ready) return fail(RTB_ERR_STATE, "transform: object was not added to a camera");
+    if (!obj->xf.apply(select, xyzw[0], xyzw[1], xyzw[2], xyzw[3])) return fail(RTB_ERR_ARG, "transform: unknown selector");
+    if (m12_out) obj->xf.matrix(m12_out);
+    return RTB_OK;
+}
+int rtb_object_transform(rtb_object* obj, const float xyzw[4], uint8_t select) {
+    // the matrix reaches the device with the next render (it travels with the frame list), which
+    // replaces the reference's two 1-thread kernels per transform (Quaternion.cu:21, Camera.cu:279,322)
+    return rtb_object_transform_host(obj, xyzw, select, nullptr);
+}
+int rtb_object_get_matrix(const rtb_object* obj, float m12[12]) {
+    if (!obj || !m12 || !obj->xf_ready) return fail(RTB_ERR_STATE, "get_matrix: object was not added to a camera");
+    obj->xf.matrix(m12);
+    return RTB_OK;
+}
+int rtb_object_set_matrix(rtb_object* obj, const float m12[12]) {
+    if (!obj || !m12 || !obj->xf_ready) return fail(RTB_ERR_STATE, "set_matrix: object was not added to a camera");
+    obj->xf.set_matrix(m12);
+    return RTB_OK;
+}
+void rtb_object_destroy(rtb_object* obj) {
+    if (!obj) return;
+    if (obj->cam) { cudaSetDevice(obj->cam->device); if (obj->cam->bound == obj) obj->cam->bound = nullptr; }
+    dfree(obj->d_scene); dfree(obj->d_rad); dfree(obj->d_frames); dfree(obj->d_work);
+    if (obj->h_frames) cudaFreeHost(obj->h_frames);
+    delete obj;
+}
+
+// ---- render --------------------------------------------------------------------------------------
+
+int rtb_object_render(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
+    int rc = check_bound(obj, cam, "render");
+    if (rc) return rc;
+    RTB_CUDA(cudaSetDevice(cam->device));
+    rc = ensure_frames(obj, 1);
+    if (rc) return rc;
+    obj->xf.matrix(obj->h_frames);
+    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * 12, cudaMemcpyHostToDevice, cam->stream));
+    rc = launch_render(obj, cam, obj->d_frames, 1, 0, 1, flags, cam->d_bgra, cam->d_ids, cam->stream);
+    if (rc) return rc;
+    // the reference's wrapper synchronises (Trixel.cu:234)
+    RTB_CUDA(cudaStreamSynchronize(cam->stream));
+    return RTB_OK;
+}
+
+int rtb_render_frame(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
+    int rc = check_bound(obj, cam, "render_frame");
+    if (rc) return rc;
+    RTB_CUDA(cudaSetDevice(cam->device));
+    rc = ensure_frames(obj, 1);
+    if (rc) return rc;
+    obj->xf.matrix(obj->h_frames);
+    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * 12, cudaMemcpyHostToDevice, cam->stream));
+    rc = launch_render(obj, cam, obj->d_frames, 1, 0, 1, flags, cam->d_bgra, cam->d_ids, cam->stream);
+    if (rc) return rc;
+    RTB_CUDA(cudaMemcpyAsync(cam->h_bgra, cam->d_bgra, sizeof(uint32_t) * (size_t)cam->pixels, cudaMemcpyDeviceToHost, cam->stream));
+    RTB_CUDA(cudaMemcpyAsync(cam->h_ids, cam->d_ids, sizeof(int32_t) * (size_t)cam->pixels, cudaMemcpyDeviceToHost, cam->stream));
+    RTB_CUDA(cudaStreamSynchronize(cam->stream));
+    return RTB_OK;
+}
+
+int rtb_render_frames_device_async(rtb_object* obj, rtb_camera* cam, int32_t num_frames, const float* m12, int32_t tile_first,
+                                   int32_t tile_stride, uint32_t flags, uint32_t* d_bgra, int32_t* d_ids, void* stream) {
+    int rc = check_bound(obj, cam, "render_frames_device");
+    if (rc) return rc;
+    if (num_frames <= 0 || !m12) return fail(RTB_ERR_ARG, "render_frames_device: bad argument");
+    RTB_CUDA(cudaSetDevice(cam->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : cam->stream;
+    // the pinned matrix staging buffer is reused: wait for the previous upload on it
+    RTB_CUDA(cudaStreamSynchronize(s));
+    rc = ensure_frames(obj, num_frames);
+    if (rc) return rc;
+    std::memcpy(obj->h_frames, m12, sizeof(float) * 12 * (size_t)num_frames);
+    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * 12 * (size_t)num_frames, cudaMemcpyHostToDevice, s));
+    return launch_render(obj, cam, obj->d_frames, num_frames, tile_first, tile_stride, flags, d_bgra, d_ids, s);
+}
+
+int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32_t steps_per_frame, const float* ops5,
+                     uint32_t flags, uint32_t* bgra_out, int32_t* ids_out) {
+    int rc = check_bound(obj, cam, "render_sweep");
+    if (rc) return rc;
+    if (num_frames <= 0 || steps_per_frame < 0 || (steps_per_frame > 0 && !ops5)) return fail(RTB_ERR_ARG, "render_sweep: bad argument");
+    RTB_CUDA(cudaSetDevice(cam->device));
+    RTB_CUDA(cudaStreamSynchronize(cam->stream));
+    rc = ensure_frames(obj, num_frames);
+    if (rc) return rc;
+    // host recurrence for every frame (Camera.cu:254-335), exactly as if the calls were made one by one
+    for (int f = 0; f < num_frames; f++) {
+        for (int s = 0; s < steps_per_frame; s++) {
+            const float* op = ops5 + 5 * ((size_t)f * steps_per_frame + s);
+            const int select = (int)op[0];
+            if (select == 0) continue;
+            if (!obj->xf.apply((uint8_t)select, op[1], op[2], op[3], op[4])) return fail(RTB_ERR_ARG, "render_sweep: unknown selector");
+        }
+        obj->xf.matrix(obj->h_frames + 12 * (size_t)f);
+    }
+    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * 12 * (size_t)num_frames, cudaMemcpyHostToDevice, cam->stream));
+
+    // ring of two device chunks; chunk k+1 renders while chunk k streams to the host
+    const size_t P = (size_t)cam->pixels;
+    int chunk_frames = (int)std::max<size_t>(1, std::min<size_t>((size_t)num_frames, (size_t)(48u << 20) / (P * 4)));
+    if (cam->ring_frames < chunk_frames) {
+        for (int k = 0; k < 2; k++) {
+            dfree(cam->ring_bgra[k]); dfree(cam->ring_ids[k]);
+            if (cam->stage_bgra[k]) { cudaFreeHost(cam->stage_bgra[k]); cam->stage_bgra[k] = nullptr; }
+            if (cam->stage_ids[k]) { cudaFreeHost(cam->stage_ids[k]); cam->stage_ids[k] = nullptr; }
+            RTB_CUDA(cudaMalloc(&cam->ring_bgra[k], 4 * P * (size_t)chunk_frames));
+            RTB_CUDA(cudaMalloc(&cam->ring_ids[k], 4 * P * (size_t)chunk_frames));
+            RTB_CUDA(cudaMallocHost(&cam->stage_bgra[k], 4 * P * (size_t)chunk_frames));
+            RTB_CUDA(cudaMallocHost(&cam->stage_ids[k], 4 * P * (size_t)chunk_frames));
+        }
+        cam->ring_frames = chunk_frames;
+    }
+    chunk_frames = std::min(chunk_frames, cam->ring_frames);
+    // caller buffers that are already pinned receive the DMA directly
+    auto is_pinned = [](const void* p) {
+        if (!p) return false;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool direct_bgra = is_pinned(bgra_out), direct_ids = is_pinned(ids_out);
+    const int chunks = (num_frames + chunk_frames - 1) / chunk_frames;
+    auto drain = [&](int k) -> int {  // staging -> caller memory for chunk k
+        const int slot = k & 1, f0 = k * chunk_frames, nf = std::min(chunk_frames, num_frames - f0);
+        RTB_CUDA(cudaEventSynchronize(cam->ev_copy[slot]));
+        if (bgra_out && !direct_bgra) std::memcpy(bgra_out + (size_t)f0 * P, cam->stage_bgra[slot], 4 * P * (size_t)nf);
+        if (ids_out && !direct_ids) std::memcpy(ids_out + (size_t)f0 * P, cam->stage_ids[slot], 4 * P * (size_t)nf);
+        return RTB_OK;
+    };
+    for (int k = 0; k < chunks; k++) {
+        const int slot = k & 1, f0 = k * chunk_frames, nf = std::min(chunk_frames, num_frames - f0);
+        if (k >= 2) {
+            // slot reuse: the device chunk must have been copied out, the staging chunk drained
+            rc = drain(k - 2);
+            if (rc) return rc;
+            RTB_CUDA(cudaStreamWaitEvent(cam->stream, cam->ev_copy[slot], 0));
+        }
+        rc = launch_render(obj, cam, obj->d_frames + 12 * (size_t)f0, nf, 0, 1, flags, bgra_out ? cam->ring_bgra[slot] : nullptr,
+                           ids_out ? cam->ring_ids[slot] : nullptr, cam->stream);
+        if (rc) return rc;
+        RTB_CUDA(cudaEventRecord(cam->ev_render[slot], cam->stream));
+        RTB_CUDA(cudaStreamWaitEvent(cam->copy_stream, cam->ev_render[slot], 0));
+        if (bgra_out)
+            RTB_CUDA(cudaMemcpyAsync(direct_bgra ? bgra_out + (size_t)f0 * P : cam->stage_bgra[slot], cam->ring_bgra[slot], 4 * P * (size_t)nf, cudaMemcpyDeviceToHost, cam->copy_stream));
+        if (ids_out)
+            RTB_CUDA(cudaMemcpyAsync(direct_ids ? ids_out + (size_t)f0 * P : cam->stage_ids[slot], cam->ring_ids[slot], 4 * P * (size_t)nf, cudaMemcpyDeviceToHost, cam->copy_stream));
+        RTB_CUDA(cudaEventRecord(cam->ev_copy[slot], cam->copy_stream));
+    }
+    for (int k = std::max(0, chunks - 2); k < chunks; k++) { rc = drain(k); if (rc) return rc; }
+    RTB_CUDA(cudaStreamSynchronize(cam->stream));
+    // keep the single-frame view coherent: last frame is also the camera's current frame
+    if (bgra_out) std::memcpy(cam->h_bgra, bgra_out + (size_t)(num_frames - 1) * P, 4 * P);
+    if (ids_out) std::memcpy(cam->h_ids, ids_out + (size_t)(num_frames - 1) * P, 4 * P);
+    return RTB_OK;
+}
+
+int rtb_device_props(int64_t out7[7]) {
+    if (!out7) return fail(RTB_ERR_ARG, "device_props: null argument");
+    cudaDeviceProp p;
+    RTB_CUDA(cudaGetDeviceProperties(&p, g_device));
+    int clock_khz = 0, mem_khz = 0;
+    cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, g_device);
+    cudaDeviceGetAttribute(&mem_khz, cudaDevAttrMemoryClockRate, g_device);
+    out7[0] = p.multiProcessorCount; out7[1] = p.l2CacheSize; out7[2] = p.persistingL2CacheMaxSize;
+    out7[3] = clock_khz; out7[4] = mem_khz; out7[5] = p.memoryBusWidth; out7[6] = p.major * 10 + p.minor;
+    return RTB_OK;
+}
+
+}  // extern "C"

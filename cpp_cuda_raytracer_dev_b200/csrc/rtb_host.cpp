@@ -1,0 +1,511 @@
+// rtb_host.cpp -- mesh load, tree build, camera basis, transform recurrence (host, fp32, no FMA).
+#include "rtb_host.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+
+namespace rtb {
+
+// =================================================================================================
+// PLY
+// =================================================================================================
+namespace {
+
+struct FileBytes {
+    std::vector<char> data;
+    bool read(const char* path) {
+        FILE* f = std::fopen(path, "rb");
+        if (!f) return false;
+        std::fseek(f, 0, SEEK_END);
+        long sz = std::ftell(f);
+        std::fseek(f, 0, SEEK_SET);
+        data.resize((size_t)sz + 1);
+        size_t got = std::fread(data.data(), 1, (size_t)sz, f);
+        std::fclose(f);
+        data[got] = 0;
+        data.resize(got + 1);
+        return got == (size_t)sz;
+    }
+};
+
+inline void emit_triangle(std::vector<float>& out, const float* a, const float* b, const float* c) {
+    out.insert(out.end(), a, a + 3);
+    out.insert(out.end(), b, b + 3);
+    out.insert(out.end(), c, c + 3);
+}
+
+// face rules of read_ply.cpp:70-149
+inline bool emit_face(std::vector<float>& out, const std::vector<float>& verts, int count, const long* idx) {
+    const long nv = (long)(verts.size() / 3);
+    for (int k = 0; k < count; k++)
+        if (idx[k] < 0 || idx[k] >= nv) return false;
+    const float* base = verts.data();
+    if (count == 3) {
+        emit_triangle(out, base + 3 * idx[2], base + 3 * idx[0], base + 3 * idx[1]);  // stored (c,a,b)
+    } else {
+        emit_triangle(out, base + 3 * idx[0], base + 3 * idx[1], base + 3 * idx[2]);  // (A,B,C)
+        emit_triangle(out, base + 3 * idx[0], base + 3 * idx[2], base + 3 * idx[3]);  // (A,C,D)
+    }
+    return true;
+}
+
+}  // namespace
+
+std::string load_ply(const char* path, int mode, std::vector<float>& points9) {
+    points9.clear();
+    if (mode < -1 || mode > 2) return "read_ply: unsupported mode (0, 1, 2 or -1)";
+    FileBytes fb;
+    if (!fb.read(path)) return std::string("read_ply: cannot read ") + path;
+    const char* p = fb.data.data();
+    const char* end = p + fb.data.size() - 1;
+    long num_vert = 0, num_face = 0;
+    int vertex_props = 0;
+    bool binary = false, in_vertex_element = false, header_done = false;
+    // header: only `element vertex|face <n>` matter to the reference (read_ply.cpp:19-44)
+    while (p < end) {
+        const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
+        const char* line_end = nl ? nl : end;
+        std::string line(p, line_end);
+        while (!line.empty() && (line.back() == '\r' || line.back() == ' ')) line.pop_back();
+        p = nl ? nl + 1 : end;
+        if (line == "end_header") { header_done = true; break; }
+        if (line.rfind("format binary_little_endian", 0) == 0) binary = true;
+        if (line.rfind("element vertex ", 0) == 0) { num_vert = std::atol(line.c_str() + 15); in_vertex_element = true; }
+        else if (line.rfind("element face ", 0) == 0) { num_face = std::atol(line.c_str() + 13); in_vertex_element = false; }
+        else if (line.rfind("element ", 0) == 0) in_vertex_element = false;
+        else if (in_vertex_element && line.rfind("property ", 0) == 0) vertex_props++;
+    }
+    if (!header_done) return "read_ply: no end_header";
+    if (num_vert <= 0 || num_face <= 0) return "read_ply: header has no vertex/face counts";
+    if (binary && mode != -1) return "read_ply: binary PLY needs mode -1 (the reference reader only parses text)";
+    std::vector<float> verts((size_t)num_vert * 3);
+    points9.reserve((size_t)num_face * 9);
+    if (binary) {
+        if (vertex_props < 3) return "read_ply: binary vertex element needs x,y,z";
+        const size_t stride = 4 * (size_t)vertex_props;
+        if ((size_t)(end - p) < stride * (size_t)num_vert) return "read_ply: truncated vertex data";
+        for (long i = 0; i < num_vert; i++, p += stride) std::memcpy(&verts[3 * (size_t)i], p, 12);
+        for (long f = 0; f < num_face; f++) {
+            if (p >= end) return "read_ply: truncated face data";
+            int count = (unsigned char)*p++;
+            if (count != 3 && count != 4) return "read_ply: only triangles and quads are supported";
+            if ((size_t)(end - p) < 4 * (size_t)count) return "read_ply: truncated face data";
+            uint32_t raw[4];
+            std::memcpy(raw, p, 4 * (size_t)count);
+            p += 4 * count;
+            long idx[4] = {(long)raw[0], (long)raw[1], (long)raw[2], count == 4 ? (long)raw[3] : 0};
+            if (!emit_face(points9, verts, count, idx)) return "read_ply: vertex index out of range";
+        }
+        return "";
+    }
+    const int columns = mode == 1 ? 5 : mode == 2 ? 6 : mode == -1 ? std::max(3, vertex_props) : 3;
+    char* cur = const_cast<char*>(p);
+    char* next = nullptr;
+    for (long i = 0; i < num_vert; i++) {
+        for (int c = 0; c < columns; c++) {
+            float v = std::strtof(cur, &next);  // `istream >> float`: one correctly rounded conversion
+            if (next == cur) return "read_ply: bad vertex record";
+            cur = next;
+            if (c < 3) verts[3 * (size_t)i + c] = v;
+        }
+    }
+    for (long f = 0; f < num_face; f++) {
+        long count = std::strtol(cur, &next, 10);
+        if (next == cur) return "read_ply: bad face record";
+        cur = next;
+        if (count != 3 && count != 4) return "read_ply: only triangles and quads are supported";
+        long idx[4] = {0, 0, 0, 0};
+        for (long k = 0; k < count; k++) {
+            idx[k] = std::strtol(cur, &next, 10);
+            if (next == cur) return "read_ply: bad face record";
+            cur = next;
+        }
+        if (!emit_face(points9, verts, (int)count, idx)) return "read_ply: vertex index out of range";
+    }
+    return "";
+}
+
+std::string save_ply(const char* path, const float* points9, uint32_t num_tri) {
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return std::string("write_ply: cannot open ") + path;
+    std::fprintf(f, "ply\nformat ascii 1.0\nelement vertex %u\nproperty float x\nproperty float y\nproperty float z\n"
+                    "element face %u\nproperty list uchar int vertex_indices\nend_header\n", num_tri * 3, num_tri);
+    for (uint64_t i = 0; i < (uint64_t)num_tri * 3; i++)
+        std::fprintf(f, "%.9g %.9g %.9g\n", points9[3 * i], points9[3 * i + 1], points9[3 * i + 2]);
+    // the loader stores face (a,b,c) as (c,a,b); writing (v1,v2,v0) restores (v0,v1,v2)
+    for (uint64_t t = 0; t < num_tri; t++)
+        std::fprintf(f, "3 %llu %llu %llu\n", (unsigned long long)(3 * t + 1), (unsigned long long)(3 * t + 2), (unsigned long long)(3 * t));
+    std::fclose(f);
+    return "";
+}
+
+// =================================================================================================
+// procedural stand-in mesh
+// =================================================================================================
+namespace {
+
+inline uint32_t hash3(int32_t x, int32_t y, int32_t z, uint32_t seed) {
+    uint32_t h = seed * 0x9E3779B1u;
+    h ^= (uint32_t)x * 0x85EBCA77u; h = (h << 13) | (h >> 19); h *= 0xC2B2AE3Du;
+    h ^= (uint32_t)y * 0x27D4EB2Fu; h = (h << 13) | (h >> 19); h *= 0x165667B1u;
+    h ^= (uint32_t)z * 0x9E3779B1u; h = (h << 13) | (h >> 19); h *= 0x85EBCA77u;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    return h;
+}
+// trilinear value noise in [-1,1]; only + - * floor, so it is reproducible everywhere
+inline double value_noise(double x, double y, double z, uint32_t seed) {
+    double fx = std::floor(x), fy = std::floor(y), fz = std::floor(z);
+    int32_t ix = (int32_t)fx, iy = (int32_t)fy, iz = (int32_t)fz;
+    double tx = x - fx, ty = y - fy, tz = z - fz;
+    tx = tx * tx * (3.0 - 2.0 * tx); ty = ty * ty * (3.0 - 2.0 * ty); tz = tz * tz * (3.0 - 2.0 * tz);
+    double acc = 0.0;
+    for (int c = 0; c < 8; c++) {
+        int dx = c & 1, dy = (c >> 1) & 1, dz = (c >> 2) & 1;
+        double wgt = (dx ? tx : 1.0 - tx) * (dy ? ty : 1.0 - ty) * (dz ? tz : 1.0 - tz);
+        double val = (double)(hash3(ix + dx, iy + dy, iz + dz, seed) >> 8) * (1.0 / 8388607.5) - 1.0;
+        acc += wgt * val;
+    }
+    return acc;
+}
+
+}  // namespace
+
+void make_geodesic(int nu, float radius, const float center[3], float displacement, uint32_t seed,
+                   std::vector<float>& points9) {
+    const double t = (1.0 + std::sqrt(5.0)) / 2.0;
+    const double ico[12][3] = {{-1, t, 0}, {1, t, 0}, {-1, -t, 0}, {1, -t, 0}, {0, -1, t}, {0, 1, t},
+                               {0, -1, -t}, {0, 1, -t}, {t, 0, -1}, {t, 0, 1}, {-t, 0, -1}, {-t, 0, 1}};
+    const int faces[20][3] = {{0, 11, 5}, {0, 5, 1}, {0, 1, 7}, {0, 7, 10}, {0, 10, 11}, {1, 5, 9}, {5, 11, 4},
+                              {11, 10, 2}, {10, 7, 6}, {7, 1, 8}, {3, 9, 4}, {3, 4, 2}, {3, 2, 6}, {3, 6, 8},
+                              {3, 8, 9}, {4, 9, 5}, {2, 4, 11}, {6, 2, 10}, {8, 6, 7}, {9, 8, 1}};
+    points9.assign((size_t)20 * nu * nu * 9, 0.0f);
+    auto vertex = [&](const int* f, int i, int j, float* out) {
+        const double a = (double)(nu - i - j) / nu, b = (double)i / nu, c = (double)j / nu;
+        double d[3];
+        for (int k = 0; k < 3; k++) d[k] = a * ico[f[0]][k] + b * ico[f[1]][k] + c * ico[f[2]][k];
+        const double inv = 1.0 / std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        for (int k = 0; k < 3; k++) d[k] *= inv;
+        // snap the direction so that a vertex shared by two faces is displaced identically
+        for (int k = 0; k < 3; k++) d[k] = std::floor(d[k] * 1048576.0 + 0.5) / 1048576.0;
+        const double nz = 0.65 * value_noise(d[0] * 3.0 + 7.3, d[1] * 3.0 + 1.9, d[2] * 3.0 + 4.1, seed) +
+                          0.35 * value_noise(d[0] * 11.0 + 0.5, d[1] * 11.0 + 8.2, d[2] * 11.0 + 2.7, seed ^ 0x5bd1e995u);
+        const double r = (double)radius * (1.0 + (double)displacement * nz);
+        for (int k = 0; k < 3; k++) out[k] = (float)((double)center[k] + r * d[k]);
+    };
+    size_t tri = 0;
+    for (int f = 0; f < 20; f++) {
+        for (int i = 0; i < nu; i++) {
+            for (int j = 0; i + j < nu; j++) {
+                float* o = &points9[9 * tri++];
+                vertex(faces[f], i, j, o); vertex(faces[f], i + 1, j, o + 3); vertex(faces[f], i, j + 1, o + 6);
+                if (i + j < nu - 1) {
+                    float* q = &points9[9 * tri++];
+                    vertex(faces[f], i + 1, j, q); vertex(faces[f], i + 1, j + 1, q + 3); vertex(faces[f], i, j + 1, q + 6);
+                }
+            }
+        }
+    }
+}
+
+// =================================================================================================
+// tree build
+// =================================================================================================
+namespace {
+
+inline float min3(float a, float b, float c) { float m = b < c ? b : c; return a < m ? a : m; }
+inline float max3(float a, float b, float c) { float m = b > c ? b : c; return a > m ? a : m; }
+
+template <class F>
+void parallel_for(int threads, int64_t count, int64_t grain, F&& body) {
+    if (threads <= 1 || count <= grain) {
+        for (int64_t i = 0; i < count; i++) body(i);
+        return;
+    }
+    std::atomic<int64_t> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            int64_t b = next.fetch_add(grain);
+            if (b >= count) return;
+            int64_t e = std::min(count, b + grain);
+            for (int64_t i = b; i < e; i++) body(i);
+        }
+    };
+    std::vector<std::thread> pool;
+    int nt = (int)std::min<int64_t>(threads, (count + grain - 1) / grain);
+    for (int t = 1; t < nt; t++) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+}
+
+// list numbering of the reference (Trixel.h:217-236): 0=x1 1=y1 2=z1 3=x0 4=y0 5=z0
+constexpr int kScanOrder[6] = {0, 3, 1, 4, 2, 5};  // Trixel.h:172-193
+
+}  // namespace
+
+void build_tree(const float* points9, int64_t n, HostTree& T, int threads) {
+    using clock = std::chrono::steady_clock;
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    const auto t_begin = clock::now();
+    const int64_t N = 2 * n - 1;
+    T.num_tri = n; T.num_nodes = N;
+    T.bounds.assign((size_t)N * 6, 0.0f);
+    T.left.assign((size_t)N, -1);
+    T.tri.assign((size_t)N, -1);
+    T.cut_flag.assign((size_t)N, 0);
+    T.s1.assign((size_t)N, 0.0f);
+    T.s2.assign((size_t)N, 0.0f);
+
+    // per-triangle AABB keys (read_ply.cpp:127-134)
+    std::vector<float> key[6];
+    std::vector<int32_t> order[6], rank[6], scratch[6];
+    for (int k = 0; k < 6; k++) { key[k].resize((size_t)n); order[k].resize((size_t)n); rank[k].resize((size_t)n); scratch[k].resize((size_t)n); }
+    parallel_for(threads, n, 1 << 16, [&](int64_t i) {
+        const float* p = points9 + 9 * i;
+        key[0][i] = max3(p[0], p[3], p[6]); key[3][i] = min3(p[0], p[3], p[6]);
+        key[1][i] = max3(p[1], p[4], p[7]); key[4][i] = min3(p[1], p[4], p[7]);
+        key[2][i] = max3(p[2], p[5], p[8]); key[5][i] = min3(p[2], p[5], p[8]);
+    });
+    // six sorted lists.  The reference's top-down merge takes the right run on ties (sort.h:31-54),
+    // i.e. equal keys end up ordered by DESCENDING original index.
+    parallel_for(std::min(threads, 6), 6, 1, [&](int64_t k) {
+        auto& ord = order[k];
+        const float* ky = key[k].data();
+        for (int64_t i = 0; i < n; i++) ord[(size_t)i] = (int32_t)i;
+        std::sort(ord.begin(), ord.end(), [ky](int32_t a, int32_t b) {
+            const float ka = ky[a], kb = ky[b];
+            return ka < kb || (!(kb < ka) && a > b);
+        });
+        auto& rk = rank[k];
+        for (int64_t i = 0; i < n; i++) rk[(size_t)ord[(size_t)i]] = (int32_t)i;
+    });
+    const auto t_sorted = clock::now();
+
+    // level-synchronous partition.  BFS numbering: the children of the interior nodes of one level,
+    // taken in node order, are the consecutive nodes of the next level (Trixel.h:143,329-352).
+    std::vector<int64_t> lo((size_t)N), hi((size_t)N);
+    std::vector<int32_t> parent((size_t)N, 0);
+    lo[0] = 0; hi[0] = n - 1;
+    auto set_bounds = [&](int64_t node, int64_t a, int64_t b) {
+        float* B = &T.bounds[(size_t)node * 6];
+        B[0] = key[3][order[3][a]]; B[1] = key[0][order[0][b]];
+        B[2] = key[4][order[4][a]]; B[3] = key[1][order[1][b]];
+        B[4] = key[5][order[5][a]]; B[5] = key[2][order[2][b]];
+    };
+    set_bounds(0, 0, n - 1);
+    T.cut_flag[0] = 5;  // Trixel.h:152 (only visible if the root is itself a leaf)
+    int64_t level_begin = 0, level_end = 1;
+    std::vector<int64_t> child_base;
+    while (level_begin < level_end) {
+        const int64_t count = level_end - level_begin;
+        child_base.assign((size_t)count + 1, 0);
+        // choose the split list of every node of this level
+        parallel_for(threads, count, 4096, [&](int64_t q) {
+            const int64_t node = level_begin + q, l = lo[node], r = hi[node];
+            if (r == l) {
+                T.cut_flag[node] = T.cut_flag[parent[node]];  // Trixel.h:194
+                T.tri[node] = order[0][l];                    // Trixel.h:202
+                child_base[(size_t)q + 1] = 0;
+                return;
+            }
+            float best = key[0][order[0][r]] - key[0][order[0][l]];
+            int cut = 0;
+            for (int s = 1; s < 6; s++) {
+                const int k = kScanOrder[s];
+                const float spread = key[k][order[k][r]] - key[k][order[k][l]];
+                if (spread > best) { best = spread; cut = k; }
+            }
+            T.cut_flag[node] = (uint8_t)cut;
+            child_base[(size_t)q + 1] = 2;
+        });
+        for (int64_t q = 0; q < count; q++) child_base[(size_t)q + 1] += child_base[(size_t)q];
+        const int64_t next_begin = level_end, next_end = level_end + child_base[(size_t)count];
+        // stable partition of the five other lists of every interior node (Trixel.h:214-327);
+        // task = (node, list), ranges of different nodes are disjoint
+        parallel_for(threads, count * 6, 64, [&](int64_t task) {
+            const int64_t q = task / 6, node = level_begin + q;
+            const int k = (int)(task % 6);
+            const int64_t l = lo[node], r = hi[node];
+            if (r == l) return;
+            const int cut = T.cut_flag[node];
+            if (k == cut) return;
+            const int64_t m = l + (r - l) / 2;
+            const int32_t* cut_rank = rank[cut].data();
+            int32_t* ord = order[k].data();
+            int32_t* tmp = scratch[k].data();
+            int64_t a = l, b = m + 1;
+            for (int64_t i = l; i <= r; i++) {
+                const int32_t t = ord[i];
+                if (cut_rank[t] <= m) tmp[a++] = t; else tmp[b++] = t;
+            }
+            int32_t* rk = rank[k].data();
+            for (int64_t i = l; i <= r; i++) { ord[i] = tmp[i]; rk[tmp[i]] = (int32_t)i; }
+        });
+        // create the children
+        parallel_for(threads, count, 4096, [&](int64_t q) {
+            const int64_t node = level_begin + q, l = lo[node], r = hi[node];
+            if (r == l) return;
+            const int64_t m = l + (r - l) / 2;
+            const int64_t cl = next_begin + child_base[(size_t)q], cr = cl + 1;
+            T.left[node] = (int32_t)cl;
+            lo[cl] = l; hi[cl] = m; parent[cl] = (int32_t)node;
+            lo[cr] = m + 1; hi[cr] = r; parent[cr] = (int32_t)node;
+            set_bounds(cl, l, m);
+            set_bounds(cr, m + 1, r);
+            const int axis = T.cut_flag[node] % 3;  // Trixel.h:353-376
+            T.s1[node] = T.bounds[(size_t)cl * 6 + 2 * axis + 1];
+            T.s2[node] = T.bounds[(size_t)cr * 6 + 2 * axis];
+        });
+        level_begin = next_begin;
+        level_end = next_end;
+    }
+    const auto t_done = clock::now();
+    T.seconds_sort = std::chrono::duration<double>(t_sorted - t_begin).count();
+    T.seconds_partition = std::chrono::duration<double>(t_done - t_sorted).count();
+}
+
+// =================================================================================================
+// camera basis
+// =================================================================================================
+namespace {
+
+// vector.cpp:13-26 (host rsqrt: magic constant + 8 Newton steps, 32-bit integer view)
+inline float host_rsqrt(float s) {
+    const float half = 0.5f * s;
+    int32_t bits;
+    std::memcpy(&bits, &half, 4);
+    bits = 0x5f375a86 - (bits >> 1);
+    float g;
+    std::memcpy(&g, &bits, 4);
+    for (int it = 0; it < 8; it++) g = g * (1.5f - half * g * g);
+    return g;
+}
+// Vector.h:116-124
+inline void normalize(Vec4& v) {
+    float s = v.x * v.x + v.y * v.y + v.z * v.z;
+    s = host_rsqrt(s);
+    v.x *= s; v.y *= s; v.z *= s;
+    v.w = 1 / s;
+}
+// vector.cpp:31-36
+inline Vec4 cross(const Vec4& a, const Vec4& b) {
+    Vec4 r = a;
+    r.x = a.y * b.z - a.z * b.y;
+    r.y = a.z * b.x - a.x * b.z;
+    r.z = a.x * b.y - a.y * b.x;
+    return r;
+}
+
+}  // namespace
+
+void camera_basis(int32_t W, int32_t H, float f_w, float f_h, float fclen, const float pos[3], const float la[3],
+                  const float up[3], CameraBasis& c) {
+    c.W = W; c.H = H;
+    std::memcpy(c.pos, pos, 12);
+    const float pix_w = f_w / (float)W, pix_h = f_h / (float)H;  // Camera.cpp:16-17
+    Vec4 n{la[0] - pos[0], la[1] - pos[1], la[2] - pos[2], 1.0f};
+    normalize(n);
+    Vec4 upv{up[0], up[1], up[2], 1.0f};
+    normalize(upv);
+    Vec4 v = cross(n, cross(upv, n));  // Camera.cpp:38-39: up x n, then n x (up x n)
+    normalize(v);
+    Vec4 u = cross(v, n);  // Camera.cpp:52
+    c.n[0] = n.x; c.n[1] = n.y; c.n[2] = n.z;
+    c.v[0] = v.x; c.v[1] = v.y; c.v[2] = v.z;
+    c.u[0] = u.x; c.u[1] = u.y; c.u[2] = u.z;
+    float ay = (float)((uint32_t)H >> 1), ax = (float)((uint32_t)W >> 1);  // Camera.cpp:61-63
+    if (!(H & 1)) ay -= 0.5f;
+    if (!(W & 1)) ax -= 0.5f;
+    for (int k = 0; k < 3; k++) {
+        c.v_mod[k] = c.v[k] * pix_h;
+        c.u_mod[k] = c.u[k] * pix_w;
+        c.n_mod[k] = (c.n[k] * fclen) - (c.v_mod[k] * ay) - (c.u_mod[k] * ax);  // Camera.cpp:65-67
+    }
+}
+
+// =================================================================================================
+// transform recurrence
+// =================================================================================================
+void Transform::reset(const float cam_pos[3]) {
+    quat = Vec4{0, 0, 0, 1};  // Quaternion.cpp:10
+    row[0] = Vec4{1, 0, 0, 0}; row[1] = Vec4{0, 1, 0, 0}; row[2] = Vec4{0, 0, 1, 0};
+    init_face = Vec4{-cam_pos[0], -cam_pos[1], -cam_pos[2], 1.0f};  // Camera.cpp:131-132
+    cur_face = init_face;
+}
+
+namespace {
+
+// quaternion accumulate + matrix, vector.cpp:40-58
+inline void accumulate(Transform& T, const Vec4& s) {
+    const float a = T.quat.x, b = T.quat.y, c = T.quat.z, d = T.quat.w;
+    T.quat.x = b * s.z - c * s.y + a * s.w + d * s.x;
+    T.quat.y = c * s.x - a * s.z + b * s.w + d * s.y;
+    T.quat.z = a * s.y - b * s.x + c * s.w + d * s.z;
+    T.quat.w = d * s.w - a * s.x - b * s.y - c * s.z;
+    const float i = T.quat.x, j = T.quat.y, k = T.quat.z, w = T.quat.w;
+    T.row[0].x = 1 - 2 * j * j - 2 * k * k; T.row[0].y = 2 * i * j - 2 * k * w; T.row[0].z = 2 * i * k + 2 * j * w;
+    T.row[1].x = 2 * i * j + 2 * k * w; T.row[1].y = 1 - 2 * i * i - 2 * k * k; T.row[1].z = 2 * j * k - 2 * i * w;
+    T.row[2].x = 2 * i * k - 2 * j * w; T.row[2].y = 2 * j * k + 2 * i * w; T.row[2].z = 1 - 2 * i * i - 2 * j * j;
+}
+// vector.cpp:60-64 with reverse = -1
+inline void rotate_reversed(const Transform& T, Vec4& v) {
+    const float tx = v.x * -1, ty = v.y * -1, tz = v.z * -1;
+    v.x = tx * T.row[0].x + ty * T.row[0].y + tz * T.row[0].z;
+    v.y = tx * T.row[1].x + ty * T.row[1].y + tz * T.row[1].z;
+    v.z = tx * T.row[2].x + ty * T.row[2].y + tz * T.row[2].z;
+}
+// Vector.h:89-100: both operands are scaled by their own w first
+inline void sub_scaled(Vec4& a, const Vec4& b) {
+    a.x = (a.x * a.w) - (b.x * b.w); a.y = (a.y * a.w) - (b.y * b.w); a.z = (a.z * a.w) - (b.z * b.w); a.w = 1.0f;
+}
+inline void add_scaled(Vec4& a, const Vec4& b) {
+    a.x = (a.x * a.w) + (b.x * b.w); a.y = (a.y * a.w) + (b.y * b.w); a.z = (a.z * a.w) + (b.z * b.w); a.w = 1.0f;
+}
+inline void negate(Vec4& v) { v.x = -v.x; v.y = -v.y; v.z = -v.z; }
+
+}  // namespace
+
+bool Transform::apply(uint8_t select, float x, float y, float z, float w) {
+    Vec4 in{x, y, z, w};
+    if (select == 30 || select == 31 || select == 32) {  // Camera.cu:257-287
+        sub_scaled(init_face, in);
+        rotate_reversed(*this, in);
+        row[0].w += in.w * in.x;
+        row[1].w += in.w * in.y;
+        row[2].w += in.w * in.z;
+        normalize(init_face);
+        cur_face = init_face;
+        rotate_reversed(*this, cur_face);
+        negate(cur_face);
+        return true;
+    }
+    if (select == 10 || select == 11) {  // Camera.cu:288-329
+        Vec4 probe = init_face;
+        accumulate(*this, in);
+        rotate_reversed(*this, probe);
+        add_scaled(probe, cur_face);
+        row[0].w -= probe.x * probe.w;
+        row[1].w -= probe.y * probe.w;
+        row[2].w -= probe.z * probe.w;
+        sub_scaled(probe, cur_face);
+        cur_face = probe;
+        normalize(cur_face);
+        negate(cur_face);
+        return true;
+    }
+    return false;
+}
+
+void Transform::matrix(float m[12]) const {
+    for (int r = 0; r < 3; r++) { m[4 * r] = row[r].x; m[4 * r + 1] = row[r].y; m[4 * r + 2] = row[r].z; m[4 * r + 3] = row[r].w; }
+}
+void Transform::set_matrix(const float m[12]) {
+    for (int r = 0; r < 3; r++) { row[r].x = m[4 * r]; row[r].y = m[4 * r + 1]; row[r].z = m[4 * r + 2]; row[r].w = m[4 * r + 3]; }
+}
+
+}  // namespace rtb

@@ -1,0 +1,63 @@
+// rtb_host.hpp -- host-side operator surface of the ray-cast path (no CUDA in this header).
+//
+// Mesh load, the n log n tree build, the camera basis and the object transform recurrence: the
+// pieces of the reference that run on the host and feed the per-pixel kernels.  Everything here is
+// fp32 with contraction off (the file is compiled with -ffp-contract=off) so that the values handed
+// to the GPU are bit-identical to the reference's.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace rtb {
+
+struct Vec4 {
+    float x = 0, y = 0, z = 0, w = 0;
+};
+
+// ---- mesh input (read_ply.cpp:13-152) --------------------------------------------------------
+// Returns an empty string on success, otherwise the error text.  points9: 9 floats per triangle.
+std::string load_ply(const char* path, int mode, std::vector<float>& points9);
+std::string save_ply(const char* path, const float* points9, uint32_t num_tri);
+void make_geodesic(int nu, float radius, const float center[3], float displacement, uint32_t seed,
+                   std::vector<float>& points9);
+
+// ---- tree (sort.h:11-60, Trixel.h:135-473) ---------------------------------------------------
+// Struct-of-arrays form of Trixel::kd_tree::kd_tree_node (Trixel.h:68-79), 2n-1 nodes, BFS order,
+// right child = left child + 1.
+struct HostTree {
+    int64_t num_tri = 0, num_nodes = 0;
+    std::vector<float> bounds;     // 6 per node: x0,x1,y0,y1,z0,z1 (kd_leaf order, Trixel.h:31-37)
+    std::vector<int32_t> left;     // -1 for leaves
+    std::vector<int32_t> tri;      // leaf triangle, -1 for interior nodes
+    std::vector<uint8_t> cut_flag; // 0=x1 1=y1 2=z1 3=x0 4=y0 5=z0 (list that was split); leaves inherit
+    std::vector<float> s1, s2;     // left child's max / right child's min on the split axis
+    double seconds_sort = 0, seconds_partition = 0;
+};
+// threads <= 0: use all hardware threads
+void build_tree(const float* points9, int64_t num_tri, HostTree& out, int threads = 0);
+
+// ---- camera (Camera.cpp:5-67) ----------------------------------------------------------------
+struct CameraBasis {
+    int32_t W = 0, H = 0;
+    float pos[3], n[3], v[3], u[3], n_mod[3], v_mod[3], u_mod[3];
+    float draw_distance = 400.0f;           // Camera.cpp:70
+    uint8_t background[4] = {240, 130, 0, 0}; // r,g,b,a  Camera.cpp:72
+};
+void camera_basis(int32_t W, int32_t H, float f_w, float f_h, float fclen, const float pos[3], const float la[3],
+                  const float up[3], CameraBasis& out);
+
+// ---- object transform (Quaternion.cpp, vector.cpp:38-65, Camera.cu:254-335) -------------------
+struct Transform {
+    Vec4 quat;       // Quaternion::vec, never renormalised
+    Vec4 row[3];     // Quaternion::rot_m x,y,z; .w = translation column
+    Vec4 init_face;  // Object::init_face (Camera.cpp:131)
+    Vec4 cur_face;   // Object::cur_face  (Camera.cpp:132)
+    void reset(const float cam_pos[3]);
+    // select: 10/11 rotate by step quaternion (x,y,z,w); 30/31/32 translate along (x,y,z) by w
+    bool apply(uint8_t select, float x, float y, float z, float w);
+    void matrix(float m12[12]) const;
+    void set_matrix(const float m12[12]);
+};
+
+}  // namespace rtb

@@ -1,0 +1,190 @@
+/* rtb.h -- C ABI of the B200-native ray-cast path (librtb.so).
+ *
+ * Drop-in boundary for the per-pixel ray-cast hot path of ams3878/cpp_cuda_raytracer_dev
+ * (primary-ray generation -> tree traversal -> Moller-Trumbore -> Phong -> framebuffer) and the
+ * operator surface that feeds it (read_ply, the n log n tree build, the camera/quaternion
+ * transform API, render-frame-to-buffer).  The reference's own host<->CUDA seam is seven free
+ * functions plus two Quaternion methods that take pointers to C++ objects and read their fields
+ * (C linkage, not C layout).  This header exports the same operations over
+ * opaque handles with plain pointers and sizes.  Every entry point cites the reference interface
+ * (file:line under TEST_Dungeonrun/) it replaces.
+ *
+ * Conventions kept from the reference: every call returns a status code and never throws
+ * (0 = success, otherwise an rtb_status; rtb_last_error() gives the text that the reference
+ * would have printf'd); caller-owned inputs are copied; rendered frames live in LIBRARY-OWNED
+ * pinned host buffers that stay valid until the next render on the same camera
+ * (Camera::h_mem.h_color.c, Camera.cpp:79); one host thread per handle, calls are synchronous
+ * unless the name says _async.  Unlike the reference every handle has an explicit destroy.
+ *
+ * There is no CPU fallback: every call that needs the GPU fails with RTB_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef RTB_H
+#define RTB_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rtb_mesh rtb_mesh;     /* = class Trixel   (Trixel.h:39)  : triangles + tree      */
+typedef struct rtb_camera rtb_camera; /* = class Camera   (Camera.h:15)  : film, rays, frame      */
+typedef struct rtb_object rtb_object; /* = class Object   (Object.h:6)   : mesh instance + its
+                                         Quaternion (Quaternion.h:5) and the per-(camera, mesh)
+                                         device arrays Camera::trixel_memory / voxel_memory      */
+
+typedef enum {
+    RTB_OK = 0,
+    RTB_ERR_ARG = 1,    /* bad argument / handle state */
+    RTB_ERR_IO = 2,     /* file could not be read or parsed */
+    RTB_ERR_CUDA = 3,   /* CUDA runtime error, or no usable device */
+    RTB_ERR_NOMEM = 4,
+    RTB_ERR_STATE = 5   /* call order violated (e.g. render before build_tree / add_object) */
+} rtb_status;
+
+/* selectors, same values as the reference */
+#define RTB_SET_COLOR_TAG 1   /* Camera.h:13 */
+#define RTB_PHONG_COLOR_TAG 2 /* Camera.h:14 */
+#define RTB_TRANSLATE_XYZ 30  /* platform_common.h:16 */
+#define RTB_TRANSLATE_X 31    /* platform_common.h:17 */
+#define RTB_TRANSLATE_Z 32    /* platform_common.h:18 */
+#define RTB_ROTATE_TRI_PY 10  /* platform_common.h:20 */
+#define RTB_ROTATE_TRI_NY 11  /* platform_common.h:21 */
+
+/* render flags */
+#define RTB_RENDER_DEFAULT 0u
+#define RTB_RENDER_NO_CULL 1u   /* visit exactly the node sequence of Trixel.cu:70-170 (no distance culling) */
+#define RTB_RENDER_COUNTERS 2u  /* accumulate per-launch work counters (rtb_camera_counters) */
+
+const char* rtb_last_error(void);
+const char* rtb_version(void);
+/* number of CUDA devices visible / select the device used by handles created afterwards on this
+ * thread.  Replaces the hard-coded cudaSetDevice(0) of Trixel.cu:213,247,269, Camera.cu:73,115,166. */
+int rtb_device_count(void);
+int rtb_set_device(int device);
+
+/* ---- mesh input -------------------------------------------------------------------------- */
+
+/* read_ply (read_ply.cpp:13): ASCII PLY subset; mode 0/1/2 = 3/5/6 numbers per vertex
+ * (read_ply.cpp:52-65); "3 a b c" faces are stored (c,a,b), "4 a b c d" faces become (a,b,c),(a,c,d).
+ * mode -1 (extension) additionally accepts `format binary_little_endian` files such as the
+ * reference's 3_walls.ply, applying the same face rules.  *points9 (9 floats per triangle, malloc'd,
+ * release with rtb_free) and *num_tri are outputs; per-triangle AABBs (the reference's kd_leaf_sort
+ * list) are derived inside rtb_mesh_create. */
+int rtb_read_ply(const char* file_name, int mode, float** points9, uint32_t* num_tri);
+void rtb_free(void* p);
+/* utility (not in the reference): write a triangle soup as an ASCII PLY that rtb_read_ply(mode 0)
+ * and the reference loader read back to the same triangles (faces are written rotated so that the
+ * loader's (c,a,b) storage restores the input order). */
+int rtb_write_ply(const char* file_name, const float* points9, uint32_t num_tri);
+/* utility (not in the reference): displaced geodesic icosphere with 20*nu*nu triangles, the
+ * labelled stand-in for the Stanford meshes that are absent from the reference checkout
+ *  and the synthetic 10M-triangle mesh of BASELINE.json configs[4]. */
+int rtb_mesh_geodesic(int nu, float radius, const float center[3], float displacement, uint32_t seed,
+                      float** points9, uint32_t* num_tri);
+
+/* ---- mesh + tree ------------------------------------------------------------------------- */
+
+/* Trixel::Trixel(num_t, points_data, color_data) + init_trixels_device_memory (Trixel.h:87,
+ * Trixel.cu:266).  rad3 = per-triangle radiance r,g,b (3 floats each, Color::radiance) or NULL
+ * with uniform_rgb (the reference app uses (.1,.55,.2) for all, WinMain.cpp:118-120). */
+int rtb_mesh_create(const float* points9, int64_t num_tri, const float* rad3, const float uniform_rgb[3], rtb_mesh** out);
+/* Trixel::set_sorted_voxels + Trixel::create_kd (Trixel.h:386, Trixel.h:135; sort.h:11): six sorted
+ * AABB lists, object-median split, BFS numbering, 2n-1 nodes.  Same tree as the reference, bit for bit. */
+int rtb_mesh_build_tree(rtb_mesh* mesh);
+int64_t rtb_mesh_num_triangles(const rtb_mesh* mesh);
+int64_t rtb_mesh_num_nodes(const rtb_mesh* mesh); /* Trixel::num_voxels */
+/* copy the host tree out in the reference's kd_tree_node terms (Trixel.h:68-79): per node
+ * left, right (-1 for leaves), tri (leaf triangle or -1), cut_flag (0..5), bounds x0,x1,y0,y1,z0,z1, s1, s2.
+ * Any output pointer may be NULL. */
+int rtb_mesh_get_tree(const rtb_mesh* mesh, int32_t* left, int32_t* right, int32_t* tri, int32_t* cut_flag,
+                      float* bounds6, float* s1, float* s2);
+/* seconds spent in the last rtb_mesh_build_tree: [0] sort, [1] partition, [2] total */
+int rtb_mesh_build_seconds(const rtb_mesh* mesh, double out3[3]);
+void rtb_mesh_destroy(rtb_mesh* mesh);
+
+/* ---- camera ------------------------------------------------------------------------------ */
+
+/* Camera::Camera(r_w, r_h, f_w, f_h, fclen, pos, look-at, up) + init_camera_device_memory
+ * (Camera.h:86, Camera.cpp:5, Camera.cu:112).  The per-pixel ray table of init_cam_mem_cuda is not
+ * materialised: rays are regenerated per pixel with the same arithmetic. */
+int rtb_camera_create(int32_t r_w, int32_t r_h, float f_w, float f_h, float fclen, const float pos[3],
+                      const float look_at[3], const float up[3], rtb_camera** out);
+/* n, v, u, n_mod, v_mod, u_mod (Camera::orientation_properties, Camera.h:32-42), 18 floats */
+int rtb_camera_get_basis(const rtb_camera* cam, float out18[18]);
+/* Camera::add_object (Camera.cpp:118): binds the object's mesh to this camera and builds the
+ * camera-relative device arrays (init_camera_trixel_device_memory Trixel.cu:244,
+ * init_camera_voxel_device_memory Camera.cu:163).  Requires rtb_mesh_build_tree. */
+int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj);
+/* Camera::color_pixels(tag) -> color_camera_device (Camera.cpp:229, Camera.cu:70):
+ * PHONG: bring the shaded frame of the last render to the host buffer; SET: fill the frame with
+ * the background colour (240,130,0) (Camera.cpp:72, Camera.cu:12-18) and copy it. */
+int rtb_camera_color_pixels(rtb_camera* cam, uint8_t color_tag_select);
+/* Camera::h_mem.h_color.c (Camera.cpp:79): W*H little-endian 0x00RRGGBB words, row 0 = bottom.
+ * Library-owned pinned memory, valid until the next render / color_pixels on this camera. */
+const uint32_t* rtb_camera_host_color(const rtb_camera* cam);
+/* hit triangle id per pixel (-1 = miss): the reference keeps these in Camera::pixel_memory::d_rmi
+ * (Camera.h:57) and never reads them back; here they come with every frame. */
+const int32_t* rtb_camera_host_ids(const rtb_camera* cam);
+/* work counters of renders issued with RTB_RENDER_COUNTERS since the last reset:
+ * [0] rays, [1] interior nodes entered (64-byte record fetches), [2] nodes popped in the reference's
+ * sense (root + every child the parent scheduled), [3] triangle tests, [4] hits */
+int rtb_camera_counters(rtb_camera* cam, uint64_t out5[5], int reset);
+void rtb_camera_destroy(rtb_camera* cam);
+
+/* ---- object + transform ------------------------------------------------------------------ */
+
+/* Object::Object(Trixel*) (Object.cpp:4) */
+int rtb_object_create(rtb_mesh* mesh, rtb_object** out);
+/* Input::set_quat(x,y,z,w) + Object::transform(input, select) -> transform_camera_voxel_device_memory
+ * (Input.cpp:15, Object.cpp:14, Camera.cu:254) incl. Quaternion::set_device_rotation (Quaternion.cu:21)
+ * and update_voxel_transform_m_translate_cuda (Camera.cu:188).  ROTATE_TRI_*: xyzw = step quaternion;
+ * TRANSLATE_*: xyz = direction, w = distance.  Requires rtb_camera_add_object. */
+int rtb_object_transform(rtb_object* obj, const float xyzw[4], uint8_t transform_select);
+/* the object's 3x4 matrix: rows x,y,z of Quaternion::rot_m, each (i,j,k,w=translation) */
+int rtb_object_get_matrix(const rtb_object* obj, float m12[12]);
+int rtb_object_set_matrix(rtb_object* obj, const float m12[12]);
+void rtb_object_destroy(rtb_object* obj);
+
+/* ---- render ------------------------------------------------------------------------------ */
+
+/* Object::render(Camera*) -> Trixel::intersect_trixels -> intersect_trixels_device
+ * (Object.cpp:10, Trixel.h:474, Trixel.cu:210).  One fused launch: ray generation, traversal,
+ * Moller-Trumbore, Phong and background into the camera's device frame; follow with
+ * rtb_camera_color_pixels(PHONG) to obtain it on the host, exactly like the reference's frame loop
+ * (WinMain.cpp:212-213). */
+int rtb_object_render(rtb_object* obj, rtb_camera* cam, uint32_t flags);
+/* = rtb_object_render + rtb_camera_color_pixels(PHONG) with one synchronisation; the frame and the
+ * id buffer are then readable through rtb_camera_host_color / rtb_camera_host_ids. */
+int rtb_render_frame(rtb_object* obj, rtb_camera* cam, uint32_t flags);
+
+/* Batched animation sweep (WinMain.cpp:174-239 with a key held down): for frame k = 0..num_frames-1
+ * apply `steps_per_frame` transforms ops[k*steps_per_frame ...] (each 5 floats: select, x, y, z, w;
+ * select 0 = no-op) and render.  All frames go through ONE persistent launch; finished frames
+ * stream to the host while later ones render.  bgra_out / ids_out are caller buffers of
+ * num_frames*W*H elements (pageable or pinned; either may be NULL) -- the only interface here that
+ * writes into caller memory.  The object's transform state advances as if the calls had been made
+ * one by one. */
+int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32_t steps_per_frame,
+                     const float* ops5, uint32_t flags, uint32_t* bgra_out, int32_t* ids_out);
+
+/* Device-resident variant for callers that own device memory and a stream (multi-GPU gather,
+ * kernel-only timing): renders frames m12[f] (12 floats each), f in [0,num_frames), restricted to
+ * image tiles t with t % tile_stride == tile_first (tiles are 32x32 pixels, row-major over the
+ * image; stride 1 = whole frame).  Output is written at its final row-major position in
+ * d_bgra/d_ids (num_frames*W*H elements each, device pointers; either may be NULL).  `stream` is a
+ * cudaStream_t (NULL = the library's own stream; pass cudaStreamLegacy for the default stream).  Asynchronous with respect to the host. */
+int rtb_render_frames_device_async(rtb_object* obj, rtb_camera* cam, int32_t num_frames, const float* m12,
+                                   int32_t tile_first, int32_t tile_stride, uint32_t flags, uint32_t* d_bgra,
+                                   int32_t* d_ids, void* stream);
+/* host-side transform recurrence only (no GPU): advance `obj` by one op and return its matrix;
+ * lets callers precompute the m12 array for rtb_render_frames_device_async. */
+int rtb_object_transform_host(rtb_object* obj, const float xyzw[4], uint8_t transform_select, float m12_out[12]);
+
+/* device properties the roofline uses: [0] SM count, [1] L2 bytes, [2] max persisting L2 bytes,
+ * [3] SM clock kHz, [4] memory clock kHz, [5] memory bus width bits, [6] compute capability*10 */
+int rtb_device_props(int64_t out7[7]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB_H */

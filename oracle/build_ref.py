@@ -109,16 +109,30 @@ def build(force=False):
     deps = [os.path.join(REF, n) for n in ORDER + ["Vector.h"]] + [os.path.join(HERE, "ref_driver.cpp"), __file__,
                                                                   os.path.join(HERE, "shim", "cuda_runtime.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
+        copy_assets()
         return OUT
     unit = [patched("Vector.h")] + [patched(n) for n in ORDER]
     with open(os.path.join(HERE, "ref_driver.cpp")) as f:
         unit.append('#line 1 "%s"\n%s\n' % (os.path.join(HERE, "ref_driver.cpp"), f.read()))
-    cmd = ["g++", "-x", "c++", "-", "-std=c++17", "-O2", "-ffp-contract=off", "-fpermissive", "-w", "-fopenmp", "-fPIC",
+    cmd = ["/usr/bin/g++", "-x", "c++", "-", "-std=c++17", "-O2", "-ffp-contract=off", "-fpermissive", "-w", "-fopenmp", "-fPIC",
            "-shared", "-I", os.path.join(HERE, "shim"), "-I", REF, "-o", OUT]
     r = subprocess.run(cmd, input="".join(unit).encode(), cwd=OUT_DIR)
     if r.returncode != 0:
         raise RuntimeError("reference emulation build failed")
+    copy_assets()
     return OUT
+
+
+def copy_assets():
+    """The reference's two loadable meshes travel to the GPU box as git-ignored build outputs
+    (oracle/_ref/data/): they are inputs of the parity tests, not product source."""
+    import shutil
+    dst = os.path.join(OUT_DIR, "data")
+    os.makedirs(dst, exist_ok=True)
+    for name in ("rabbit_70k.ply", "3_walls.ply"):
+        src = os.path.join(REF, name)
+        if os.path.exists(src) and not os.path.exists(os.path.join(dst, name)):
+            shutil.copyfile(src, os.path.join(dst, name))
 
 
 if __name__ == "__main__":

@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+@pytest.fixture(scope="session")
+def rtb():
+    import cpp_cuda_raytracer_dev_b200 as m
+    return m
+
+
+@pytest.fixture(scope="session")
+def orc():
+    from oracle import orc as m
+    m.build()
+    return m

@@ -1,0 +1,202 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north star): hit ids bit-exact except documented edge/tie pixels
+(<= 1e-4 of the pixels; in practice 0 here), colour within 1/255 per channel.
+"""
+import numpy as np
+import pytest
+
+from common import WALLS_CAMERA, cam12, cam_kwargs, channel_diff, golden, mesh_path
+
+pytestmark = pytest.mark.gpu
+
+ID_MISMATCH_BUDGET = 1e-4   # fraction of pixels, BASELINE.json north star
+COLOUR_TOL = 1              # 1/255 per channel, BASELINE.json north star
+
+
+class Pair:
+    """The same scene on the CUDA path and in the oracle."""
+
+    def __init__(self, rtb, orc, pts, W, H, cam=None, colors=None):
+        cam = cam or {}
+        self.rtb, self.W, self.H = rtb, W, H
+        self.mesh = rtb.Trixel(pts, colors=colors)
+        self.mesh.create_kd()
+        self.cam = rtb.Camera(W, H, **cam_kwargs(W, H, **cam))
+        self.obj = rtb.Object(self.mesh)
+        self.cam.add_object(self.obj)
+        self.ref = orc.Scene(pts, W, H, cam12(W, H, **cam), rgb=colors if colors is not None else orc.DEFAULT_RGB)
+
+    def transform(self, select, q):
+        self.obj.transform(q, select)
+        self.ref.transform(select, *q)
+
+    def check(self, flags=0, exact=True):
+        ids, bgra = self.obj.render_frame(self.cam, flags)
+        oids, obgra = self.ref.render()
+        bad = int((ids.astype(np.int64) != oids).sum())
+        if exact:
+            assert bad == 0, "%d of %d hit ids differ" % (bad, ids.size)
+        assert bad <= ID_MISMATCH_BUDGET * ids.size
+        same = ids.astype(np.int64) == oids
+        assert channel_diff(bgra[same], obgra[same]).max(initial=0) <= COLOUR_TOL
+        return ids, bgra, oids, obgra
+
+    def close(self):
+        self.obj.close(); self.cam.close(); self.mesh.close(); self.ref.close()
+
+
+@pytest.fixture(scope="module")
+def gpu(rtb):
+    if rtb.device_count() < 1:
+        pytest.fail("no CUDA device: -m gpu tests must run on the GPU box")
+    rtb.set_device(0)
+    return rtb
+
+
+def test_icosphere_frames_cull_and_nocull(gpu, orc):
+    pts = gpu.geodesic_mesh(24)
+    p = Pair(gpu, orc, pts, 320, 180)
+    n = np.array([0.0, 0.0, 1.0], np.float32)
+    for k in range(6):
+        if k in (1, 2, 3):
+            p.transform(gpu.ROTATE_TRI_PY, gpu.R_KEY_QUAT)
+        if k == 4:
+            for _ in range(60):
+                p.transform(gpu.TRANSLATE_Z, (float(n[0]), float(n[1]), float(n[2]), 0.005))
+        if k == 5:
+            p.transform(gpu.ROTATE_TRI_NY, gpu.T_KEY_QUAT)
+        m_gpu, m_ref = p.obj.matrix(), p.ref.matrix()
+        assert np.array_equal(m_gpu.view(np.uint32), m_ref.view(np.uint32))
+        ids, bgra, oids, obgra = p.check(flags=0)
+        ids2, bgra2, _, _ = p.check(flags=gpu.RENDER_NO_CULL)
+        assert np.array_equal(ids, ids2) and np.array_equal(bgra, bgra2)
+        assert (ids >= 0).sum() > 500
+    p.close()
+
+
+def test_nocull_visits_the_reference_node_sequence(gpu, orc):
+    """Without culling the kernel pops exactly the nodes Trixel.cu:70-170 pops."""
+    pts = gpu.geodesic_mesh(16)
+    p = Pair(gpu, orc, pts, 256, 144)
+    p.transform(gpu.ROTATE_TRI_PY, gpu.R_KEY_QUAT)
+    p.cam.counters(reset=True)
+    p.ref.counters[:] = 0
+    p.check(flags=gpu.RENDER_NO_CULL | gpu.RENDER_COUNTERS)
+    c = p.cam.counters()
+    assert c["rays"] == 256 * 144
+    assert c["boxes"] == int(p.ref.counters[0])   # node pops
+    assert c["tris"] == int(p.ref.counters[1])    # Moller-Trumbore tests
+    # culling must only ever remove work
+    p.check(flags=gpu.RENDER_COUNTERS)
+    c2 = p.cam.counters()
+    assert c2["tris"] <= c["tris"] and c2["boxes"] <= c["boxes"] and c2["hits"] == c["hits"]
+    p.close()
+
+
+def test_bunny_default_and_closeup(gpu, orc):
+    path = mesh_path("rabbit_70k.ply")
+    if path is None:
+        pytest.skip("rabbit_70k.ply not shipped (oracle/_ref/data missing)")
+    pts = gpu.read_ply(path, 1)
+    assert pts.shape == (69451, 9)
+    p = Pair(gpu, orc, pts, 960, 540)
+    g = golden()["bunny_960x540"]
+    for k in range(4):
+        if k:
+            p.transform(gpu.ROTATE_TRI_PY, gpu.R_KEY_QUAT)
+        ids, bgra, oids, obgra = p.check()
+        assert int((ids >= 0).sum()) == g["frames"][k]["hits"]
+        assert orc.fnv1a64(ids.astype(np.int64)) == g["frames"][k]["id_hash"]
+    p.close()
+    p = Pair(gpu, orc, pts, 960, 540)
+    n = p.cam.basis()[0:3]
+    for _ in range(150):
+        p.transform(gpu.TRANSLATE_Z, (float(n[0]), float(n[1]), float(n[2]), 0.005))
+    ids, bgra, oids, obgra = p.check()
+    gc = golden()["bunny_960x540_closeup"]
+    assert int((ids >= 0).sum()) == gc["hits"] == 277301
+    assert orc.fnv1a64(ids.astype(np.int64)) == gc["id_hash"]
+    p.close()
+
+
+def test_three_walls_ties(gpu, orc):
+    """Every hit on 3_walls is an exact 3-way tie between copies: the visit order decides."""
+    path = mesh_path("3_walls.ply")
+    if path is None:
+        pytest.skip("3_walls.ply not shipped")
+    pts = gpu.read_ply(path, -1)
+    assert pts.shape == (36, 9)
+    p = Pair(gpu, orc, pts, 960, 540, cam=WALLS_CAMERA)
+    ids, bgra, oids, obgra = p.check()
+    g = golden()["walls_960x540"]
+    assert int((ids >= 0).sum()) == g["hits"] == 234101
+    u, c = np.unique(ids[ids >= 0], return_counts=True)
+    assert {str(int(a)): int(b) for a, b in zip(u, c)} == g["winners"]
+    assert orc.fnv1a64(ids.astype(np.int64)) == g["id_hash"]
+    p.close()
+
+
+@pytest.mark.parametrize("ntri,W,H", [(1, 64, 48), (2, 97, 61), (3, 333, 211), (20, 1, 1), (80, 31, 33)])
+def test_small_meshes_and_ragged_frames(gpu, orc, ntri, W, H):
+    pts = gpu.geodesic_mesh(2)[:ntri] if ntri < 80 else gpu.geodesic_mesh(2)
+    p = Pair(gpu, orc, pts, W, H)
+    p.check()
+    p.transform(gpu.ROTATE_TRI_PY, gpu.R_KEY_QUAT)
+    p.check(flags=gpu.RENDER_NO_CULL)
+    p.close()
+
+
+def test_per_triangle_colours(gpu, orc):
+    pts = gpu.geodesic_mesh(8)
+    rng = np.random.default_rng(7)
+    cols = rng.uniform(0.05, 1.0, size=(len(pts), 3)).astype(np.float32)
+    p = Pair(gpu, orc, pts, 200, 120, colors=cols)
+    p.check()
+    p.close()
+
+
+def test_camera_inside_root_box_sees_nothing(gpu, orc):
+    """Quirk kept from Trixel.cu:146: a ray origin inside a node's box rejects the node."""
+    pts = gpu.geodesic_mesh(6, radius=2.0, center=(0.0, 0.1, -1.0))
+    p = Pair(gpu, orc, pts, 96, 64)
+    ids, bgra, oids, obgra = p.check()
+    assert (ids == -1).all()
+    p.close()
+
+
+def test_sweep_equals_frame_by_frame(gpu, orc):
+    pts = gpu.geodesic_mesh(20)
+    W, H, F = 256, 144, 9
+    p = Pair(gpu, orc, pts, W, H)
+    ops = gpu.orbit_ops(F)
+    ids_s, col_s = p.obj.render_sweep(p.cam, ops)
+    q = Pair(gpu, orc, pts, W, H)
+    for f in range(F):
+        if f:
+            q.transform(gpu.ROTATE_TRI_PY, gpu.R_KEY_QUAT)
+        ids, bgra, oids, obgra = q.check()
+        assert np.array_equal(ids_s[f], ids) and np.array_equal(col_s[f], bgra)
+    assert np.array_equal(p.obj.matrix().view(np.uint32), q.obj.matrix().view(np.uint32))
+    p.close(); q.close()
+
+
+def test_tile_partition_is_bit_identical(gpu, orc):
+    """Multi-GPU sharding unit: tiles t % G == r rendered separately compose the 1-GPU frame."""
+    import torch
+    pts = gpu.geodesic_mesh(20)
+    W, H = 300, 170
+    p = Pair(gpu, orc, pts, W, H)
+    p.transform(gpu.ROTATE_TRI_PY, gpu.R_KEY_QUAT)
+    full_ids, full_col, _, _ = p.check()
+    m = p.obj.matrix()
+    for G in (2, 3, 8):
+        col = torch.zeros(W * H, dtype=torch.int32, device="cuda")
+        ids = torch.full((W * H,), -7, dtype=torch.int32, device="cuda")
+        s = torch.cuda.current_stream().cuda_stream
+        for r in range(G):
+            p.obj.render_frames_device_async(p.cam, m, col.data_ptr(), ids.data_ptr(), s, tile_first=r, tile_stride=G)
+        torch.cuda.synchronize()
+        assert np.array_equal(ids.cpu().numpy(), full_ids)
+        assert np.array_equal(col.cpu().numpy().view(np.uint32), full_col)
+    p.close()
