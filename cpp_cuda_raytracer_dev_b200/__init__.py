@@ -35,7 +35,7 @@ EXPORTS = [
     "rtb_camera_add_object", "rtb_camera_color_pixels", "rtb_camera_host_color", "rtb_camera_host_ids",
     "rtb_camera_counters", "rtb_camera_destroy", "rtb_object_create", "rtb_object_transform", "rtb_object_get_matrix",
     "rtb_object_set_matrix", "rtb_object_destroy", "rtb_object_render", "rtb_render_frame", "rtb_render_sweep",
-    "rtb_render_frames_device_async", "rtb_object_transform_host", "rtb_device_props",
+    "rtb_render_frames_device_async", "rtb_object_transform_host", "rtb_device_props", "rtb_launch_count",
 ]
 
 
@@ -90,6 +90,7 @@ def _load():
     L.rtb_render_sweep.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, C.c_uint32, vp, vp]
     L.rtb_render_frames_device_async.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_uint32, vp, vp, vp]
     L.rtb_device_props.argtypes = [vp]
+    L.rtb_launch_count.restype = C.c_uint64
     return L
 
 
@@ -107,6 +108,10 @@ def device_count():
 
 def set_device(i):
     _check(lib.rtb_set_device(i), "rtb_set_device")
+
+
+def launch_count():
+    return int(lib.rtb_launch_count())
 
 
 def device_props():

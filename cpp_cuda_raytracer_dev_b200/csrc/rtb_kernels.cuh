@@ -65,23 +65,30 @@ struct RenderParams {
 #define RTB_EPS_UP __int_as_float(0x24e69595)
 #define RTB_TINY 3.7252902984619140625e-09f /* 2^-28: above this, neighbouring floats are > 1e-16 apart */
 
+// The double-precision forms are only reachable for |x| < 2^-28, NaN or exact ties; they live in
+// separate functions so the common path stays branch-light fp32.
+__device__ __noinline__ bool slow_ge_minus_eps(float hi, float lo) { return (double)hi >= (double)lo - 1e-16; }
+__device__ __noinline__ bool slow_lt_plus_eps(float a, float s) { return (double)a < (double)s + 1e-16; }
+__device__ __noinline__ bool slow_gt_minus_eps(float b, float s) { return (double)b > (double)s - 1e-16; }
+
 // (double)hi >= (double)lo - 1e-16          (Trixel.cu:146, first clause)
+// hi >= lo implies it; hi < lo with |lo| >= 2^-28 refutes it (lo - 1e-16 rounds above prev(lo)).
 __device__ __forceinline__ bool cmp_ge_minus_eps(float hi, float lo) {
-    if (hi >= lo) return true;
-    if (fabsf(lo) >= RTB_TINY) return false;
-    return (double)hi >= (double)lo - 1e-16;
+    bool r = hi >= lo;
+    if (!r && !(fabsf(lo) >= RTB_TINY)) r = slow_ge_minus_eps(hi, lo);
+    return r;
 }
 // (double)a < (double)s + 1e-16             (Trixel.cu:155)
 __device__ __forceinline__ bool cmp_lt_plus_eps(float a, float s) {
-    if (a < s) return true;
-    if (a > s && fabsf(s) >= RTB_TINY) return false;
-    return (double)a < (double)s + 1e-16;
+    bool r = a < s;
+    if (!r && !(a > s && fabsf(s) >= RTB_TINY)) r = slow_lt_plus_eps(a, s);
+    return r;
 }
 // (double)b > (double)s - 1e-16             (Trixel.cu:156)
 __device__ __forceinline__ bool cmp_gt_minus_eps(float b, float s) {
-    if (b > s) return true;
-    if (b < s && fabsf(s) >= RTB_TINY) return false;
-    return (double)b > (double)s - 1e-16;
+    bool r = b > s;
+    if (!r && !(b < s && fabsf(s) >= RTB_TINY)) r = slow_gt_minus_eps(b, s);
+    return r;
 }
 // (float)(((double)S1 + 1e-16) + (double)ds)   (Trixel.cu:150: `s1 = cvm->s1[cni] + EPS + ds`)
 __device__ __forceinline__ float s1_plus_eps_plus_ds(float S1, float ds) {
@@ -327,7 +334,9 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const RenderParam
             }
             auto culled = [&](float tmin) -> bool {
                 // never true for NaN/inf slack; keeps every node that could hold a closer hit
-                return CULL && (tmin > best + (slack_abs + P.cull_rel * (fabsf(tmin) + fabsf(best))));
+                if (!CULL) return false;
+                const float lim = best + (slack_abs + P.cull_rel * (fabsf(tmin) + fabsf(best)));
+                return tmin > lim;
             };
 
             int sp = 0;
@@ -377,8 +386,10 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const RenderParam
                     slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ltmin, ltmax);
                     slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, rtmin, rtmax);
                     if (COUNT) c_boxes += (int)visit_l + (int)visit_r;  // children the reference would pop
-                    bool go_l = visit_l && (lref < 0 || box_entered(ltmin, ltmax)) && !culled(ltmin);
-                    bool go_r = visit_r && (rref < 0 || box_entered(rtmin, rtmax)) && !culled(rtmin);
+                    const bool l_in = box_entered(ltmin, ltmax), r_in = box_entered(rtmin, rtmax);
+                    const bool l_cull = culled(ltmin), r_cull = culled(rtmin);
+                    const bool go_l = visit_l & ((lref < 0) | l_in) & !l_cull;
+                    const bool go_r = visit_r & ((rref < 0) | r_in) & !r_cull;
                     const int first = left_first ? lref : rref, second = left_first ? rref : lref;
                     const float f_tmin = left_first ? ltmin : rtmin, f_tmax = left_first ? ltmax : rtmax;
                     const float s_tmin = left_first ? rtmin : ltmin, s_tmax = left_first ? rtmax : ltmax;
@@ -413,8 +424,9 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const RenderParam
                 if (COUNT) c_hits++;
             }
             const long long o = (long long)frame * P.W * P.H + pix;
-            if (P.out_bgra) P.out_bgra[o] = color;
-            if (P.out_ids) P.out_ids[o] = id;
+            // frames are write-once streams: keep them from displacing the scene in L2
+            if (P.out_bgra) __stcs(P.out_bgra + o, color);
+            if (P.out_ids) __stcs(P.out_ids + o, id);
         }
     }
     if (COUNT) {

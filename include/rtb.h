@@ -180,6 +180,9 @@ int rtb_render_frames_device_async(rtb_object* obj, rtb_camera* cam, int32_t num
  * lets callers precompute the m12 array for rtb_render_frames_device_async. */
 int rtb_object_transform_host(rtb_object* obj, const float xyzw[4], uint8_t transform_select, float m12_out[12]);
 
+/* number of kernels this library has launched in this process (render, pack and fill kernels) */
+uint64_t rtb_launch_count(void);
+
 /* device properties the roofline uses: [0] SM count, [1] L2 bytes, [2] max persisting L2 bytes,
  * [3] SM clock kHz, [4] memory clock kHz, [5] memory bus width bits, [6] compute capability*10 */
 int rtb_device_props(int64_t out7[7]);
