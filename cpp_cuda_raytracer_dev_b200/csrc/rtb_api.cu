@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -12,6 +13,7 @@
 #include "../../include/rtb.h"
 #include "rtb_host.hpp"
 #include "rtb_kernels.cuh"
+#include "rtb_render.cuh"
 
 namespace {
 
@@ -98,10 +100,58 @@ int ensure_frames(rtb_object* o, int frames) {
     if (o->d_frames) cudaFree(o->d_frames);
     if (o->h_frames) cudaFreeHost(o->h_frames);
     o->d_frames = nullptr; o->h_frames = nullptr; o->frames_capacity = 0;
-    RTB_CUDA(cudaMalloc(&o->d_frames, sizeof(float) * 12 * (size_t)cap));
-    RTB_CUDA(cudaMallocHost(&o->h_frames, sizeof(float) * 12 * (size_t)cap));
+    RTB_CUDA(cudaMalloc(&o->d_frames, sizeof(float) * rtb::kFrameStride * (size_t)cap));
+    RTB_CUDA(cudaMallocHost(&o->h_frames, sizeof(float) * rtb::kFrameStride * (size_t)cap));
     o->frames_capacity = cap;
     return RTB_OK;
+}
+
+// One frame record for the kernel: the object's 3x4 matrix followed by the pixel rectangle outside
+// which no primary ray can reach the root box.  The rectangle is the projection of the eight corners
+// of the (camera-relative, translated) root box through the inverse rotation onto the pixel grid,
+// enlarged by 2 pixels -- three orders of magnitude more than the rounding error of the slab test
+// (Trixel.cu:76-95,146) -- so pixels outside it are background exactly as in the reference.  If a
+// corner is not in front of the camera, or the matrix is not invertible, the rectangle is the frame.
+void fill_frame_record(const rtb_object* o, const rtb_camera* c, const float m12[12], float* rec) {
+    std::memcpy(rec, m12, sizeof(float) * 12);
+    const rtb::CameraBasis& b = c->basis;
+    int rect[4] = {0, 0, b.W - 1, b.H - 1};
+    auto dot = [](const double* p, const float* q) { return p[0] * q[0] + p[1] * q[1] + p[2] * q[2]; };
+    auto dotf = [](const float* p, const float* q) { return (double)p[0] * q[0] + (double)p[1] * q[1] + (double)p[2] * q[2]; };
+    const double R[3][3] = {{m12[0], m12[1], m12[2]}, {m12[4], m12[5], m12[6]}, {m12[8], m12[9], m12[10]}};
+    const double det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
+                       R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+    const double pw = dotf(b.u_mod, b.u), ph = dotf(b.v_mod, b.v), f = dotf(b.n_mod, b.n);
+    bool ok = std::isfinite(det) && std::fabs(det) > 1e-6 && pw > 0 && ph > 0 && f > 0 && o->root_ref >= 0;
+    if (ok) {
+        double inv[3][3];
+        inv[0][0] = (R[1][1] * R[2][2] - R[1][2] * R[2][1]) / det; inv[0][1] = (R[0][2] * R[2][1] - R[0][1] * R[2][2]) / det; inv[0][2] = (R[0][1] * R[1][2] - R[0][2] * R[1][1]) / det;
+        inv[1][0] = (R[1][2] * R[2][0] - R[1][0] * R[2][2]) / det; inv[1][1] = (R[0][0] * R[2][2] - R[0][2] * R[2][0]) / det; inv[1][2] = (R[0][2] * R[1][0] - R[0][0] * R[1][2]) / det;
+        inv[2][0] = (R[1][0] * R[2][1] - R[1][1] * R[2][0]) / det; inv[2][1] = (R[0][1] * R[2][0] - R[0][0] * R[2][1]) / det; inv[2][2] = (R[0][0] * R[1][1] - R[0][1] * R[1][0]) / det;
+        const double ax = -dotf(b.n_mod, b.u) / pw, ay = -dotf(b.n_mod, b.v) / ph;
+        double lo_x = 1e300, hi_x = -1e300, lo_y = 1e300, hi_y = -1e300;
+        for (int k = 0; k < 8 && ok; k++) {
+            const double cx = (double)o->root_box[(k & 1) ? 3 : 0] + m12[3];
+            const double cy = (double)o->root_box[(k & 2) ? 4 : 1] + m12[7];
+            const double cz = (double)o->root_box[(k & 4) ? 5 : 2] + m12[11];
+            const double p[3] = {inv[0][0] * cx + inv[0][1] * cy + inv[0][2] * cz, inv[1][0] * cx + inv[1][1] * cy + inv[1][2] * cz,
+                                 inv[2][0] * cx + inv[2][1] * cy + inv[2][2] * cz};
+            const double depth = dot(p, b.n);
+            const double scale = std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+            if (!(depth > 1e-3 * scale) || !std::isfinite(depth)) { ok = false; break; }
+            const double ix = ax + f * dot(p, b.u) / (depth * pw), iy = ay + f * dot(p, b.v) / (depth * ph);
+            if (!std::isfinite(ix) || !std::isfinite(iy)) { ok = false; break; }
+            lo_x = std::min(lo_x, ix); hi_x = std::max(hi_x, ix); lo_y = std::min(lo_y, iy); hi_y = std::max(hi_y, iy);
+        }
+        if (ok) {
+            const double margin = 2.0;
+            auto clampi = [](double v, int lo, int hi) { return (int)std::max((double)lo, std::min((double)hi, v)); };
+            rect[0] = clampi(std::floor(lo_x - margin), 0, b.W); rect[1] = clampi(std::floor(lo_y - margin), 0, b.H);
+            rect[2] = clampi(std::ceil(hi_x + margin), -1, b.W - 1); rect[3] = clampi(std::ceil(hi_y + margin), -1, b.H - 1);
+        }
+    }
+    if (std::getenv("RTB_NO_RECT")) { rect[0] = 0; rect[1] = 0; rect[2] = b.W - 1; rect[3] = b.H - 1; }
+    std::memcpy(rec + 12, rect, sizeof rect);
 }
 
 // Launch the persistent render kernel over `num_frames` matrices already resident in o->d_frames.
@@ -127,7 +177,7 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, int num_f
     if (tile_stride < 1 || tile_first < 0 || tile_first >= tile_stride) return fail(RTB_ERR_ARG, "render: bad tile_first/tile_stride");
     P.tile_first = tile_first; P.tile_stride = tile_stride;
     P.my_tiles = tile_first < tiles ? (tiles - tile_first + tile_stride - 1) / tile_stride : 0;
-    P.total_items = (long long)num_frames * P.my_tiles * kItemsPerTile;
+    P.total_items = (long long)num_frames * P.my_tiles;
     P.out_bgra = d_bgra; P.out_ids = d_ids;
     P.work_counter = o->d_work;
     P.counters = c->d_counters;
@@ -135,16 +185,22 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, int num_f
     if (P.total_items == 0) return RTB_OK;
 
     const bool cull = !(flags & RTB_RENDER_NO_CULL), count = (flags & RTB_RENDER_COUNTERS) != 0;
-    void (*kern)(const RenderParams) = cull ? (count ? render_kernel<true, true> : render_kernel<true, false>)
-                                            : (count ? render_kernel<false, true> : render_kernel<false, false>);
+    auto env_int = [](const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; };
+    void (*kern)(const RenderParams) = cull ? (count ? render_stream_kernel<true, true> : render_stream_kernel<true, false>)
+                                            : (count ? render_stream_kernel<false, true> : render_stream_kernel<false, false>);
     int per_sm = 0;
     RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, 0));
     per_sm = std::max(per_sm, 1);
     const long long warps_total = (long long)c->sm_count * per_sm * (kBlockThreads / 32);
-    long long chunk = 1;  // measured: 1 beats 2, 4, 13 on the dragon stand-in (finer balance, atomics are not the limit)
-    if (const char* env = std::getenv("RTB_CHUNK")) chunk = std::max(1, std::atoi(env));
-    P.chunk = (int)chunk;
-    const long long fetches = (P.total_items + chunk - 1) / chunk;
+    // work unit: Morton block of 2^shift pixels; small launches get small units so every warp has work
+    const long long pixels = (long long)num_frames * P.my_tiles * kTile * kTile;
+    int shift = 8;
+    while (shift > 5 && (pixels >> shift) < warps_total * 4) shift--;
+    P.unit_shift = std::min(10, std::max(5, env_int("RTB_UNIT_SHIFT", shift)));
+    P.t_active = std::min(31, std::max(0, env_int("RTB_T_ACTIVE", 20)));
+    P.t_leaf = std::max(1, env_int("RTB_T_LEAF", 8));
+    P.total_items = (long long)num_frames * P.my_tiles * ((kTile * kTile) >> P.unit_shift);
+    const long long fetches = P.total_items;
     const long long blocks_needed = (fetches + (kBlockThreads / 32) - 1) / (kBlockThreads / 32);
     const int grid = (int)std::max(1ll, std::min<long long>((long long)c->sm_count * per_sm, blocks_needed));
     RTB_CUDA(cudaMemsetAsync(o->d_work, 0, sizeof(unsigned long long), stream));
@@ -232,7 +288,7 @@ int rtb_mesh_geodesic(int nu, float radius, const float center[3], float displac
 // ---- mesh ----------------------------------------------------------------------------------------
 
 int rtb_mesh_create(const float* points9, int64_t num_tri, const float* rad3, const float uniform_rgb[3], rtb_mesh** out) {
-    if (!points9 || num_tri <= 0 || num_tri > 0x3fffffff || !out) return fail(RTB_ERR_ARG, "mesh_create: bad argument");
+    if (!points9 || num_tri <= 0 || num_tri > 0x1fffffff || !out) return fail(RTB_ERR_ARG, "mesh_create: bad argument");
     rtb_mesh* m = new rtb_mesh();
     m->device = g_device;
     m->n = num_tri;
@@ -399,7 +455,7 @@ int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj) {
     obj->root_box[0] = (rb[0] - cx) + 0.0f; obj->root_box[3] = (rb[1] - cx) + 0.0f;
     obj->root_box[1] = (rb[2] - cy) + 0.0f; obj->root_box[4] = (rb[3] - cy) + 0.0f;
     obj->root_box[2] = (rb[4] - cz) + 0.0f; obj->root_box[5] = (rb[5] - cz) + 0.0f;
-    obj->root_ref = n == 1 ? ~T.tri[0] : 0;
+    obj->root_ref = n == 1 ? (int)(rtb::kRefLeaf | (unsigned)T.tri[0]) : 0;
 
     // pin nodes + triangles in L2 (the 800k-triangle dragon fits).  The
     // window is attached to every render launch (launch_render).
@@ -522,8 +578,12 @@ int rtb_object_render(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
     RTB_CUDA(cudaSetDevice(cam->device));
     rc = ensure_frames(obj, 1);
     if (rc) return rc;
-    obj->xf.matrix(obj->h_frames);
-    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * 12, cudaMemcpyHostToDevice, cam->stream));
+    {
+        float m12[12];
+        obj->xf.matrix(m12);
+        fill_frame_record(obj, cam, m12, obj->h_frames);
+    }
+    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * rtb::kFrameStride, cudaMemcpyHostToDevice, cam->stream));
     rc = launch_render(obj, cam, obj->d_frames, 1, 0, 1, flags, cam->d_bgra, cam->d_ids, cam->stream);
     if (rc) return rc;
     // the reference's wrapper synchronises (Trixel.cu:234)
@@ -537,8 +597,12 @@ int rtb_render_frame(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
     RTB_CUDA(cudaSetDevice(cam->device));
     rc = ensure_frames(obj, 1);
     if (rc) return rc;
-    obj->xf.matrix(obj->h_frames);
-    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * 12, cudaMemcpyHostToDevice, cam->stream));
+    {
+        float m12[12];
+        obj->xf.matrix(m12);
+        fill_frame_record(obj, cam, m12, obj->h_frames);
+    }
+    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * rtb::kFrameStride, cudaMemcpyHostToDevice, cam->stream));
     rc = launch_render(obj, cam, obj->d_frames, 1, 0, 1, flags, cam->d_bgra, cam->d_ids, cam->stream);
     if (rc) return rc;
     RTB_CUDA(cudaMemcpyAsync(cam->h_bgra, cam->d_bgra, sizeof(uint32_t) * (size_t)cam->pixels, cudaMemcpyDeviceToHost, cam->stream));
@@ -558,8 +622,8 @@ int rtb_render_frames_device_async(rtb_object* obj, rtb_camera* cam, int32_t num
     RTB_CUDA(cudaStreamSynchronize(s));
     rc = ensure_frames(obj, num_frames);
     if (rc) return rc;
-    std::memcpy(obj->h_frames, m12, sizeof(float) * 12 * (size_t)num_frames);
-    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * 12 * (size_t)num_frames, cudaMemcpyHostToDevice, s));
+    for (int f = 0; f < num_frames; f++) fill_frame_record(obj, cam, m12 + 12 * (size_t)f, obj->h_frames + rtb::kFrameStride * (size_t)f);
+    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * rtb::kFrameStride * (size_t)num_frames, cudaMemcpyHostToDevice, s));
     return launch_render(obj, cam, obj->d_frames, num_frames, tile_first, tile_stride, flags, d_bgra, d_ids, s);
 }
 
@@ -580,9 +644,11 @@ int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32
             if (select == 0) continue;
             if (!obj->xf.apply((uint8_t)select, op[1], op[2], op[3], op[4])) return fail(RTB_ERR_ARG, "render_sweep: unknown selector");
         }
-        obj->xf.matrix(obj->h_frames + 12 * (size_t)f);
+        float m12[12];
+        obj->xf.matrix(m12);
+        fill_frame_record(obj, cam, m12, obj->h_frames + rtb::kFrameStride * (size_t)f);
     }
-    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * 12 * (size_t)num_frames, cudaMemcpyHostToDevice, cam->stream));
+    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * rtb::kFrameStride * (size_t)num_frames, cudaMemcpyHostToDevice, cam->stream));
 
     // ring of two device chunks; chunk k+1 renders while chunk k streams to the host
     const size_t P = (size_t)cam->pixels;
@@ -624,7 +690,7 @@ int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32
             if (rc) return rc;
             RTB_CUDA(cudaStreamWaitEvent(cam->stream, cam->ev_copy[slot], 0));
         }
-        rc = launch_render(obj, cam, obj->d_frames + 12 * (size_t)f0, nf, 0, 1, flags, bgra_out ? cam->ring_bgra[slot] : nullptr,
+        rc = launch_render(obj, cam, obj->d_frames + rtb::kFrameStride * (size_t)f0, nf, 0, 1, flags, bgra_out ? cam->ring_bgra[slot] : nullptr,
                            ids_out ? cam->ring_ids[slot] : nullptr, cam->stream);
         if (rc) return rc;
         RTB_CUDA(cudaEventRecord(cam->ev_render[slot], cam->stream));

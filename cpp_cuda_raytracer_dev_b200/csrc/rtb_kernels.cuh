@@ -9,7 +9,10 @@
 //           boxes (s1 == left child's max, s2 == right child's min on the split axis,
 //           Trixel.h:353-376) and are read from them.
 //             q0 = L.t0x L.t0y L.t0z L.t1x      q1 = L.t1y L.t1z R.t0x R.t0y
-//             q2 = R.t0z R.t1x R.t1y R.t1z      q3 = left_ref right_ref axis pad   (as int bits)
+//             q2 = R.t0z R.t1x R.t1y R.t1z      q3 = left_ref right_ref S1 S2
+//           S1/S2 are copies of L.t1[axis] / R.t0[axis] so the hot loop needs no axis-indexed
+//           select; a child reference is a 32-bit word: bit 31 = leaf, bits 29-30 = split axis of
+//           THIS node (stored in left_ref only), bits 0-28 = record index or triangle id.
 //   tris  : one 48-byte record (3 x float4) per triangle
 //             t0 = e1.xyz n.x    t1 = e2.xyz n.y    t2 = (cam_pos - p1).xyz n.z
 //   rad   : float4 per triangle (r,g,b,-) or absent when the mesh has one colour.
@@ -19,7 +22,7 @@
 // association order -- the translation unit is compiled with -fmad=false and the code below uses
 // __fmul_rn/__fadd_rn/__fsub_rn so nothing can be contracted into an FMA.  Comparisons that the
 // reference performs in double precision (because its epsilons are double literals,
-// vector.cuh:10-11) are reproduced exactly; see the cmp_* helpers.
+// vector.cuh:10-11) are reproduced exactly; see the exact_* helpers and their fp32 shortcuts.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,11 +30,11 @@
 namespace rtb {
 
 constexpr int kTile = 32;        // multi-GPU interleave granularity: 32x32 pixel tiles
-constexpr int kWarpTileW = 8;    // one warp renders 8x4 pixels
-constexpr int kWarpTileH = 4;
-constexpr int kItemsPerTile = (kTile / kWarpTileW) * (kTile / kWarpTileH);  // 16
 constexpr int kStackDepth = 40;  // >= tree height + 2 (median split: height = ceil(log2 n))
 constexpr int kBlockThreads = 128;
+constexpr int kFrameStride = 16;
+constexpr unsigned kRefLeaf = 0x80000000u, kRefIndexMask = 0x1fffffffu;
+constexpr int kRefAxisShift = 29;
 
 struct RenderParams {
     int W, H;
@@ -39,18 +42,20 @@ struct RenderParams {
     float root_box[6];  // t0x t0y t0z t1x t1y t1z of node 0, camera-relative
     float draw_distance;
     uint32_t background;  // 0x00RRGGBB
-    int root_ref;         // 0 = interior root record 0; < 0: ~triangle (single-triangle mesh)
+    int root_ref;         // encoded reference of node 0 (record 0, or leaf|triangle for a single-triangle mesh)
     const float4* __restrict__ nodes;
     const float4* __restrict__ tris;
     const float4* __restrict__ rad;  // may be null
     float uniform_rad[3];
-    const float* __restrict__ frames;  // 12 floats per frame: rows x,y,z = (i,j,k,w)
+    const float* __restrict__ frames;  // kFrameStride floats per frame: rows x,y,z = (i,j,k,w), then the pixel rectangle
+                                       // x0,y0,x1,y1 (int bits, inclusive) outside which no ray can reach the root box
     int num_frames;
     int tiles_x;           // tiles per image row
     int tile_first, tile_stride;
     int my_tiles;          // number of 32x32 tiles of one frame rendered by this launch
-    int chunk;             // consecutive warp items taken per work fetch
-    long long total_items; // num_frames * my_tiles * kItemsPerTile
+    int unit_shift;        // log2 pixels per work unit: 5..10, a Morton block of a 32x32 tile
+    int t_active, t_leaf;  // refill when <= t_active lanes still traverse; leaf step when >= t_leaf lanes wait at a leaf
+    long long total_items; // work units: num_frames * my_tiles * (1024 >> unit_shift)
     uint32_t* __restrict__ out_bgra;
     int32_t* __restrict__ out_ids;
     unsigned long long* work_counter;
@@ -65,44 +70,52 @@ struct RenderParams {
 #define RTB_EPS_UP __int_as_float(0x24e69595)
 #define RTB_TINY 3.7252902984619140625e-09f /* 2^-28: above this, neighbouring floats are > 1e-16 apart */
 
-// The double-precision forms are only reachable for |x| < 2^-28, NaN or exact ties; they live in
-// separate functions so the common path stays branch-light fp32.
-__device__ __noinline__ bool slow_ge_minus_eps(float hi, float lo) { return (double)hi >= (double)lo - 1e-16; }
-__device__ __noinline__ bool slow_lt_plus_eps(float a, float s) { return (double)a < (double)s + 1e-16; }
-__device__ __noinline__ bool slow_gt_minus_eps(float b, float s) { return (double)b > (double)s - 1e-16; }
-
-// (double)hi >= (double)lo - 1e-16          (Trixel.cu:146, first clause)
-// hi >= lo implies it; hi < lo with |lo| >= 2^-28 refutes it (lo - 1e-16 rounds above prev(lo)).
-__device__ __forceinline__ bool cmp_ge_minus_eps(float hi, float lo) {
-    bool r = hi >= lo;
-    if (!r && !(fabsf(lo) >= RTB_TINY)) r = slow_ge_minus_eps(hi, lo);
-    return r;
-}
-// (double)a < (double)s + 1e-16             (Trixel.cu:155)
-__device__ __forceinline__ bool cmp_lt_plus_eps(float a, float s) {
-    bool r = a < s;
-    if (!r && !(a > s && fabsf(s) >= RTB_TINY)) r = slow_lt_plus_eps(a, s);
-    return r;
-}
-// (double)b > (double)s - 1e-16             (Trixel.cu:156)
-__device__ __forceinline__ bool cmp_gt_minus_eps(float b, float s) {
-    bool r = b > s;
-    if (!r && !(b < s && fabsf(s) >= RTB_TINY)) r = slow_gt_minus_eps(b, s);
-    return r;
-}
+// Exact double-precision forms of the reference's epsilon comparisons.  The hot loop uses fp32
+// shortcuts that are provably equal to these whenever they can decide (see child_order / box_entered
+// in rtb_render.cuh) and calls the functions below only for the rare undecidable inputs: operands
+// below 2^-28 in magnitude, exact ties, NaN.
+__device__ __noinline__ bool exact_ge_minus_eps(float hi, float lo) { return (double)hi >= (double)lo - 1e-16; }   // Trixel.cu:146
+__device__ __noinline__ bool exact_lt_plus_eps(float a, float s) { return (double)a < (double)s + 1e-16; }         // Trixel.cu:155
+__device__ __noinline__ bool exact_gt_minus_eps(float b, float s) { return (double)b > (double)s - 1e-16; }        // Trixel.cu:156
 // (float)(((double)S1 + 1e-16) + (double)ds)   (Trixel.cu:150: `s1 = cvm->s1[cni] + EPS + ds`)
-__device__ __forceinline__ float s1_plus_eps_plus_ds(float S1, float ds) {
+__device__ __noinline__ float exact_s1(float S1, float ds) {
     return __double2float_rn(__dadd_rn(__dadd_rn((double)S1, 1e-16), (double)ds));
 }
 
-// vector.cuh:79-95 + 117-120: Quake start value, 21 Newton steps, then scale
+// sm_100a three-input min/max (FMNMX3).  NaN operands are ignored exactly like nested fmax/fmin.
+__device__ __forceinline__ float fmax3(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+__device__ __forceinline__ float fmin3(float a, float b, float c) { float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+
+// vector.cuh:79-95 + 117-120: Quake start value, 21 Newton steps, then scale.
+// Each step is a pure function of the previous iterate, so once the sequence reaches a fixed point
+// (or a 2-cycle) the value after exactly 21 steps is known without running them: the result is
+// bit-identical to the full loop (a NaN iterate never compares equal and runs all 21 steps).
+__device__ __forceinline__ float rsqrt21(float s) {
+    const float half = __fmul_rn(0.5f, s);
+    float g0 = __int_as_float(0x5f375a86 - (__float_as_int(half) >> 1));
+    float g1 = __fmul_rn(g0, __fsub_rn(1.5f, __fmul_rn(__fmul_rn(half, g0), g0)));
+    int k = 1;
+#pragma unroll 1
+    while (k < 21) {
+        const float g2 = __fmul_rn(g1, __fsub_rn(1.5f, __fmul_rn(__fmul_rn(half, g1), g1)));
+        k++;
+        if (g2 == g1) break;                                        // fixed point
+        if (g2 == g0) { g1 = ((21 - k) & 1) ? g1 : g2; break; }      // 2-cycle: parity of the remaining steps
+        g0 = g1; g1 = g2;
+    }
+    return g1;
+}
 __device__ __forceinline__ void normalize21(float& x, float& y, float& z) {
-    const float s = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+    const float g = rsqrt21(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+    x = __fmul_rn(x, g); y = __fmul_rn(y, g); z = __fmul_rn(z, g);
+}
+// the literal 21-step loop (pack kernels, and the reference for the shortcut above in tests)
+__device__ __forceinline__ float rsqrt21_literal(float s) {
     const float half = __fmul_rn(0.5f, s);
     float g = __int_as_float(0x5f375a86 - (__float_as_int(half) >> 1));
 #pragma unroll
     for (int k = 0; k < 21; k++) g = __fmul_rn(g, __fsub_rn(1.5f, __fmul_rn(__fmul_rn(half, g), g)));
-    x = __fmul_rn(x, g); y = __fmul_rn(y, g); z = __fmul_rn(z, g);
+    return g;
 }
 // vector.cuh:122-124
 __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
@@ -126,12 +139,20 @@ __device__ __forceinline__ void slab(const Ray& r, float b0x, float b0y, float b
     const float t1y = __fadd_rn(__fmul_rn(py ? b1y : b0y, r.iy), r.fy);
     const float t0z = __fadd_rn(__fmul_rn(pz ? b0z : b1z, r.iz), r.fz);
     const float t1z = __fadd_rn(__fmul_rn(pz ? b1z : b0z, r.iz), r.fz);
-    tmin = fmaxf(t0z, fmaxf(t0x, t0y));
-    tmax = fminf(t1z, fminf(t1x, t1y));
+    tmin = fmax3(t0z, t0x, t0y);  // fmax(t0z, fmax(t0x, t0y)), Trixel.cu:94
+    tmax = fmin3(t1z, t1x, t1y);  // Trixel.cu:95
 }
-// Trixel.cu:146: enter iff tmax >= tmin - EPS && tmin > -EPS (both in double)
-__device__ __forceinline__ bool box_entered(float tmin, float tmax) {
-    return cmp_ge_minus_eps(tmax, tmin) && (tmin > -RTB_EPS_UP);
+// Trixel.cu:146: enter iff (double)tmax >= (double)tmin - EPS && (double)tmin > -EPS.
+// fp32 shortcut: tmax >= tmin proves the first clause; tmax < tmin with |tmin| >= 2^-28 refutes it
+// (tmin - 1e-16 then rounds to a double strictly above the float below tmin).  `unsure` is raised
+// for everything else (tiny |tmin|, NaN) and the caller re-evaluates with box_entered_exact.
+__device__ __forceinline__ bool box_entered_fast(float tmin, float tmax, bool& unsure) {
+    const bool ge = tmax >= tmin;
+    unsure |= !ge & !(fabsf(tmin) >= RTB_TINY);
+    return ge & (tmin > -RTB_EPS_UP);
+}
+__device__ __forceinline__ bool box_entered_exact(float tmin, float tmax) {
+    return exact_ge_minus_eps(tmax, tmin) && (tmin > -RTB_EPS_UP);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -178,14 +199,14 @@ __global__ void pack_nodes_kernel(const float* __restrict__ bounds6, const int* 
     R[0] = __fadd_rn(__fsub_rn(br[0], cx), 0.0f); R[3] = __fadd_rn(__fsub_rn(br[1], cx), 0.0f);
     R[1] = __fadd_rn(__fsub_rn(br[2], cy), 0.0f); R[4] = __fadd_rn(__fsub_rn(br[3], cy), 0.0f);
     R[2] = __fadd_rn(__fsub_rn(br[4], cz), 0.0f); R[5] = __fadd_rn(__fsub_rn(br[5], cz), 0.0f);
-    const int lref = record_of[l] >= 0 ? record_of[l] : ~tri[l];
-    const int rref = record_of[r] >= 0 ? record_of[r] : ~tri[r];
     const int axis = cut_flag[i] % 3;
+    const unsigned lref = (record_of[l] >= 0 ? (unsigned)record_of[l] : (kRefLeaf | (unsigned)tri[l])) | ((unsigned)axis << kRefAxisShift);
+    const unsigned rref = record_of[r] >= 0 ? (unsigned)record_of[r] : (kRefLeaf | (unsigned)tri[r]);
     float4* o = nodes + 4ll * rec;
     o[0] = make_float4(L[0], L[1], L[2], L[3]);
     o[1] = make_float4(L[4], L[5], R[0], R[1]);
     o[2] = make_float4(R[2], R[3], R[4], R[5]);
-    o[3] = make_float4(__int_as_float(lref), __int_as_float(rref), __int_as_float(axis), 0.0f);
+    o[3] = make_float4(__uint_as_float(lref), __uint_as_float(rref), L[3 + axis], R[axis]);
 }
 
 __global__ void fill_kernel(uint32_t* __restrict__ out, long long n, uint32_t value) {
@@ -270,179 +291,6 @@ __device__ __forceinline__ uint32_t phong(const RenderParams& P, const float* __
     const uint32_t g8 = (uint32_t)__float2uint_rz(__fmul_rn(__fdiv_rn(pg, mx), 255.0f)) & 0xffu;
     const uint32_t b8 = (uint32_t)__float2uint_rz(__fmul_rn(__fdiv_rn(pb, mx), 255.0f)) & 0xffu;
     return (r8 << 16) | (g8 << 8) | b8;
-}
-
-template <bool CULL, bool COUNT>
-__global__ void __launch_bounds__(kBlockThreads) render_kernel(const RenderParams P) {
-    const unsigned lane = threadIdx.x & 31u;
-    unsigned long long c_nodes = 0, c_boxes = 0, c_tris = 0, c_rays = 0, c_hits = 0;
-    const long long items_per_frame = (long long)P.my_tiles * kItemsPerTile;
-
-    int stk_ref[kStackDepth];
-    float stk_tmin[kStackDepth], stk_tmax[kStackDepth];
-
-    for (;;) {
-        // ---- warp-level work fetch: `chunk` consecutive 8x4 warp items per atomic -------------
-        long long base = 0;
-        if (lane == 0) base = (long long)atomicAdd(P.work_counter, (unsigned long long)P.chunk);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= P.total_items) break;
-        const long long stop = base + P.chunk < P.total_items ? base + P.chunk : P.total_items;
-        for (long long item = base; item < stop; item++) {
-            const int frame = (int)(item / items_per_frame);
-            const int rem = (int)(item - (long long)frame * items_per_frame);
-            const int tile = P.tile_first + (rem / kItemsPerTile) * P.tile_stride;
-            const int sub = rem % kItemsPerTile;
-            const int px = (tile % P.tiles_x) * kTile + (sub % (kTile / kWarpTileW)) * kWarpTileW + (int)(lane % kWarpTileW);
-            const int py = (tile / P.tiles_x) * kTile + (sub / (kTile / kWarpTileW)) * kWarpTileH + (int)(lane / kWarpTileW);
-            if (px >= P.W || py >= P.H) continue;
-            const float* __restrict__ M = P.frames + 12ll * frame;
-            const long long pix = (long long)py * P.W + px;
-
-            // ---- primary ray, Camera.cu:103-104 (row 0 = bottom) ------------------------------
-            const float fxp = (float)px, fyp = (float)py;
-            float cmx = __fadd_rn(__fadd_rn(P.n_mod[0], __fmul_rn(P.u_mod[0], fxp)), __fmul_rn(P.v_mod[0], fyp));
-            float cmy = __fadd_rn(__fadd_rn(P.n_mod[1], __fmul_rn(P.u_mod[1], fxp)), __fmul_rn(P.v_mod[1], fyp));
-            float cmz = __fadd_rn(__fadd_rn(P.n_mod[2], __fmul_rn(P.u_mod[2], fxp)), __fmul_rn(P.v_mod[2], fyp));
-            normalize21(cmx, cmy, cmz);
-            // ---- into object space, Trixel.cu:60-66 (sign dance kept for -0 fidelity) ----------
-            Ray r;
-            {
-                const float m0 = __ldg(M + 0), m1 = __ldg(M + 1), m2 = __ldg(M + 2), m3 = __ldg(M + 3);
-                const float m4 = __ldg(M + 4), m5 = __ldg(M + 5), m6 = __ldg(M + 6), m7 = __ldg(M + 7);
-                const float m8 = __ldg(M + 8), m9 = __ldg(M + 9), m10 = __ldg(M + 10), m11 = __ldg(M + 11);
-                r.ox = m3; r.oy = m7; r.oz = m11;
-                r.dx = __fmul_rn(-1.0f, __fadd_rn(__fadd_rn(__fmul_rn(m0, -cmx), __fmul_rn(m1, -cmy)), __fmul_rn(m2, -cmz)));
-                r.dy = __fmul_rn(-1.0f, __fadd_rn(__fadd_rn(__fmul_rn(m4, -cmx), __fmul_rn(m5, -cmy)), __fmul_rn(m6, -cmz)));
-                r.dz = __fmul_rn(-1.0f, __fadd_rn(__fadd_rn(__fmul_rn(m8, -cmx), __fmul_rn(m9, -cmy)), __fmul_rn(m10, -cmz)));
-            }
-            r.ix = __frcp_rn(r.dx); r.iy = __frcp_rn(r.dy); r.iz = __frcp_rn(r.dz);
-            r.fx = __fdiv_rn(r.ox, r.dx); r.fy = __fdiv_rn(r.oy, r.dy); r.fz = __fdiv_rn(r.oz, r.dz);
-
-            float best = P.draw_distance;  // Trixel.cu:47
-            int id = -1;
-            if (COUNT) c_rays++;
-
-            // conservative culling slack: rounding error bound of any slab value of this ray
-            float slack_abs = 0.0f;
-            if (CULL) {
-                const float bx = fmaxf(fabsf(P.root_box[0]), fabsf(P.root_box[3]));
-                const float by = fmaxf(fabsf(P.root_box[1]), fabsf(P.root_box[4]));
-                const float bz = fmaxf(fabsf(P.root_box[2]), fabsf(P.root_box[5]));
-                const float e = fmaxf(fmaxf(bx * fabsf(r.ix) + fabsf(r.fx), by * fabsf(r.iy) + fabsf(r.fy)), bz * fabsf(r.iz) + fabsf(r.fz));
-                slack_abs = e * 9.5367431640625e-07f;  // 8 * 2^-23
-            }
-            auto culled = [&](float tmin) -> bool {
-                // never true for NaN/inf slack; keeps every node that could hold a closer hit
-                if (!CULL) return false;
-                const float lim = best + (slack_abs + P.cull_rel * (fabsf(tmin) + fabsf(best)));
-                return tmin > lim;
-            };
-
-            int sp = 0;
-            int cur;
-            float cur_tmin, cur_tmax;
-            bool have = false;
-            if (P.root_ref < 0) {
-                // single-triangle mesh: the root is a leaf, tested unconditionally (Trixel.cu:98)
-                if (COUNT) { c_tris++; c_boxes++; }
-                moller_trumbore(r, P.tris, ~P.root_ref, best, id);
-                cur = 0; cur_tmin = 0.0f; cur_tmax = 0.0f;
-            } else {
-                slab(r, P.root_box[0], P.root_box[1], P.root_box[2], P.root_box[3], P.root_box[4], P.root_box[5], cur_tmin, cur_tmax);
-                if (COUNT) c_boxes++;
-                have = box_entered(cur_tmin, cur_tmax);
-                cur = 0;
-            }
-
-            while (have) {
-                // ---- interior descent: `cur` is an interior node whose box test passed -----------
-                while (cur >= 0) {
-                    if (COUNT) c_nodes++;
-                    const float4* rec = P.nodes + 4ll * cur;
-                    const float4 q0 = ldg4(rec), q1 = ldg4(rec + 1), q2 = ldg4(rec + 2), q3 = ldg4(rec + 3);
-                    const int lref = __float_as_int(q3.x), rref = __float_as_int(q3.y), axis = __float_as_int(q3.z);
-                    // split-axis components, Trixel.cu:88-90 (three-term sums with 0/1 flags)
-                    const float fxa = axis == 0 ? 1.0f : 0.0f, fya = axis == 1 ? 1.0f : 0.0f, fza = axis == 2 ? 1.0f : 0.0f;
-                    const float dir = __fadd_rn(__fadd_rn(__fmul_rn(r.dx, fxa), __fmul_rn(r.dy, fya)), __fmul_rn(r.dz, fza));
-                    const float ds = __fadd_rn(__fadd_rn(__fmul_rn(r.ox, fxa), __fmul_rn(r.oy, fya)), __fmul_rn(r.oz, fza));
-                    // s1 = left child's max, s2 = right child's min on the split axis
-                    const float S1 = axis == 0 ? q0.w : (axis == 1 ? q1.x : q1.y);
-                    const float S2 = axis == 0 ? q1.z : (axis == 1 ? q1.w : q2.x);
-                    const float a = __fmul_rn(cur_tmin, dir), b = __fmul_rn(cur_tmax, dir);  // Trixel.cu:149
-                    const float s2 = __fadd_rn(S2, ds);                                      // Trixel.cu:151
-                    bool visit_l, visit_r, left_first;
-                    if (cmp_lt_plus_eps(a, s2)) {  // Trixel.cu:155-161
-                        visit_l = true; left_first = true;
-                        visit_r = cmp_gt_minus_eps(b, s2);
-                    } else {  // Trixel.cu:162-168
-                        const float s1 = s1_plus_eps_plus_ds(S1, ds);
-                        visit_r = true; left_first = false;
-                        visit_l = (b < s1) || (a < s1);
-                    }
-                    // children that the reference would pop: leaves are always intersected, interior
-                    // nodes only after their own box test (Trixel.cu:98,146)
-                    float ltmin, ltmax, rtmin, rtmax;
-                    slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ltmin, ltmax);
-                    slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, rtmin, rtmax);
-                    if (COUNT) c_boxes += (int)visit_l + (int)visit_r;  // children the reference would pop
-                    const bool l_in = box_entered(ltmin, ltmax), r_in = box_entered(rtmin, rtmax);
-                    const bool l_cull = culled(ltmin), r_cull = culled(rtmin);
-                    const bool go_l = visit_l & ((lref < 0) | l_in) & !l_cull;
-                    const bool go_r = visit_r & ((rref < 0) | r_in) & !r_cull;
-                    const int first = left_first ? lref : rref, second = left_first ? rref : lref;
-                    const float f_tmin = left_first ? ltmin : rtmin, f_tmax = left_first ? ltmax : rtmax;
-                    const float s_tmin = left_first ? rtmin : ltmin, s_tmax = left_first ? rtmax : ltmax;
-                    const bool go_first = left_first ? go_l : go_r, go_second = left_first ? go_r : go_l;
-                    if (go_second) { stk_ref[sp] = second; stk_tmin[sp] = s_tmin; stk_tmax[sp] = s_tmax; sp++; }
-                    if (go_first) { cur = first; cur_tmin = f_tmin; cur_tmax = f_tmax; }
-                    else {
-                        bool got = false;
-                        while (sp > 0) {
-                            sp--;
-                            if (!culled(stk_tmin[sp])) { cur = stk_ref[sp]; cur_tmin = stk_tmin[sp]; cur_tmax = stk_tmax[sp]; got = true; break; }
-                        }
-                        if (!got) { have = false; break; }
-                    }
-                }
-                if (!have) break;
-                // ---- leaf: cur == ~triangle --------------------------------------------------------
-                if (COUNT) c_tris++;
-                moller_trumbore(r, P.tris, ~cur, best, id);
-                bool got = false;
-                while (sp > 0) {
-                    sp--;
-                    if (!culled(stk_tmin[sp])) { cur = stk_ref[sp]; cur_tmin = stk_tmin[sp]; cur_tmax = stk_tmax[sp]; got = true; break; }
-                }
-                if (!got) have = false;
-            }
-
-            // ---- shade + write ------------------------------------------------------------------
-            uint32_t color = P.background;
-            if (id >= 0) {
-                color = phong(P, M, r, best, id, cmx, cmy, cmz);
-                if (COUNT) c_hits++;
-            }
-            const long long o = (long long)frame * P.W * P.H + pix;
-            // frames are write-once streams: keep them from displacing the scene in L2
-            if (P.out_bgra) __stcs(P.out_bgra + o, color);
-            if (P.out_ids) __stcs(P.out_ids + o, id);
-        }
-    }
-    if (COUNT) {
-        // warp-reduce then one atomic per counter per warp
-        for (int s = 16; s > 0; s >>= 1) {
-            c_rays += __shfl_down_sync(0xffffffffu, c_rays, s);
-            c_nodes += __shfl_down_sync(0xffffffffu, c_nodes, s);
-            c_boxes += __shfl_down_sync(0xffffffffu, c_boxes, s);
-            c_tris += __shfl_down_sync(0xffffffffu, c_tris, s);
-            c_hits += __shfl_down_sync(0xffffffffu, c_hits, s);
-        }
-        if (lane == 0) {
-            atomicAdd(P.counters + 0, c_rays); atomicAdd(P.counters + 1, c_nodes); atomicAdd(P.counters + 2, c_boxes);
-            atomicAdd(P.counters + 3, c_tris); atomicAdd(P.counters + 4, c_hits);
-        }
-    }
 }
 
 }  // namespace rtb

@@ -1,0 +1,300 @@
+// rtb_render.cuh -- the hot kernel: persistent warps that stream pixels through a lane-level
+// state machine (ray generation -> traversal -> Moller-Trumbore -> Phong -> frame store).
+//
+// Why this shape (ncu evidence in profiles/): the first version rendered one 8x4 pixel tile per
+// warp and ran at 13-14 of 32 active threads per instruction -- rays of one tile need very
+// different numbers of node visits (the meshes have ~14 triangles per pixel), lanes waiting at a
+// leaf idled through the other lanes' interior steps, and finished lanes idled until the slowest
+// ray of the tile was done.  Here a warp owns no tile: every lane that runs out of work is refilled
+// with the next pixel of the warp's current work unit (a Morton-ordered block of a 32x32 image
+// tile, so refills stay spatially coherent), units are fetched with one atomic per warp, and the
+// warp alternates between warp-uniform phases chosen by ballot:
+//     interior step  (fetch one 64-byte node record, test both child boxes, push / descend)
+//     leaf step      (one Moller-Trumbore test)
+//     retire+refill  (Phong + streaming store for finished rays, ray setup for new pixels)
+// The visit ORDER of every ray is exactly the reference's (Trixel.cu:70-170): first-visited wins
+// ties, so hit ids stay bit-identical; distance culling only drops subtrees that cannot contain a
+// closer hit (see `cull_base`).
+#pragma once
+#include "rtb_kernels.cuh"
+
+namespace rtb {
+
+constexpr int kStateEmpty = 0, kStateTraverse = 1, kStateDone = 2;
+
+__device__ __forceinline__ uint32_t compact_even_bits(uint32_t x) {
+    x &= 0x55555555u;
+    x = (x ^ (x >> 1)) & 0x33333333u;
+    x = (x ^ (x >> 2)) & 0x0f0f0f0fu;
+    x = (x ^ (x >> 4)) & 0x00ff00ffu;
+    x = (x ^ (x >> 8)) & 0x0000ffffu;
+    return x;
+}
+
+// ordered "not equal": false when either operand is NaN
+__device__ __forceinline__ bool ordered_ne(float x, float y) { return (x < y) | (x > y); }
+
+// Exact evaluation of everything the fp32 shortcuts of one interior step decide (Trixel.cu:146,
+// 149-168), for the rare inputs they cannot: operands below 2^-28 in magnitude, exact ties, NaN.
+// Returns bit 0 = left child first, bit 1 = second child scheduled, bit 2 = left box entered,
+// bit 3 = right box entered.
+__device__ __noinline__ int interior_decisions_exact(float a, float b, float s2, float S1, float ds, float ltmin, float ltmax,
+                                                     float rtmin, float rtmax) {
+    int out = 0;
+    if (exact_lt_plus_eps(a, s2)) {  // Trixel.cu:155-161: left is popped first, right only if the exit lies beyond s2
+        out |= 1;
+        if (exact_gt_minus_eps(b, s2)) out |= 2;
+    } else {  // Trixel.cu:162-168
+        const float s1 = exact_s1(S1, ds);
+        if ((b < s1) || (a < s1)) out |= 2;
+    }
+    if (box_entered_exact(ltmin, ltmax)) out |= 4;
+    if (box_entered_exact(rtmin, rtmax)) out |= 8;
+    return out;
+}
+
+template <bool CULL, bool COUNT>
+__global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const RenderParams P) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lanemask_lt = (1u << lane) - 1u;
+    unsigned long long c_nodes = 0, c_boxes = 0, c_tris = 0, c_rays = 0, c_hits = 0;
+
+    // Traversal stack: the top entry lives in registers (top_*), deeper entries in local memory.
+    // A pop hands out the register copy at once and re-loads the new top in the background, so the
+    // memory latency of the stack is off the dependent chain.
+    int stk_ref[kStackDepth];
+    float stk_tmin[kStackDepth], stk_tmax[kStackDepth];
+    int top_ref = 0;
+    float top_tmin = 0.0f, top_tmax = 0.0f;
+
+    // ---- per-lane ray state ---------------------------------------------------------------------
+    Ray r;
+    r.dx = r.dy = r.dz = r.ix = r.iy = r.iz = r.fx = r.fy = r.fz = r.ox = r.oy = r.oz = 0.0f;
+    float cmx = 0.0f, cmy = 0.0f, cmz = 0.0f;  // camera-space ray (Camera::pixel_memory::rmd), needed again by Phong
+    float best = 0.0f, slack_abs = 0.0f, cull_base = 0.0f, cur_tmin = 0.0f, cur_tmax = 0.0f;
+    int id = -1, cur = 0, sp = 0, frame = 0, pix = 0;
+    int state = kStateEmpty;
+    bool want_pop = false;
+
+    // ---- warp-uniform unit state ----------------------------------------------------------------
+    const int unit_pixels = 1 << P.unit_shift;
+    const int units_per_tile = (kTile * kTile) >> P.unit_shift;
+    int u_next = unit_pixels;  // nothing loaded yet
+    int u_frame = 0, u_x0 = 0, u_y0 = 0, u_base = 0;
+    int u_rx0 = 0, u_ry0 = 0, u_rx1 = -1, u_ry1 = -1;  // pixel rectangle of the unit's frame that can reach the root box
+    bool exhausted = false;
+
+    // Distance culling that cannot change the answer: a subtree (or leaf) is skipped only if its box
+    // entry lies beyond the current best hit by more than the rounding error the slab arithmetic of
+    // this ray can have (slack_abs) plus a relative margin: tmin > best + slack_abs + rel*(|tmin|+|best|).
+    // cull_base caches the terms that only change with `best`.  Never true for NaN/inf operands.
+    auto set_cull_base = [&]() { cull_base = best + (slack_abs + P.cull_rel * fabsf(best)); };
+    auto culled = [&](float tmin) -> bool { return CULL && (tmin > __fmaf_rn(P.cull_rel, fabsf(tmin), cull_base)); };
+
+    for (;;) {
+        unsigned m_trav = __ballot_sync(0xffffffffu, state == kStateTraverse);
+
+        // ================= traversal: steps until enough lanes have run dry ==========================
+        // (while pixels remain, fall out to retire + refill as soon as no more than t_active lanes are
+        // still traversing; once the work is exhausted, drain)
+        const int keep_active = exhausted ? 0 : P.t_active;
+        while (__popc(m_trav) > keep_active) {
+            // ---- lanes that finished a node or leaf take the stack top ------------------------------
+            if (want_pop) {
+                if (sp == 0) { state = kStateDone; want_pop = false; }
+                else {
+                    if (!culled(top_tmin)) { cur = top_ref; cur_tmin = top_tmin; cur_tmax = top_tmax; want_pop = false; }
+                    sp--;
+                    if (sp > 0) { top_ref = stk_ref[sp - 1]; top_tmin = stk_tmin[sp - 1]; top_tmax = stk_tmax[sp - 1]; }
+                }
+            }
+            const bool ready = (state == kStateTraverse) & !want_pop;
+            const bool at_leaf = ready & (cur < 0);
+            const unsigned m_ready = __ballot_sync(0xffffffffu, ready);
+            const unsigned m_leaf = __ballot_sync(0xffffffffu, at_leaf);
+            if (m_leaf != 0u && (__popc(m_leaf) >= P.t_leaf || m_leaf == m_ready)) {
+                // ---- leaf step: always intersected when popped (Trixel.cu:98) -----------------------
+                if (at_leaf) {
+                    if (COUNT) c_tris++;
+                    if (moller_trumbore(r, P.tris, (int)((unsigned)cur & kRefIndexMask), best, id)) set_cull_base();
+                    want_pop = true;
+                }
+            } else if (ready & !at_leaf) {
+                // ---- interior step: `cur` is a node whose own box test passed ------------------------
+                if (COUNT) c_nodes++;
+                const float4* rec = P.nodes + 4ll * (int)((unsigned)cur & kRefIndexMask);
+                const float4 q0 = ldg4(rec), q1 = ldg4(rec + 1), q2 = ldg4(rec + 2), q3 = ldg4(rec + 3);
+                const int lref = __float_as_int(q3.x), rref = __float_as_int(q3.y);
+                const float S1 = q3.z, S2 = q3.w;  // left child's max / right child's min on the split axis (Trixel.h:353-376)
+                const int axis = (lref >> kRefAxisShift) & 3;
+                // Split-axis components.  Trixel.cu:88-90 forms them as three-term sums with 0/1 flags,
+                // which for finite operands is the selected component up to the sign of a zero; neither
+                // the products below nor the comparisons can see that sign.
+                const float dir = axis == 0 ? r.dx : (axis == 1 ? r.dy : r.dz);
+                const float ds = axis == 0 ? r.ox : (axis == 1 ? r.oy : r.oz);
+                const float a = __fmul_rn(cur_tmin, dir), b = __fmul_rn(cur_tmax, dir);  // Trixel.cu:149
+                const float s2 = __fadd_rn(S2, ds);                                      // Trixel.cu:151
+                // ---- both child boxes (children the reference would pop: leaves are always intersected,
+                // interior nodes only after their own box test, Trixel.cu:98,146) -----------------------
+                float ltmin, ltmax, rtmin, rtmax;
+                slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ltmin, ltmax);
+                slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, rtmin, rtmax);
+                // ---- decisions, fp32 shortcuts of the reference's double-precision comparisons ------------
+                //   (double)a < (double)s2 + EPS  ==  a < s2        } when a != s2, b != s2 and |s2| >= 2^-28:
+                //   (double)b > (double)s2 - EPS  ==  b > s2        } s2 +- 1e-16 stays strictly between s2's float neighbours
+                //   (b < s1) || (a < s1)          ==  min(a,b) < sf   when min(a,b) != sf and |sf| >= 2^-27, sf = fl(S1 + ds):
+                //        s1 = (float)(((double)S1 + EPS) + (double)ds) is sf or its upper neighbour, never below sf
+                //   (double)tmax >= (double)tmin - EPS  ==  tmax >= tmin   when |tmin| >= 2^-28
+                // `decidable` is false for ties, tiny operands and NaN; those lanes take the exact path.
+                const float sf = __fadd_rn(S1, ds);
+                const float mab = fminf(a, b);
+                const bool decidable = (fabsf(s2) >= RTB_TINY) & (fabsf(sf) >= 2.0f * RTB_TINY) & ordered_ne(a, s2) & ordered_ne(b, s2) &
+                                       ordered_ne(mab, sf) & (fabsf(ltmin) >= RTB_TINY) & (fabsf(rtmin) >= RTB_TINY);
+                bool left_first = a < s2;
+                bool visit_second = left_first ? (b > s2) : (mab < sf);
+                bool l_in = (ltmax >= ltmin) & (ltmin > -RTB_EPS_UP);
+                bool r_in = (rtmax >= rtmin) & (rtmin > -RTB_EPS_UP);
+                if (!decidable) {
+                    const int ex = interior_decisions_exact(a, b, s2, S1, ds, ltmin, ltmax, rtmin, rtmax);
+                    left_first = (ex & 1) != 0; visit_second = (ex & 2) != 0; l_in = (ex & 4) != 0; r_in = (ex & 8) != 0;
+                }
+                if (COUNT) c_boxes += 1 + (int)visit_second;
+                const bool l_ok = ((lref < 0) | l_in) & !culled(ltmin);
+                const bool r_ok = ((rref < 0) | r_in) & !culled(rtmin);
+                const bool go_first = left_first ? l_ok : r_ok;
+                const bool go_second = (left_first ? r_ok : l_ok) & visit_second;
+                if (go_second) {
+                    if (sp > 0) { stk_ref[sp - 1] = top_ref; stk_tmin[sp - 1] = top_tmin; stk_tmax[sp - 1] = top_tmax; }
+                    top_ref = left_first ? rref : lref;
+                    top_tmin = left_first ? rtmin : ltmin;
+                    top_tmax = left_first ? rtmax : ltmax;
+                    sp++;
+                }
+                cur = left_first ? lref : rref;
+                cur_tmin = left_first ? ltmin : rtmin;
+                cur_tmax = left_first ? ltmax : rtmax;
+                want_pop = !go_first;
+            }
+            m_trav = __ballot_sync(0xffffffffu, state == kStateTraverse);
+        }
+
+        // ================= retire: Phong + store for finished rays ===================================
+        if (state == kStateDone) {
+            uint32_t color = P.background;
+            if (id >= 0) {
+                color = phong(P, P.frames + (long long)kFrameStride * frame, r, best, id, cmx, cmy, cmz);
+                if (COUNT) c_hits++;
+            }
+            const long long o = (long long)frame * P.W * P.H + pix;
+            // frames are write-once streams: keep them from displacing the scene in L2
+            if (P.out_bgra) __stcs(P.out_bgra + o, color);
+            if (P.out_ids) __stcs(P.out_ids + o, id);
+            state = kStateEmpty;
+        }
+        const unsigned m_empty = ~m_trav;
+
+        // ================= refill: next pixels of the warp's unit ====================================
+        if (!exhausted && u_next >= unit_pixels) {
+            unsigned long long uid = 0;
+            if (lane == 0) uid = atomicAdd(P.work_counter, 1ull);
+            uid = __shfl_sync(0xffffffffu, uid, 0);
+            if ((long long)uid >= P.total_items) {
+                exhausted = true;
+            } else {
+                const long long per_frame = (long long)P.my_tiles * units_per_tile;
+                u_frame = (int)((long long)uid / per_frame);
+                const int rem = (int)((long long)uid - (long long)u_frame * per_frame);
+                const int tile = P.tile_first + (rem / units_per_tile) * P.tile_stride;
+                u_base = (rem % units_per_tile) << P.unit_shift;
+                u_x0 = (tile % P.tiles_x) * kTile;
+                u_y0 = (tile / P.tiles_x) * kTile;
+                u_next = 0;
+                const float* __restrict__ F = P.frames + (long long)kFrameStride * u_frame;
+                u_rx0 = __float_as_int(__ldg(F + 12)); u_ry0 = __float_as_int(__ldg(F + 13));
+                u_rx1 = __float_as_int(__ldg(F + 14)); u_ry1 = __float_as_int(__ldg(F + 15));
+            }
+        }
+        if (exhausted) {
+            if (m_trav == 0u) break;  // nothing in flight, nothing left to fetch
+        } else {
+            const int slot = __popc(m_empty & lanemask_lt);
+            const int avail = unit_pixels - u_next;
+            if (((m_empty >> lane) & 1u) && slot < avail) {
+                const uint32_t K = (uint32_t)(u_base + u_next + slot);  // Morton ordinal inside the 32x32 tile
+                const int px = u_x0 + (int)compact_even_bits(K), py = u_y0 + (int)compact_even_bits(K >> 1);
+                if (px < P.W && py < P.H) {
+                    if (px < u_rx0 || px > u_rx1 || py < u_ry0 || py > u_ry1) {
+                        // outside the (conservatively enlarged) projection of the root box: the ray cannot
+                        // pass the root's box test (Trixel.cu:146), the pixel is background
+                        const long long o = (long long)u_frame * P.W * P.H + (long long)py * P.W + px;
+                        if (P.out_bgra) __stcs(P.out_bgra + o, P.background);
+                        if (P.out_ids) __stcs(P.out_ids + o, -1);
+                        if (COUNT) { c_rays++; c_boxes++; }
+                    } else {
+                        frame = u_frame;
+                        pix = py * P.W + px;
+                        const float* __restrict__ M = P.frames + (long long)kFrameStride * frame;
+                        // ---- primary ray, Camera.cu:103-104 (row 0 = bottom) --------------------------
+                        const float fxp = (float)px, fyp = (float)py;
+                        cmx = __fadd_rn(__fadd_rn(P.n_mod[0], __fmul_rn(P.u_mod[0], fxp)), __fmul_rn(P.v_mod[0], fyp));
+                        cmy = __fadd_rn(__fadd_rn(P.n_mod[1], __fmul_rn(P.u_mod[1], fxp)), __fmul_rn(P.v_mod[1], fyp));
+                        cmz = __fadd_rn(__fadd_rn(P.n_mod[2], __fmul_rn(P.u_mod[2], fxp)), __fmul_rn(P.v_mod[2], fyp));
+                        normalize21(cmx, cmy, cmz);
+                        // ---- into object space, Trixel.cu:60-66 (sign dance kept for -0 fidelity) ------
+                        const float m0 = __ldg(M + 0), m1 = __ldg(M + 1), m2 = __ldg(M + 2), m3 = __ldg(M + 3);
+                        const float m4 = __ldg(M + 4), m5 = __ldg(M + 5), m6 = __ldg(M + 6), m7 = __ldg(M + 7);
+                        const float m8 = __ldg(M + 8), m9 = __ldg(M + 9), m10 = __ldg(M + 10), m11 = __ldg(M + 11);
+                        r.ox = m3; r.oy = m7; r.oz = m11;
+                        r.dx = __fmul_rn(-1.0f, __fadd_rn(__fadd_rn(__fmul_rn(m0, -cmx), __fmul_rn(m1, -cmy)), __fmul_rn(m2, -cmz)));
+                        r.dy = __fmul_rn(-1.0f, __fadd_rn(__fadd_rn(__fmul_rn(m4, -cmx), __fmul_rn(m5, -cmy)), __fmul_rn(m6, -cmz)));
+                        r.dz = __fmul_rn(-1.0f, __fadd_rn(__fadd_rn(__fmul_rn(m8, -cmx), __fmul_rn(m9, -cmy)), __fmul_rn(m10, -cmz)));
+                        r.ix = __frcp_rn(r.dx); r.iy = __frcp_rn(r.dy); r.iz = __frcp_rn(r.dz);
+                        r.fx = __fdiv_rn(r.ox, r.dx); r.fy = __fdiv_rn(r.oy, r.dy); r.fz = __fdiv_rn(r.oz, r.dz);
+                        best = P.draw_distance;  // Trixel.cu:47
+                        id = -1;
+                        sp = 0;
+                        want_pop = false;
+                        if (COUNT) c_rays++;
+                        if (CULL) {
+                            const float bx = fmaxf(fabsf(P.root_box[0]), fabsf(P.root_box[3]));
+                            const float by = fmaxf(fabsf(P.root_box[1]), fabsf(P.root_box[4]));
+                            const float bz = fmaxf(fabsf(P.root_box[2]), fabsf(P.root_box[5]));
+                            const float e = fmaxf(fmaxf(bx * fabsf(r.ix) + fabsf(r.fx), by * fabsf(r.iy) + fabsf(r.fy)), bz * fabsf(r.iz) + fabsf(r.fz));
+                            slack_abs = e * 9.5367431640625e-07f;  // 8 * 2^-23
+                            set_cull_base();
+                        }
+                        cur = P.root_ref;
+                        if (P.root_ref < 0) {
+                            // single-triangle mesh: the root is a leaf, tested unconditionally (Trixel.cu:98)
+                            cur_tmin = 0.0f; cur_tmax = 0.0f;
+                            state = kStateTraverse;
+                            if (COUNT) c_boxes++;
+                        } else {
+                            slab(r, P.root_box[0], P.root_box[1], P.root_box[2], P.root_box[3], P.root_box[4], P.root_box[5], cur_tmin, cur_tmax);
+                            if (COUNT) c_boxes++;
+                            state = box_entered_exact(cur_tmin, cur_tmax) ? kStateTraverse : kStateDone;
+                        }
+                    }
+                }
+            }
+            const int want = __popc(m_empty);
+            u_next += want < avail ? want : avail;
+        }
+    }
+
+    if (COUNT) {
+        for (int s = 16; s > 0; s >>= 1) {
+            c_rays += __shfl_down_sync(0xffffffffu, c_rays, s);
+            c_nodes += __shfl_down_sync(0xffffffffu, c_nodes, s);
+            c_boxes += __shfl_down_sync(0xffffffffu, c_boxes, s);
+            c_tris += __shfl_down_sync(0xffffffffu, c_tris, s);
+            c_hits += __shfl_down_sync(0xffffffffu, c_hits, s);
+        }
+        if (lane == 0) {
+            atomicAdd(P.counters + 0, c_rays); atomicAdd(P.counters + 1, c_nodes); atomicAdd(P.counters + 2, c_boxes);
+            atomicAdd(P.counters + 3, c_tris); atomicAdd(P.counters + 4, c_hits);
+        }
+    }
+}
+
+}  // namespace rtb

@@ -16,14 +16,27 @@ for r in rows:
         kernels.append(cur)
     if cur is not None:
         cur.append(r)
-k = kernels[which]
+# one block per (source file, kernel); merge all blocks of the kernel launch `which`
+names = []
+for b in kernels:
+    fn = next((r[1] for r in b if r and r[0] == "Function Name"), "?")
+    if fn not in names:
+        names.append(fn)
+sel = names[which] if which < len(names) else names[0]
+k = [r for b in kernels if next((r[1] for r in b if r and r[0] == "Function Name"), "?") == sel for r in
+     ([["FILE", next((r[1] for r in b if r and r[0] == "File Path"), "?")]] + b)]
 hdr = next(r for r in k if r and r[0] == "Line No")
 ix = {name: i for i, name in enumerate(hdr)}
 lines = []
 tot_inst = tot_thr = tot_samp = 0
+curfile = ""
 for r in k:
+    if r and r[0] == "FILE":
+        curfile = r[1].split("/")[-1].replace("rtb_", "").replace(".cuh", "")
+        continue
     if len(r) != len(hdr) or r[0] in ("Line No", ""):
         continue
+    r = list(r); r[0] = curfile[:7] + ":" + r[0]
     try:
         inst = int(r[ix["Instructions Executed"]]); thr = int(r[ix["Thread Instructions Executed"]]); samp = int(r[ix["# Samples"]])
     except ValueError:
@@ -34,4 +47,4 @@ for r in k:
 print("kernel %d: warp-inst %.3fG thread-inst %.3fG avg-threads %.1f samples %d" % (which, tot_inst / 1e9, tot_thr / 1e9, tot_thr / max(tot_inst, 1), tot_samp))
 for samp, inst, thr, ln, src, st in sorted(lines, reverse=True)[:top]:
     top_st = ",".join("%s:%d" % kv for kv in sorted(st.items(), key=lambda kv: -kv[1])[:3])
-    print("%5.1f%% samp %5.1f%% inst  thr/inst %4.1f  L%-4s %-70s %s" % (100.0 * samp / tot_samp, 100.0 * inst / tot_inst, thr / max(inst, 1), ln, src.strip()[:70], top_st))
+    print("%5.1f%% samp %5.1f%% inst  thr/inst %4.1f  L%-12s %-70s %s" % (100.0 * samp / tot_samp, 100.0 * inst / tot_inst, thr / max(inst, 1), ln, src.strip()[:70], top_st))
