@@ -12,6 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librtb.so")
+DRIVER = os.path.join(HERE, "rtb_render")  # headless driver (csrc/rtb_render_main.cpp)
 SOURCES = ["rtb_api.cu", "rtb_host.cpp"]
 HEADERS = ["rtb_host.hpp", "rtb_kernels.cuh", "rtb_render.cuh", os.path.join("..", "..", "include", "rtb.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
@@ -26,10 +27,10 @@ def nvcc_path():
 
 
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(DRIVER):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [__file__]
+    t = min(os.path.getmtime(LIB), os.path.getmtime(DRIVER))
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS + ["rtb_framework.hpp", "rtb_render_main.cpp"]] + [__file__]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -45,6 +46,15 @@ def build(force=False, verbose=False):
         sys.stderr.write(r.stdout)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed, see %s" % log)
+    # the headless C++ driver on top of the C ABI (host code only)
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", os.path.join(CSRC, "rtb_render_main.cpp"), "-o", DRIVER, "-L", HERE, "-lrtb",
+           "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    with open(log, "a") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("g++ failed for rtb_render, see %s" % log)
     return LIB
 
 

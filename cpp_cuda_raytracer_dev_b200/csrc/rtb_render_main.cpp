@@ -1,0 +1,117 @@
+// rtb_render_main.cpp -- headless Linux driver: the reference's WinMain.cpp:69-237 without the window.
+//
+//   rtb_render --mesh FILE|geodesic:NU [--mode 0|1|2|-1] [--res WxH] [--frames N] [--zoom K]
+//              [--rotate X,Y,Z,W] [--out PREFIX] [--cam px,py,pz,lx,ly,lz,ux,uy,uz] [--sweep]
+//
+// Same call sequence as the reference app: Camera(...) -> read_ply -> colour table -> Trixel ->
+// set_sorted_voxels -> create_kd -> Object -> add_object -> per frame { [transform]; render;
+// color_pixels(PHONG); present; color_pixels(SET) }.  "Present" writes PREFIX_NNNN.ppm and
+// PREFIX_NNNN.ids (raw int32 hit ids) instead of StretchDIBits.  --sweep renders all frames through the
+// batched rtb_render_sweep call instead of the frame loop.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rtb_framework.hpp"
+
+using namespace rtbfw;
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+int main(int argc, char** argv) {
+    std::string mesh = "geodesic:64", out;
+    int mode = 0, W = 960, H = 540, frames = 1, zoom = 0;
+    bool sweep = false;
+    float quat[4] = {0.0f, 0.09950371902099893f, 0.0f, 0.9950371902099893f};  // WinMain.cpp:187 (R key)
+    float cam[9] = {0.0f, 0.10f, -1.0f, 0.0f, 0.10f, 0.0f, 0.0f, 1.0f, 0.0f};  // WinMain.cpp:71-73
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto next = [&]() { return i + 1 < argc ? argv[++i] : ""; };
+        if (a == "--mesh") mesh = next();
+        else if (a == "--mode") mode = std::atoi(next());
+        else if (a == "--res") std::sscanf(next(), "%dx%d", &W, &H);
+        else if (a == "--frames") frames = std::atoi(next());
+        else if (a == "--zoom") zoom = std::atoi(next());
+        else if (a == "--out") out = next();
+        else if (a == "--sweep") sweep = true;
+        else if (a == "--rotate") std::sscanf(next(), "%f,%f,%f,%f", &quat[0], &quat[1], &quat[2], &quat[3]);
+        else if (a == "--cam") std::sscanf(next(), "%f,%f,%f,%f,%f,%f,%f,%f,%f", &cam[0], &cam[1], &cam[2], &cam[3], &cam[4], &cam[5], &cam[6], &cam[7], &cam[8]);
+        else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
+    }
+    if (rtb_device_count() < 1) { std::fprintf(stderr, "rtb_render: no CUDA device (there is no CPU fallback)\n"); return 3; }
+
+    const float ar = (float)W / (float)H;  // WinMain.cpp:29,67
+    Camera* main_cam = new Camera(W, H, ar * 0.024f, 0.024f, 0.055f, cam[0], cam[1], cam[2], cam[3], cam[4], cam[5], cam[6], cam[7], cam[8]);
+
+    double t0 = now_s();
+    T_fp* points_for_trixels = nullptr;
+    T_uint tot_num_trixels = 0;
+    int rc;
+    if (mesh.rfind("geodesic:", 0) == 0) {
+        const float center[3] = {0.0f, 0.1f, 0.0f};
+        rc = rtb_mesh_geodesic(std::atoi(mesh.c_str() + 9), 0.08f, center, 0.05f, 1234u, &points_for_trixels, &tot_num_trixels);
+    } else {
+        rc = read_ply(mesh.c_str(), &points_for_trixels, &tot_num_trixels, (u8)(mode < 0 ? 255 : mode));
+    }
+    if (rc != 0) { std::fprintf(stderr, "mesh: %s\n", rtb_last_error()); return 1; }
+    Color color_for_trixels;  // WinMain.cpp:114-121
+    std::vector<Color::radiance> rad(tot_num_trixels, Color::radiance{0.1f, 0.55f, 0.20f});
+    color_for_trixels.rad = rad.data();
+    std::printf("Time to Read Tree: %f seconds\n\t\t primitives: %u\n\n", now_s() - t0, tot_num_trixels);
+
+    t0 = now_s();
+    Trixel* trixel_list = new Trixel(tot_num_trixels, points_for_trixels, &color_for_trixels);
+    trixel_list->set_sorted_voxels(nullptr, tot_num_trixels);
+    if (trixel_list->create_kd() != 0) { std::fprintf(stderr, "create_kd: %s\n", rtb_last_error()); return 1; }
+    std::printf("Total Time to build tree: %f seconds\n", now_s() - t0);
+    Object* obj1 = new Object(trixel_list);
+    if (main_cam->add_object(obj1) != 0) { std::fprintf(stderr, "add_object: %s\n", rtb_last_error()); return 1; }
+
+    Input input;
+    for (int k = 0; k < zoom; k++) {  // W key, WinMain.cpp:190-193
+        input.set_quat(main_cam->o_prop.n.x, main_cam->o_prop.n.y, main_cam->o_prop.n.z, 0.005f);
+        obj1->transform(&input, TRANSLATE_Z);
+    }
+    auto present = [&](int frame, const uint32_t* c, const int32_t* id) {
+        if (out.empty()) return;
+        char name[64];
+        std::snprintf(name, sizeof name, "_%04d", frame);
+        write_ppm(out + name + ".ppm", c, (uint32_t)W, (uint32_t)H);
+        write_raw_ids(out + name + ".ids", id, (uint64_t)W * H);
+    };
+
+    t0 = now_s();
+    if (sweep) {
+        std::vector<float> ops(5 * (size_t)frames);
+        for (int f = 0; f < frames; f++) { ops[5 * f] = f ? (float)ROTATE_TRI_PY : 0.0f; std::memcpy(&ops[5 * f + 1], quat, sizeof quat); }
+        std::vector<uint32_t> colors((size_t)frames * W * H);
+        std::vector<int32_t> ids((size_t)frames * W * H);
+        if (rtb_render_sweep(obj1->handle, main_cam->handle, frames, 1, ops.data(), RTB_RENDER_DEFAULT, colors.data(), ids.data()) != 0) {
+            std::fprintf(stderr, "render_sweep: %s\n", rtb_last_error());
+            return 1;
+        }
+        const double dt = now_s() - t0;
+        for (int f = 0; f < frames; f++) present(f, colors.data() + (size_t)f * W * H, ids.data() + (size_t)f * W * H);
+        std::printf("Resolution: %d x %d\nFPS: %f (sweep of %d frames, %.1f Mrays/s)\n", W, H, frames / dt, frames, frames * (double)W * H / dt / 1e6);
+    } else {
+        main_cam->color_pixels(SET_COLOR_TAG);
+        for (int f = 0; f < frames; f++) {
+            if (f) {  // R key held down, WinMain.cpp:186-189
+                input.set_quat(quat[0], quat[1], quat[2], quat[3]);
+                obj1->transform(&input, ROTATE_TRI_PY);
+            }
+            obj1->render(main_cam);                   // WinMain.cpp:212
+            main_cam->color_pixels(PHONG_COLOR_TAG);  // WinMain.cpp:213
+            present(f, main_cam->h_color.c, main_cam->h_color.id);
+            main_cam->color_pixels(SET_COLOR_TAG);    // WinMain.cpp:237
+        }
+        const double dt = now_s() - t0;
+        std::printf("Resolution: %d x %d\nFPS: %f (frame loop of %d frames incl. PPM output)\n", W, H, frames / dt, frames);
+    }
+    delete obj1; delete trixel_list; delete main_cam;
+    rtb_free(points_for_trixels);
+    return 0;
+}

@@ -1,0 +1,132 @@
+"""Host side of the product (mesh load, tree build, camera, transform; no GPU needed) against the
+oracle, and the C-ABI surface of librtb.so."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from common import ROOT, WALLS_CAMERA, cam12, cam_kwargs, golden, hex32, mesh_path
+
+
+def test_library_exports_every_declared_symbol(rtb):
+    hdr = open(os.path.join(ROOT, "include", "rtb.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rtb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = ctypes.CDLL(rtb.LIB_PATH)
+    missing = [name for name in sorted(declared) if not hasattr(lib, name)]
+    assert not missing, missing
+    assert declared == set(rtb.EXPORTS)
+    assert rtb.lib.rtb_version().startswith(b"rtb")
+
+
+def test_status_codes_not_exceptions(rtb):
+    """Reference convention: status code + message, never throw."""
+    p, n = ctypes.c_void_p(), ctypes.c_uint32()
+    rc = rtb.lib.rtb_read_ply(b"/nonexistent/file.ply", 0, ctypes.byref(p), ctypes.byref(n))
+    assert rc == 2 and b"cannot read" in rtb.lib.rtb_last_error()
+    assert rtb.lib.rtb_mesh_build_tree(None) == 1
+    with pytest.raises(rtb.RtbError):
+        rtb.read_ply("/nonexistent/file.ply", 0)
+
+
+def test_ply_loader_matches_oracle(rtb, orc, tmp_path):
+    for name, mode in (("rabbit_70k.ply", 1), ("3_walls.ply", -1)):
+        path = mesh_path(name)
+        if path is None:
+            continue
+        assert np.array_equal(rtb.read_ply(path, mode).view(np.uint32), orc.read_ply(path, mode).view(np.uint32))
+    # the four column modes and both face kinds on a synthetic file
+    verts = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0.5, 0.5, 1.25]], np.float32)
+    for mode, extra in ((0, 0), (1, 2), (2, 3)):
+        f = tmp_path / ("m%d.ply" % mode)
+        with open(f, "w") as fh:
+            fh.write("ply\nformat ascii 1.0\nelement vertex 5\nelement face 3\nend_header\n")
+            for v in verts:
+                fh.write(" ".join(["%.9g" % c for c in v] + ["0.5"] * extra) + "\n")
+            fh.write("4 0 1 2 3\n3 0 1 4\n3 2 3 4\n")
+        got = rtb.read_ply(str(f), mode)
+        assert np.array_equal(got.view(np.uint32), orc.read_ply(str(f), mode).view(np.uint32))
+        assert got.shape == (4, 9)
+        assert got[0].tolist() == [0, 0, 0, 1, 0, 0, 1, 1, 0] and got[1].tolist() == [0, 0, 0, 1, 1, 0, 0, 1, 0]   # quad -> (A,B,C),(A,C,D)
+        assert got[2].tolist() == [0.5, 0.5, 1.25, 0, 0, 0, 1, 0, 0]                                               # "3 a b c" stored (c,a,b)
+    # write_ply round trip
+    pts = rtb.geodesic_mesh(3)
+    out = tmp_path / "rt.ply"
+    rtb.write_ply(str(out), pts)
+    assert np.array_equal(rtb.read_ply(str(out), 0).view(np.uint32), pts.view(np.uint32))
+    assert np.array_equal(orc.read_ply(str(out), 0).view(np.uint32), pts.view(np.uint32))
+
+
+def tree_equal(t, on):
+    leaf = on["is_leaf"] == 1
+    ok = np.array_equal(t["left"], np.where(leaf, -1, on["left"]).astype(np.int32))
+    ok &= np.array_equal(t["right"], np.where(leaf, -1, on["right"]).astype(np.int32))
+    ok &= np.array_equal(t["tri"], np.where(leaf, on["tri"], -1).astype(np.int32))
+    ok &= np.array_equal(t["cut_flag"], on["cut_flag"])
+    ob = np.stack([on[k] for k in ("x0", "x1", "y0", "y1", "z0", "z1")], 1)
+    ok &= np.array_equal(t["bounds"].view(np.uint32), ob.view(np.uint32))
+    ok &= np.array_equal(t["s1"][~leaf].view(np.uint32), on["s1"][~leaf].view(np.uint32))
+    ok &= np.array_equal(t["s2"][~leaf].view(np.uint32), on["s2"][~leaf].view(np.uint32))
+    return bool(ok)
+
+
+@pytest.mark.parametrize("case", ["ico16", "ico40", "one", "two", "seven", "ties", "bunny", "walls"])
+def test_tree_build_is_bit_identical_to_oracle(rtb, orc, case):
+    if case == "bunny":
+        path = mesh_path("rabbit_70k.ply")
+        if path is None:
+            pytest.skip("rabbit_70k.ply not available")
+        pts = rtb.read_ply(path, 1)
+    elif case == "walls":
+        path = mesh_path("3_walls.ply")
+        if path is None:
+            pytest.skip("3_walls.ply not available")
+        pts = rtb.read_ply(path, -1)
+    elif case == "ties":   # many equal keys: the (key, descending index) order decides every split
+        base = rtb.geodesic_mesh(2)
+        pts = np.concatenate([base, base, base[::-1]])
+    else:
+        pts = {"ico16": rtb.geodesic_mesh(16), "ico40": rtb.geodesic_mesh(40), "one": rtb.geodesic_mesh(2)[:1],
+               "two": rtb.geodesic_mesh(2)[:2], "seven": rtb.geodesic_mesh(2)[:7]}[case]
+    m = rtb.Trixel(pts, require_device=False)
+    m.create_kd()
+    assert tree_equal(m.tree(), orc.build_tree(pts))
+    assert m.num_voxels == 2 * len(pts) - 1
+    m.close()
+
+
+def test_camera_basis_matches_oracle_and_golden(rtb, orc):
+    for key, rec in golden()["camera"].items():
+        W, H = (int(v) for v in key.split("_")[0].split("x"))
+        c = rec["cam12"]
+        cam = rtb.Camera(W, H, c[0], c[1], c[2], c[3:6], c[6:9], c[9:12], require_device=False)
+        assert hex32(cam.basis()) == rec["basis"], key
+        cam.close()
+
+
+def test_geodesic_mesh_is_deterministic(rtb):
+    a, b = rtb.geodesic_mesh(12), rtb.geodesic_mesh(12)
+    assert a.shape == (20 * 144, 9) and np.array_equal(a, b)
+    assert not np.array_equal(a, rtb.geodesic_mesh(12, seed=5))
+    r = np.linalg.norm(a.reshape(-1, 3) - np.array([0.0, 0.1, 0.0]), axis=1)
+    assert 0.07 < r.min() and r.max() < 0.09
+
+
+def test_render_without_gpu_fails_loudly(rtb):
+    """No CPU fallback: on a box without a usable device the render path must report an error."""
+    if rtb.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    pts = rtb.geodesic_mesh(2)
+    with pytest.raises(rtb.RtbError):
+        rtb.Trixel(pts)                      # device upload fails -> status code -> exception in the binding
+    m = rtb.Trixel(pts, require_device=False)
+    m.create_kd()
+    cam = rtb.Camera(64, 48, **cam_kwargs(64, 48), require_device=False)
+    obj = rtb.Object(m)
+    with pytest.raises(rtb.RtbError):
+        cam.add_object(obj)
+    with pytest.raises(rtb.RtbError):
+        obj.render(cam)

@@ -1,0 +1,92 @@
+"""The N>1 path on CPU: two ranks over gloo shard a frame by interleaved tiles and a sweep by frame
+blocks, gather to rank 0 and reassemble; the result must be bit-identical to the single-rank frame.
+The per-rank renderer here is the oracle restricted to the rank's share (the GPU kernel itself is
+covered by tests/test_gpu_parity.py::test_tile_partition_is_bit_identical)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from common import cam12
+
+W, H, WORLD, FRAMES = 200, 100, 2, 3
+R_KEY = (0.0, 0.09950371902099893, 0.0, 0.9950371902099893)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, port, result_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(WORLD))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    import cpp_cuda_raytracer_dev_b200 as rtb
+    from cpp_cuda_raytracer_dev_b200 import shard
+    from oracle import orc
+    pts = rtb.geodesic_mesh(8)
+    scene = orc.Scene(pts, W, H, cam12(W, H))
+    for _ in range(110):
+        scene.transform(32, 0.0, 0.0, 1.0, 0.005)
+
+    # ---- one frame, sharded by tiles ---------------------------------------------------------------
+    ids, bgra = scene.render()
+    mask = shard.tile_mask(W, H, rank, WORLD)
+    my_ids = np.where(mask, ids, -7).astype(np.int64)          # what this rank's GPU would have written
+    my_col = np.where(mask, bgra, 0xdeadbeef).astype(np.int64)
+    got_ids = [torch.empty(W * H, dtype=torch.int64) for _ in range(WORLD)] if rank == 0 else None
+    got_col = [torch.empty(W * H, dtype=torch.int64) for _ in range(WORLD)] if rank == 0 else None
+    dist.gather(torch.from_numpy(my_ids), got_ids, dst=0)
+    dist.gather(torch.from_numpy(my_col), got_col, dst=0)
+    ok = True
+    if rank == 0:
+        full_ids = shard.compose_tiles([t.numpy() for t in got_ids], W, H)
+        full_col = shard.compose_tiles([t.numpy() for t in got_col], W, H)
+        ok &= np.array_equal(full_ids, ids) and np.array_equal(full_col, bgra.astype(np.int64))
+        ok &= bool((ids >= 0).sum() > 1000)
+
+    # ---- a sweep, sharded by frame blocks -----------------------------------------------------------
+    mats = [scene.matrix()]
+    for _ in range(WORLD * FRAMES - 1):
+        scene.transform(10, *R_KEY)
+        mats.append(scene.matrix())
+    first, last = shard.frame_block(0, rank, WORLD, FRAMES)
+    mine = np.stack([scene.render(m12=mats[f])[0] for f in range(first, last)])
+    got = [torch.empty((FRAMES, W * H), dtype=torch.int64) for _ in range(WORLD)] if rank == 0 else None
+    dist.gather(torch.from_numpy(mine), got, dst=0)
+    if rank == 0:
+        sweep = torch.cat(got).numpy()
+        for f in range(WORLD * FRAMES):
+            ok &= np.array_equal(sweep[f], scene.render(m12=mats[f])[0])
+        with open(result_path, "w") as fh:
+            fh.write("ok" if ok else "mismatch")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_gloo_tiles_and_frames(tmp_path):
+    result = tmp_path / "result.txt"
+    mp.spawn(_worker, args=(_free_port(), str(result)), nprocs=WORLD, join=True)
+    assert result.read_text() == "ok"
+
+
+def test_tile_partition_covers_every_pixel_once():
+    from cpp_cuda_raytracer_dev_b200 import shard
+    for (w, h) in ((960, 540), (3840, 2160), (333, 211), (31, 33), (1, 1)):
+        for world in (1, 2, 3, 4, 8):
+            cover = np.zeros(w * h, np.int32)
+            for r in range(world):
+                cover += shard.tile_mask(w, h, r, world)
+            assert (cover == 1).all()
+            counts = [int(shard.tile_mask(w, h, r, world).sum()) for r in range(world)]
+            if w * h > 100000:
+                assert max(counts) - min(counts) <= 0.05 * max(counts)   # balanced to within a few tiles
+    blocks = [shard.frame_block(s, r, 4, 60) for s in range(3) for r in range(4)]
+    assert blocks == [(k * 60, k * 60 + 60) for k in range(12)]
