@@ -13,9 +13,13 @@ A "step" is one pass of the hot path over one batch: FRAMES_PER_STEP consecutive
 orbit (default 60, so 10 steps = the 600-frame orbit).  `value` = Mrays/s with everything resident
 in HBM (kernel-only, CUDA events on the launching stream); `e2e` = the same metric through the C-ABI
 call rtb_render_sweep with HOST buffers: transform ops in, every frame's colour + hit-id buffer out
-to pinned host memory inside the timed region.  N > 1 (torchrun): frames are sharded round-robin in
-blocks over the ranks (weak scaling: every rank renders FRAMES_PER_STEP frames per step), the scene
-is replicated, and the finished frames are gathered to rank 0 with NCCL on a side stream.
+to pinned host memory inside the timed region.  N > 1 (torchrun), scene replicated on every rank:
+  --shard frames (default): the sweep is dealt out in blocks of FRAMES_PER_STEP frames per rank and
+      step (weak scaling); frames are independent units, so there is NO data-path collective --
+      every rank delivers its own frames (BASELINE.json: "for the animation sweep, by frames");
+  --shard tiles: every frame is split into interleaved 32x32 tiles (tile t -> rank t % N), a step is
+      N * FRAMES_PER_STEP frames (weak scaling), and the finished tiles are gathered to rank 0 with
+      NCCL on a side stream and reassembled there -- the path's one real exchange step.
 
 `--impl reference` times the reference's own kernels compiled for the host (oracle/_ref, falling
 back to the C port) on a bounded sample of the same workload with all host threads.
@@ -222,18 +226,35 @@ def run_ours(args):
     for g in range(1, len(mats)):
         mats[g] = obj.transform_host(rtb.R_KEY_QUAT, rtb.ROTATE_TRI_PY)
 
+    tiles_mode = world > 1 and args.shard == "tiles"
+    if tiles_mode:  # the NCCL gather runs beside the persistent render kernel: leave it a few SMs
+        os.environ.setdefault("RTB_RESERVE_SMS", "8")
+    FS = F * world if tiles_mode else F  # frames a rank touches per step
+
     def my_mats(step):
+        if tiles_mode:  # every rank renders its tiles of all N*F frames of the step
+            return mats[step * world * F:(step + 1) * world * F]
         b = (step * world + rank) * F
         return mats[b:b + F]
 
     stream = torch.cuda.Stream()
     side = torch.cuda.Stream()
-    d_col = [torch.empty(F * P, dtype=torch.int32, device="cuda") for _ in range(2)]
-    d_ids = [torch.empty(F * P, dtype=torch.int32, device="cuda") for _ in range(2)]
-    gather_col = gather_ids = None
-    if world > 1 and rank == 0:
-        gather_col = [torch.empty(F * P, dtype=torch.int32, device="cuda") for _ in range(world)]
-        gather_ids = [torch.empty(F * P, dtype=torch.int32, device="cuda") for _ in range(world)]
+    # per-frame elements of this rank's output: the whole frame, or (tiles mode) only its own tiles in
+    # the compact tile-major exchange format
+    PE = cam.tile_major_elements(world) if tiles_mode else P
+    d_col = [torch.empty(FS * PE, dtype=torch.int32, device="cuda") for _ in range(2)]
+    d_ids = [torch.empty(FS * PE, dtype=torch.int32, device="cuda") for _ in range(2)]
+    gather_col = gather_ids = final_col = final_ids = None
+    if tiles_mode and rank == 0:
+        gather_col = [[torch.empty(FS * PE, dtype=torch.int32, device="cuda") for _ in range(world)] for _ in range(2)]
+        gather_ids = [[torch.empty(FS * PE, dtype=torch.int32, device="cuda") for _ in range(world)] for _ in range(2)]
+        final_col = torch.empty(FS * P, dtype=torch.int32, device="cuda")
+        final_ids = torch.empty(FS * P, dtype=torch.int32, device="cuda")
+
+    def compose(slot):
+        if tiles_mode and rank == 0:
+            cam.compose_tiles_device_async(FS, [t.data_ptr() for t in gather_col[slot]], final_col.data_ptr(), stream.cuda_stream)
+            cam.compose_tiles_device_async(FS, [t.data_ptr() for t in gather_ids[slot]], final_ids.data_ptr(), stream.cuda_stream)
     flush = torch.empty(160 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     region_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
 
@@ -257,21 +278,29 @@ def run_ours(args):
         with torch.cuda.stream(stream):
             flush.fill_(step & 0xff)  # L2 flush between timed iterations (inside the timed region, outside the kernel's event pair)
             if gather_done[slot] is not None:
-                stream.wait_event(gather_done[slot])  # the slot's previous gather must have drained
+                # the slot's previous gather must have drained; rank 0 then reassembles those frames here,
+                # on the render stream, where the scatter kernel has the whole GPU (beside the persistent
+                # render kernel it would only get the SMs that kernel leaves free)
+                stream.wait_event(gather_done[slot])
+                compose(slot)
             ev[step][0].record(stream)
-            obj.render_frames_device_async(cam, my_mats(step), d_col[slot].data_ptr(), d_ids[slot].data_ptr(), stream.cuda_stream)
+            obj.render_frames_device_async(cam, my_mats(step), d_col[slot].data_ptr(), d_ids[slot].data_ptr(), stream.cuda_stream,
+                                           tile_first=rank if tiles_mode else 0, tile_stride=world if tiles_mode else 1,
+                                           flags=rtb.RENDER_TILE_MAJOR if tiles_mode else 0)
             ev[step][1].record(stream)
-        if world > 1:
+        if tiles_mode:
             side.wait_event(ev[step][1])
             with torch.cuda.stream(side):
-                dist.gather(d_col[slot], gather_col if rank == 0 else None, dst=0)
-                dist.gather(d_ids[slot], gather_ids if rank == 0 else None, dst=0)
+                dist.gather(d_col[slot], gather_col[slot] if rank == 0 else None, dst=0)
+                dist.gather(d_ids[slot], gather_ids[slot] if rank == 0 else None, dst=0)
                 e = torch.cuda.Event()
                 e.record(side)
                 gather_done[slot] = e
-    for e in gather_done:
-        if e is not None:
-            stream.wait_event(e)  # the region ends when the last frames have reached rank 0
+    for slot, e in enumerate(gather_done):
+        if e is not None:  # the region ends when the last frames have reached rank 0 and are reassembled
+            stream.wait_event(e)
+            with torch.cuda.stream(stream):
+                compose(slot)
     region_ev[1].record(stream)
     barrier()
     clocks = sampler.result()
@@ -288,11 +317,15 @@ def run_ours(args):
 
     # ---------------- work counters (separate, untimed pass over the timed steps' first block) -------
     cam.counters(reset=True)
-    obj.render_frames_device_async(cam, my_mats(Wm), d_col[0].data_ptr(), d_ids[0].data_ptr(), stream.cuda_stream, flags=rtb.RENDER_COUNTERS)
+    targs = dict(tile_first=rank if tiles_mode else 0, tile_stride=world if tiles_mode else 1)
+    if tiles_mode:  # the untimed passes below write whole row-major frames of this rank's tiles
+        d_col = [torch.empty(FS * P, dtype=torch.int32, device="cuda")]
+        d_ids = [torch.empty(FS * P, dtype=torch.int32, device="cuda")]
+    obj.render_frames_device_async(cam, my_mats(Wm), d_col[0].data_ptr(), d_ids[0].data_ptr(), stream.cuda_stream, flags=rtb.RENDER_COUNTERS, **targs)
     torch.cuda.synchronize()
     c_act = cam.counters(reset=True)
     obj.render_frames_device_async(cam, my_mats(Wm), d_col[0].data_ptr(), d_ids[0].data_ptr(), stream.cuda_stream,
-                                   flags=rtb.RENDER_COUNTERS | rtb.RENDER_NO_CULL)
+                                   flags=rtb.RENDER_COUNTERS | rtb.RENDER_NO_CULL, **targs)
     torch.cuda.synchronize()
     c_ref = cam.counters(reset=True)
     coverage = c_act["hits"] / max(c_act["rays"], 1)
@@ -340,11 +373,20 @@ def run_ours(args):
     def flops_reference(c):  # 21*N_int + 45*N_leaf + 110 + 60*[hit]
         return 21.0 * (c["boxes"] - c["tris"]) + 45.0 * c["tris"] + 110.0 * c["rays"] + 60.0 * c["hits"]
 
+    traffic, traffic_src = None, None
+    for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True) if os.path.isdir(os.path.join(ROOT, "profiles")) else []:
+        if name.endswith("_traffic.json"):
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                rec = json.load(f).get(args.workload)
+            if rec and rec.get("bytes"):
+                traffic, traffic_src = rec["bytes"], "%s (%s)" % (name, rec.get("report"))
+                break
     achieved = bytes_actual(c_act) / launch_s / 1e9
     fp32_peak = props["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
     roofline = {
         "bound": "hbm", "kernel": "rtb::render_kernel<true,false>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-        "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": bytes_actual(c_act),
+        "peak_source": peak_src,
         "note": "algorithmic bytes = 64 B x interior records entered + 48 B x triangle tests + 48 B x hits + 8 B x rays, counted by the kernel itself "
                 "in an untimed pass; the scene is L2-resident by design, so DRAM traffic is far below this and the binding limits are L2 latency and "
                 "FP32/ALU issue (see DESIGN.md); HBM copy peak used as the denominator per the bench contract",
@@ -368,13 +410,15 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "mesh": mesh_label, "triangles": int(len(pts)), "resolution": [W, H], "frames_per_step": F,
                    "frames_total": K * world * F, "camera": "WinMain.cpp:69-74 default, R-key quaternion step per frame", "coverage": coverage,
-                   "parallelism": "frames x%d (scene replicated, NCCL gather to rank 0 on a side stream)" % world if world > 1 else "single GPU",
+                   "parallelism": ("tiles x%d (scene replicated, 32x32 tiles round-robin, NCCL gather to rank 0 + reassembly on a side stream)" % world
+                                   if tiles_mode else "frames x%d (scene replicated, blocks of %d frames per rank, no collective)" % (world, F)) if world > 1 else "single GPU",
                    "l2": "explicit flush (160 MB write) before every step; per-step working set = scene %.0f MB + %.0f MB output" % (
                        (64.0 * (len(pts) - 1) + 48.0 * len(pts)) / 1e6, F * P * 8 / 1e6),
                    "fps": fps, "fps_vs_readme_100fps": fps / README_FPS, "tree_build_s": build_s["total"]},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(F * 5 * 4), "d2h_bytes_per_step": int(F * P * 8),
                 "fps": K * world * F / e2e_time, "api": "rtb_render_sweep (host ops in, pinned host colour+id frames out)", "matches_device_run": same},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "kernel_ms": {"mean": float(np.mean(kernel_ms)), "min": float(np.min(kernel_ms)), "max": float(np.max(kernel_ms))},
     }
     print(json.dumps(line))
     if world > 1:
@@ -389,6 +433,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="dragon_orbit_960x540", choices=sorted(WORKLOADS))
     ap.add_argument("--frames-per-step", type=int, default=0)
+    ap.add_argument("--shard", default="frames", choices=["frames", "tiles"], help="multi-GPU partition (N > 1)")
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(HERE, "librtb.so")
 
 SET_COLOR_TAG, PHONG_COLOR_TAG = 1, 2  # Camera.h:13-14
 TRANSLATE_XYZ, TRANSLATE_X, TRANSLATE_Z, ROTATE_TRI_PY, ROTATE_TRI_NY = 30, 31, 32, 10, 11  # platform_common.h:16-21
-RENDER_DEFAULT, RENDER_NO_CULL, RENDER_COUNTERS = 0, 1, 2
+RENDER_DEFAULT, RENDER_NO_CULL, RENDER_COUNTERS, RENDER_TILE_MAJOR = 0, 1, 2, 4
 R_KEY_QUAT = (0.0, 0.09950371902099893, 0.0, 0.9950371902099893)  # WinMain.cpp:187
 T_KEY_QUAT = (0.0, -0.09950371902099893, 0.0, 0.9950371902099893)  # WinMain.cpp:207
 DEFAULT_RGB = (0.1, 0.55, 0.2)  # WinMain.cpp:118-120
@@ -35,7 +35,7 @@ EXPORTS = [
     "rtb_camera_add_object", "rtb_camera_color_pixels", "rtb_camera_host_color", "rtb_camera_host_ids",
     "rtb_camera_counters", "rtb_camera_destroy", "rtb_object_create", "rtb_object_transform", "rtb_object_get_matrix",
     "rtb_object_set_matrix", "rtb_object_destroy", "rtb_object_render", "rtb_render_frame", "rtb_render_sweep",
-    "rtb_render_frames_device_async", "rtb_object_transform_host", "rtb_device_props", "rtb_launch_count",
+    "rtb_render_frames_device_async", "rtb_object_transform_host", "rtb_device_props", "rtb_launch_count", "rtb_tile_major_elements", "rtb_compose_tiles_device_async",
 ]
 
 
@@ -91,6 +91,9 @@ def _load():
     L.rtb_render_frames_device_async.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_uint32, vp, vp, vp]
     L.rtb_device_props.argtypes = [vp]
     L.rtb_launch_count.restype = C.c_uint64
+    L.rtb_tile_major_elements.restype = C.c_int64
+    L.rtb_tile_major_elements.argtypes = [vp, C.c_int32]
+    L.rtb_compose_tiles_device_async.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp]
     return L
 
 
@@ -231,6 +234,18 @@ class Camera:
     def h_ids(self):
         p = lib.rtb_camera_host_ids(self.h)
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), shape=(self.W * self.H,))
+
+    def tile_major_elements(self, tile_stride):
+        """Per-frame element count of a RENDER_TILE_MAJOR buffer when tiles are dealt to `tile_stride` ranks."""
+        return int(lib.rtb_tile_major_elements(self.h, tile_stride))
+
+    def compose_tiles_device_async(self, num_frames, part_ptrs, out_ptr, stream_ptr=None):
+        """Scatter gathered tile-major buffers (one device pointer per rank) into row-major frames."""
+        if stream_ptr == 0:
+            stream_ptr = 1  # cudaStreamLegacy
+        arr = (C.c_void_p * len(part_ptrs))(*part_ptrs)
+        _check(lib.rtb_compose_tiles_device_async(self.h, num_frames, len(part_ptrs), arr, out_ptr, stream_ptr or None),
+               "rtb_compose_tiles_device_async")
 
     def counters(self, reset=True):
         out = np.zeros(5, np.uint64)

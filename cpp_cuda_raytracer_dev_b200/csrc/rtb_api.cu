@@ -179,6 +179,8 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, int num_f
     P.my_tiles = tile_first < tiles ? (tiles - tile_first + tile_stride - 1) / tile_stride : 0;
     P.total_items = (long long)num_frames * P.my_tiles;
     P.out_bgra = d_bgra; P.out_ids = d_ids;
+    P.tile_major = (flags & RTB_RENDER_TILE_MAJOR) ? 1 : 0;
+    P.frame_stride = P.tile_major ? (long long)((tiles + tile_stride - 1) / tile_stride) * kTile * kTile : (long long)b.W * b.H;
     P.work_counter = o->d_work;
     P.counters = c->d_counters;
     P.cull_rel = 1e-5f;
@@ -202,7 +204,10 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, int num_f
     P.total_items = (long long)num_frames * P.my_tiles * ((kTile * kTile) >> P.unit_shift);
     const long long fetches = P.total_items;
     const long long blocks_needed = (fetches + (kBlockThreads / 32) - 1) / (kBlockThreads / 32);
-    const int grid = (int)std::max(1ll, std::min<long long>((long long)c->sm_count * per_sm, blocks_needed));
+    // RTB_RESERVE_SMS leaves SMs free for kernels that must run beside this persistent one (the NCCL
+    // gather of the multi-GPU tile exchange); the default keeps the whole GPU.
+    const int sms = std::max(1, c->sm_count - std::max(0, env_int("RTB_RESERVE_SMS", 0)));
+    const int grid = (int)std::max(1ll, std::min<long long>((long long)sms * per_sm, blocks_needed));
     RTB_CUDA(cudaMemsetAsync(o->d_work, 0, sizeof(unsigned long long), stream));
     // per-launch L2 policy: the scene (nodes + triangles) persists, everything else streams.  Set
     // on the launch so that it also holds on streams the caller owns.
@@ -706,6 +711,32 @@ int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32
     // keep the single-frame view coherent: last frame is also the camera's current frame
     if (bgra_out) std::memcpy(cam->h_bgra, bgra_out + (size_t)(num_frames - 1) * P, 4 * P);
     if (ids_out) std::memcpy(cam->h_ids, ids_out + (size_t)(num_frames - 1) * P, 4 * P);
+    return RTB_OK;
+}
+
+int64_t rtb_tile_major_elements(const rtb_camera* cam, int32_t tile_stride) {
+    if (!cam || tile_stride < 1) return 0;
+    const int tiles = ((cam->basis.W + rtb::kTile - 1) / rtb::kTile) * ((cam->basis.H + rtb::kTile - 1) / rtb::kTile);
+    return (int64_t)((tiles + tile_stride - 1) / tile_stride) * rtb::kTile * rtb::kTile;
+}
+
+int rtb_compose_tiles_device_async(rtb_camera* cam, int32_t num_frames, int32_t world, const void* const* d_parts, void* d_out, void* stream) {
+    if (!cam || num_frames <= 0 || world < 1 || world > 8 || !d_parts || !d_out) return fail(RTB_ERR_ARG, "compose_tiles: bad argument");
+    RTB_CUDA(cudaSetDevice(cam->device));
+    rtb::ComposeParts parts;
+    std::memset(&parts, 0, sizeof parts);
+    for (int r = 0; r < world; r++) {
+        if (!d_parts[r]) return fail(RTB_ERR_ARG, "compose_tiles: null part");
+        parts.part[r] = (const uint32_t*)d_parts[r];
+    }
+    const int tiles_x = (cam->basis.W + rtb::kTile - 1) / rtb::kTile;
+    const long long slots = rtb_tile_major_elements(cam, world) / (rtb::kTile * rtb::kTile);
+    if (num_frames > 65535 || cam->basis.H > 65535) return fail(RTB_ERR_ARG, "compose_tiles: too many frames or rows for one launch");
+    cudaStream_t s = stream ? (cudaStream_t)stream : cam->stream;
+    const dim3 grid((unsigned)(((cam->basis.W + 3) / 4 + 127) / 128), (unsigned)cam->basis.H, (unsigned)num_frames);
+    rtb::compose_tiles_kernel<<<grid, 128, 0, s>>>(parts, world, cam->basis.W, cam->basis.H, tiles_x, slots, (uint32_t*)d_out);
+    g_launches++;
+    RTB_CUDA(cudaGetLastError());
     return RTB_OK;
 }
 

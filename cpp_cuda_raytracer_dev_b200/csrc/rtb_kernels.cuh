@@ -56,6 +56,8 @@ struct RenderParams {
     int unit_shift;        // log2 pixels per work unit: 5..10, a Morton block of a 32x32 tile
     int t_active, t_leaf;  // refill when <= t_active lanes still traverse; leaf step when >= t_leaf lanes wait at a leaf
     long long total_items; // work units: num_frames * my_tiles * (1024 >> unit_shift)
+    long long frame_stride;  // output elements per frame: W*H (row-major) or my_tile_slots*1024 (tile-major)
+    int tile_major;          // 1: compact tile-major output (the multi-GPU exchange format), 0: final row-major position
     uint32_t* __restrict__ out_bgra;
     int32_t* __restrict__ out_ids;
     unsigned long long* work_counter;
@@ -207,6 +209,27 @@ __global__ void pack_nodes_kernel(const float* __restrict__ bounds6, const int* 
     o[1] = make_float4(L[4], L[5], R[0], R[1]);
     o[2] = make_float4(R[2], R[3], R[4], R[5]);
     o[3] = make_float4(__uint_as_float(lref), __uint_as_float(rref), L[3 + axis], R[axis]);
+}
+
+// Reassembly of a frame from per-rank tile-major buffers (the receiving side of the multi-GPU
+// exchange): tile t of the image was rendered by rank t % world into slot t / world of that rank's
+// buffer; every rank's buffer has `slots` 32x32 slots per frame.
+struct ComposeParts { const uint32_t* part[8]; };
+// grid = (ceil(W/4 / 128), H, frames), block = 128: one thread moves 4 horizontally adjacent pixels
+// (they always lie in one tile row), 16-byte loads and stores when the frame width allows it.
+__global__ void compose_tiles_kernel(ComposeParts parts, int world, int W, int H, int tiles_x, long long slots, uint32_t* __restrict__ out) {
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x >= W) return;
+    const long long frame = blockIdx.z;
+    const int t = (y / kTile) * tiles_x + (x / kTile);
+    const int rank = t % world, slot = t / world;
+    const uint32_t* src = parts.part[rank] + (frame * slots + slot) * (kTile * kTile) + (y % kTile) * kTile + (x % kTile);
+    uint32_t* dst = out + (frame * H + y) * (long long)W + x;
+    if ((W & 3) == 0) {
+        __stcs(reinterpret_cast<uint4*>(dst), __ldcs(reinterpret_cast<const uint4*>(src)));
+    } else {
+        for (int k = 0; k < 4 && x + k < W; k++) __stcs(dst + k, __ldcs(src + k));
+    }
 }
 
 __global__ void fill_kernel(uint32_t* __restrict__ out, long long n, uint32_t value) {

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const R
     const int unit_pixels = 1 << P.unit_shift;
     const int units_per_tile = (kTile * kTile) >> P.unit_shift;
     int u_next = unit_pixels;  // nothing loaded yet
-    int u_frame = 0, u_x0 = 0, u_y0 = 0, u_base = 0;
+    int u_frame = 0, u_x0 = 0, u_y0 = 0, u_base = 0, u_slot = 0;
     int u_rx0 = 0, u_ry0 = 0, u_rx1 = -1, u_ry1 = -1;  // pixel rectangle of the unit's frame that can reach the root box
     bool exhausted = false;
 
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const R
                 color = phong(P, P.frames + (long long)kFrameStride * frame, r, best, id, cmx, cmy, cmz);
                 if (COUNT) c_hits++;
             }
-            const long long o = (long long)frame * P.W * P.H + pix;
+            const long long o = (long long)frame * P.frame_stride + pix;
             // frames are write-once streams: keep them from displacing the scene in L2
             if (P.out_bgra) __stcs(P.out_bgra + o, color);
             if (P.out_ids) __stcs(P.out_ids + o, id);
@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const R
                 const long long per_frame = (long long)P.my_tiles * units_per_tile;
                 u_frame = (int)((long long)uid / per_frame);
                 const int rem = (int)((long long)uid - (long long)u_frame * per_frame);
-                const int tile = P.tile_first + (rem / units_per_tile) * P.tile_stride;
+                u_slot = rem / units_per_tile;
+                const int tile = P.tile_first + u_slot * P.tile_stride;
                 u_base = (rem % units_per_tile) << P.unit_shift;
                 u_x0 = (tile % P.tiles_x) * kTile;
                 u_y0 = (tile / P.tiles_x) * kTile;
@@ -221,18 +222,20 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const R
             const int avail = unit_pixels - u_next;
             if (((m_empty >> lane) & 1u) && slot < avail) {
                 const uint32_t K = (uint32_t)(u_base + u_next + slot);  // Morton ordinal inside the 32x32 tile
-                const int px = u_x0 + (int)compact_even_bits(K), py = u_y0 + (int)compact_even_bits(K >> 1);
+                const int lx = (int)compact_even_bits(K), ly = (int)compact_even_bits(K >> 1);
+                const int px = u_x0 + lx, py = u_y0 + ly;
                 if (px < P.W && py < P.H) {
+                    const int opix = P.tile_major ? (u_slot * kTile + ly) * kTile + lx : py * P.W + px;
                     if (px < u_rx0 || px > u_rx1 || py < u_ry0 || py > u_ry1) {
                         // outside the (conservatively enlarged) projection of the root box: the ray cannot
                         // pass the root's box test (Trixel.cu:146), the pixel is background
-                        const long long o = (long long)u_frame * P.W * P.H + (long long)py * P.W + px;
+                        const long long o = (long long)u_frame * P.frame_stride + opix;
                         if (P.out_bgra) __stcs(P.out_bgra + o, P.background);
                         if (P.out_ids) __stcs(P.out_ids + o, -1);
                         if (COUNT) { c_rays++; c_boxes++; }
                     } else {
                         frame = u_frame;
-                        pix = py * P.W + px;
+                        pix = opix;
                         const float* __restrict__ M = P.frames + (long long)kFrameStride * frame;
                         // ---- primary ray, Camera.cu:103-104 (row 0 = bottom) --------------------------
                         const float fxp = (float)px, fyp = (float)py;

@@ -54,6 +54,7 @@ typedef enum {
 #define RTB_RENDER_DEFAULT 0u
 #define RTB_RENDER_NO_CULL 1u   /* visit exactly the node sequence of Trixel.cu:70-170 (no distance culling) */
 #define RTB_RENDER_COUNTERS 2u  /* accumulate per-launch work counters (rtb_camera_counters) */
+#define RTB_RENDER_TILE_MAJOR 4u /* rtb_render_frames_device_async: compact tile-major output (multi-GPU exchange format) */
 
 const char* rtb_last_error(void);
 const char* rtb_version(void);
@@ -176,6 +177,16 @@ int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32
 int rtb_render_frames_device_async(rtb_object* obj, rtb_camera* cam, int32_t num_frames, const float* m12,
                                    int32_t tile_first, int32_t tile_stride, uint32_t flags, uint32_t* d_bgra,
                                    int32_t* d_ids, void* stream);
+/* Multi-GPU exchange format.  With RTB_RENDER_TILE_MAJOR, rtb_render_frames_device_async writes only
+ * the tiles of this rank, compactly: frame f, owned tile slot j (image tile tile_first + j*tile_stride),
+ * pixel (lx,ly) of the tile -> element (f*slots + j)*1024 + ly*32 + lx, slots = ceil(tiles/tile_stride).
+ * rtb_tile_major_elements returns slots*1024, the per-frame element count of such a buffer (equal on
+ * all ranks, so the buffers can be gathered with one equal-sized collective).  After the gather,
+ * rtb_compose_tiles_device_async scatters `world` such buffers (d_parts[r] = rank r's, device
+ * pointers to 32-bit elements: colours or ids alike) into the final row-major frames d_out. */
+int64_t rtb_tile_major_elements(const rtb_camera* cam, int32_t tile_stride);
+int rtb_compose_tiles_device_async(rtb_camera* cam, int32_t num_frames, int32_t world, const void* const* d_parts, void* d_out, void* stream);
+
 /* host-side transform recurrence only (no GPU): advance `obj` by one op and return its matrix;
  * lets callers precompute the m12 array for rtb_render_frames_device_async. */
 int rtb_object_transform_host(rtb_object* obj, const float xyzw[4], uint8_t transform_select, float m12_out[12]);

@@ -199,4 +199,20 @@ def test_tile_partition_is_bit_identical(gpu, orc):
         torch.cuda.synchronize()
         assert np.array_equal(ids.cpu().numpy(), full_ids)
         assert np.array_equal(col.cpu().numpy().view(np.uint32), full_col)
+        # the exchange format: every "rank" renders compact tile-major buffers, rank 0 reassembles them
+        pe = p.cam.tile_major_elements(G)
+        parts_c = [torch.full((2 * pe,), 0x55, dtype=torch.int32, device="cuda") for _ in range(G)]
+        parts_i = [torch.full((2 * pe,), -9, dtype=torch.int32, device="cuda") for _ in range(G)]
+        m2 = np.stack([m, m])
+        for r in range(G):
+            p.obj.render_frames_device_async(p.cam, m2, parts_c[r].data_ptr(), parts_i[r].data_ptr(), s, tile_first=r, tile_stride=G,
+                                             flags=gpu.RENDER_TILE_MAJOR)
+        out_c = torch.empty(2 * W * H, dtype=torch.int32, device="cuda")
+        out_i = torch.empty(2 * W * H, dtype=torch.int32, device="cuda")
+        p.cam.compose_tiles_device_async(2, [t.data_ptr() for t in parts_c], out_c.data_ptr(), s)
+        p.cam.compose_tiles_device_async(2, [t.data_ptr() for t in parts_i], out_i.data_ptr(), s)
+        torch.cuda.synchronize()
+        for f in range(2):
+            assert np.array_equal(out_i.cpu().numpy()[f * W * H:(f + 1) * W * H], full_ids)
+            assert np.array_equal(out_c.cpu().numpy().view(np.uint32)[f * W * H:(f + 1) * W * H], full_col)
     p.close()
