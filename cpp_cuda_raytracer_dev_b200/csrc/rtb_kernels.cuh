@@ -76,11 +76,11 @@ struct RenderParams {
 // shortcuts that are provably equal to these whenever they can decide (see child_order / box_entered
 // in rtb_render.cuh) and calls the functions below only for the rare undecidable inputs: operands
 // below 2^-28 in magnitude, exact ties, NaN.
-__device__ __noinline__ bool exact_ge_minus_eps(float hi, float lo) { return (double)hi >= (double)lo - 1e-16; }   // Trixel.cu:146
-__device__ __noinline__ bool exact_lt_plus_eps(float a, float s) { return (double)a < (double)s + 1e-16; }         // Trixel.cu:155
-__device__ __noinline__ bool exact_gt_minus_eps(float b, float s) { return (double)b > (double)s - 1e-16; }        // Trixel.cu:156
+__device__ __forceinline__ bool exact_ge_minus_eps(float hi, float lo) { return (double)hi >= (double)lo - 1e-16; }   // Trixel.cu:146
+__device__ __forceinline__ bool exact_lt_plus_eps(float a, float s) { return (double)a < (double)s + 1e-16; }         // Trixel.cu:155
+__device__ __forceinline__ bool exact_gt_minus_eps(float b, float s) { return (double)b > (double)s - 1e-16; }        // Trixel.cu:156
 // (float)(((double)S1 + 1e-16) + (double)ds)   (Trixel.cu:150: `s1 = cvm->s1[cni] + EPS + ds`)
-__device__ __noinline__ float exact_s1(float S1, float ds) {
+__device__ __forceinline__ float exact_s1(float S1, float ds) {
     return __double2float_rn(__dadd_rn(__dadd_rn((double)S1, 1e-16), (double)ds));
 }
 

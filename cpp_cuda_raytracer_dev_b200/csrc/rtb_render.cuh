@@ -38,7 +38,7 @@ __device__ __forceinline__ bool ordered_ne(float x, float y) { return (x < y) | 
 // 149-168), for the rare inputs they cannot: operands below 2^-28 in magnitude, exact ties, NaN.
 // Returns bit 0 = left child first, bit 1 = second child scheduled, bit 2 = left box entered,
 // bit 3 = right box entered.
-__device__ __noinline__ int interior_decisions_exact(float a, float b, float s2, float S1, float ds, float ltmin, float ltmax,
+__device__ __forceinline__ int interior_decisions_exact(float a, float b, float s2, float S1, float ds, float ltmin, float ltmax,
                                                      float rtmin, float rtmax) {
     int out = 0;
     if (exact_lt_plus_eps(a, s2)) {  // Trixel.cu:155-161: left is popped first, right only if the exit lies beyond s2
@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const R
             } else if (ready & !at_leaf) {
                 // ---- interior step: `cur` is a node whose own box test passed ------------------------
                 if (COUNT) c_nodes++;
-                const float4* rec = P.nodes + 4ll * (int)((unsigned)cur & kRefIndexMask);
+                const float4* rec;  // P.nodes + 64 bytes * record index, as one IMAD.WIDE
+                asm("mad.wide.u32 %0, %1, 64, %2;" : "=l"(rec) : "r"((unsigned)cur & kRefIndexMask), "l"(P.nodes));
                 const float4 q0 = ldg4(rec), q1 = ldg4(rec + 1), q2 = ldg4(rec + 2), q3 = ldg4(rec + 3);
                 const int lref = __float_as_int(q3.x), rref = __float_as_int(q3.y);
                 const float S1 = q3.z, S2 = q3.w;  // left child's max / right child's min on the split axis (Trixel.h:353-376)
@@ -130,8 +131,10 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const R
                 // Split-axis components.  Trixel.cu:88-90 forms them as three-term sums with 0/1 flags,
                 // which for finite operands is the selected component up to the sign of a zero; neither
                 // the products below nor the comparisons can see that sign.
-                const float dir = axis == 0 ? r.dx : (axis == 1 ? r.dy : r.dz);
-                const float ds = axis == 0 ? r.ox : (axis == 1 ? r.oy : r.oz);
+                const bool ax0 = axis == 0, ax1 = axis == 1;
+                float dir = r.dz, ds = r.oz;
+                dir = ax1 ? r.dy : dir; ds = ax1 ? r.oy : ds;
+                dir = ax0 ? r.dx : dir; ds = ax0 ? r.ox : ds;
                 const float a = __fmul_rn(cur_tmin, dir), b = __fmul_rn(cur_tmax, dir);  // Trixel.cu:149
                 const float s2 = __fadd_rn(S2, ds);                                      // Trixel.cu:151
                 // ---- both child boxes (children the reference would pop: leaves are always intersected,
@@ -161,8 +164,8 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const R
                 if (COUNT) c_boxes += 1 + (int)visit_second;
                 const bool l_ok = ((lref < 0) | l_in) & !culled(ltmin);
                 const bool r_ok = ((rref < 0) | r_in) & !culled(rtmin);
-                const bool go_first = left_first ? l_ok : r_ok;
-                const bool go_second = (left_first ? r_ok : l_ok) & visit_second;
+                const bool go_first = (left_first & l_ok) | (!left_first & r_ok);
+                const bool go_second = ((left_first & r_ok) | (!left_first & l_ok)) & visit_second;
                 if (go_second) {
                     if (sp > 0) { stk_ref[sp - 1] = top_ref; stk_tmin[sp - 1] = top_tmin; stk_tmax[sp - 1] = top_tmax; }
                     top_ref = left_first ? rref : lref;
