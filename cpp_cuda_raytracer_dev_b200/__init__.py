@@ -18,7 +18,7 @@ import numpy as np
 from . import build as _build
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librtb.so")
+LIB_PATH = os.environ.get("RTB_LIB") or os.path.join(HERE, "librtb.so")  # RTB_LIB: development override
 
 SET_COLOR_TAG, PHONG_COLOR_TAG = 1, 2  # Camera.h:13-14
 TRANSLATE_XYZ, TRANSLATE_X, TRANSLATE_Z, ROTATE_TRI_PY, ROTATE_TRI_NY = 30, 31, 32, 10, 11  # platform_common.h:16-21

@@ -678,7 +678,10 @@ int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32
 
     // ring of two device chunks; chunk k+1 renders while chunk k streams to the host
     const size_t P = (size_t)cam->pixels;
-    int chunk_frames = (int)std::max<size_t>(1, std::min<size_t>((size_t)num_frames, (size_t)(48u << 20) / (P * 4)));
+    // chunk = the frames rendered by one launch and copied out together.  Small enough that the first
+    // copy starts early (the sweep is PCIe-bound: 8 bytes per pixel leave the device), large enough to
+    // amortise launches: about 16 MB per buffer.
+    int chunk_frames = (int)std::max<size_t>(1, std::min<size_t>((size_t)num_frames, (size_t)(16u << 20) / (P * 4)));
     if (cam->ring_frames < chunk_frames) {
         for (int k = 0; k < 2; k++) {
             dfree(cam->ring_bgra[k]); dfree(cam->ring_ids[k]);
