@@ -35,7 +35,7 @@ EXPORTS = [
     "rtb_camera_add_object", "rtb_camera_color_pixels", "rtb_camera_host_color", "rtb_camera_host_ids",
     "rtb_camera_counters", "rtb_camera_destroy", "rtb_object_create", "rtb_object_transform", "rtb_object_get_matrix",
     "rtb_object_set_matrix", "rtb_object_destroy", "rtb_object_render", "rtb_render_frame", "rtb_render_sweep",
-    "rtb_render_frames_device_async", "rtb_object_transform_host", "rtb_device_props", "rtb_launch_count", "rtb_tile_major_elements", "rtb_compose_tiles_device_async",
+    "rtb_render_frames_device_async", "rtb_object_transform_host", "rtb_device_props", "rtb_launch_count", "rtb_tile_major_elements", "rtb_compose_tiles_device_async", "rtb_selftest_exact",
 ]
 
 
@@ -91,6 +91,7 @@ def _load():
     L.rtb_render_frames_device_async.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_uint32, vp, vp, vp]
     L.rtb_device_props.argtypes = [vp]
     L.rtb_launch_count.restype = C.c_uint64
+    L.rtb_selftest_exact.argtypes = [C.c_uint64, C.c_int64, vp]
     L.rtb_tile_major_elements.restype = C.c_int64
     L.rtb_tile_major_elements.argtypes = [vp, C.c_int32]
     L.rtb_compose_tiles_device_async.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp]
@@ -111,6 +112,12 @@ def device_count():
 
 def set_device(i):
     _check(lib.rtb_set_device(i), "rtb_set_device")
+
+
+def selftest_exact(seed, count):
+    out = np.zeros(4, np.uint64)
+    _check(lib.rtb_selftest_exact(seed, count, out.ctypes.data), "rtb_selftest_exact")
+    return dict(zip(["rsqrt_mismatch", "rcp_mismatch", "decision_mismatch", "decidable"], out.tolist()))
 
 
 def launch_count():

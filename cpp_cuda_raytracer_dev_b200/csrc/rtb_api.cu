@@ -764,6 +764,25 @@ int rtb_compose_tiles_device_async(rtb_camera* cam, int32_t num_frames, int32_t 
     return RTB_OK;
 }
 
+int rtb_selftest_exact(uint64_t seed, int64_t count, uint64_t out4[4]) {
+    if (count <= 0 || !out4) return fail(RTB_ERR_ARG, "selftest_exact: bad argument");
+    RTB_CUDA(cudaSetDevice(g_device));
+    unsigned long long* d = nullptr;
+    RTB_CUDA(cudaMalloc(&d, sizeof(unsigned long long) * 4));
+    cudaError_t e = cudaMemset(d, 0, sizeof(unsigned long long) * 4);
+    if (e == cudaSuccess) {
+        rtb::selftest_exact_kernel<<<(unsigned)((count + 255) / 256), 256>>>(seed, count, d);
+        g_launches++;
+        e = cudaGetLastError();
+    }
+    unsigned long long h[4] = {0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, std::string("selftest_exact: ") + cudaGetErrorString(e));
+    for (int k = 0; k < 4; k++) out4[k] = h[k];
+    return RTB_OK;
+}
+
 uint64_t rtb_launch_count(void) { return g_launches.load(); }
 
 int rtb_device_props(int64_t out7[7]) {

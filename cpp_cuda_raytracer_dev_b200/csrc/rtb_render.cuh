@@ -53,6 +53,74 @@ __device__ __forceinline__ int interior_decisions_exact(float a, float b, float 
     return out;
 }
 
+// The fp32 shortcuts of the same decisions (same bit layout), valid whenever `decidable` comes back true:
+//   (double)a < (double)s2 + EPS  ==  a < s2        } when a != s2, b != s2 and |s2| >= 2^-28:
+//   (double)b > (double)s2 - EPS  ==  b > s2        } s2 +- 1e-16 stays strictly between s2's float neighbours
+//   (b < s1) || (a < s1)          ==  min(a,b) < sf   when min(a,b) != sf and |sf| >= 2^-27, sf = fl(S1 + ds):
+//        s1 = (float)(((double)S1 + EPS) + (double)ds) is sf or its upper neighbour, never below sf
+//   (double)tmax >= (double)tmin - EPS  ==  tmax >= tmin   when |tmin| >= 2^-28
+// `decidable` is false for ties, tiny operands and NaN; those lanes take the exact path.
+__device__ __forceinline__ void interior_decisions_fast(float a, float b, float s2, float S1, float ds, float ltmin, float ltmax, float rtmin,
+                                                        float rtmax, bool& decidable, bool& left_first, bool& visit_second, bool& l_in,
+                                                        bool& r_in) {
+    const float sf = __fadd_rn(S1, ds);
+    const float mab = fminf(a, b);
+    decidable = (fabsf(s2) >= RTB_TINY) & (fabsf(sf) >= 2.0f * RTB_TINY) & ordered_ne(a, s2) & ordered_ne(b, s2) & ordered_ne(mab, sf) &
+                (fabsf(ltmin) >= RTB_TINY) & (fabsf(rtmin) >= RTB_TINY);
+    left_first = a < s2;
+    visit_second = left_first ? (b > s2) : (mab < sf);
+    l_in = (ltmax >= ltmin) & (ltmin > -RTB_EPS_UP);
+    r_in = (rtmax >= rtmin) & (rtmin > -RTB_EPS_UP);
+}
+
+// Self-test of the exactness arguments (rtb_selftest_exact): every thread draws operands -- raw random
+// bit patterns over all exponents, plus neighbours within a few ulps of each other to provoke ties --
+// and checks (0) the early-exit Newton rsqrt against the literal 21-step loop, (1) __frcp_rn against
+// the reference's (float)(1.0 / (double)f), (2) the fp32 decision shortcuts against the exact
+// double-precision evaluation wherever they claim to be decidable.  out[3] counts decidable samples.
+__device__ __forceinline__ uint32_t selftest_hash(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return (uint32_t)x;
+}
+__global__ void selftest_exact_kernel(uint64_t seed, long long count, unsigned long long* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float v[9];
+    const uint32_t mode = selftest_hash(seed + 977 * (uint64_t)i) % 4u;
+    for (int k = 0; k < 9; k++) {
+        uint32_t bits = selftest_hash(seed * 31 + (uint64_t)i * 16 + k);
+        if (mode >= 1) bits = (bits & 0x807fffffu) | ((96u + (bits >> 23) % 64u) << 23);  // magnitudes 2^-31 .. 2^32
+        v[k] = __uint_as_float(bits);
+    }
+    if (mode >= 2) {  // provoke ties: derive operands from each other within a few ulps
+        const int d = (int)(selftest_hash(seed + 5 * (uint64_t)i) % 5u) - 2;
+        v[2] = __uint_as_float(__float_as_uint(v[0]) + d);                         // s2 ~ a
+        v[1] = mode == 3 ? v[2] : v[1];                                            // b == s2
+        v[6] = __uint_as_float(__float_as_uint(v[5]) + (d & 1));                   // ltmax ~ ltmin
+        v[3] = __fsub_rn(v[0], v[4]);                                              // S1 + ds ~ a
+    }
+    unsigned long long bad0 = 0, bad1 = 0, bad2 = 0, dec = 0;
+    const float s = fabsf(v[0]);
+    if (__float_as_uint(rsqrt21(s)) != __float_as_uint(rsqrt21_literal(s)) && !(rsqrt21(s) != rsqrt21(s) && rsqrt21_literal(s) != rsqrt21_literal(s))) bad0 = 1;
+    const float f = v[1];
+    if (f == f && f != 0.0f && fabsf(f) <= 3.0e38f) {
+        const float ref = (float)(1.0 / (double)f);
+        if (__float_as_uint(__frcp_rn(f)) != __float_as_uint(ref)) bad1 = 1;
+    }
+    bool decidable, lf, vs, li, ri;
+    interior_decisions_fast(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], decidable, lf, vs, li, ri);
+    if (decidable) {
+        dec = 1;
+        const int ex = interior_decisions_exact(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
+        const int fast = (int)lf | ((int)vs << 1) | ((int)li << 2) | ((int)ri << 3);
+        if (ex != fast) bad2 = 1;
+    }
+    if (bad0) atomicAdd(out + 0, 1ull);
+    if (bad1) atomicAdd(out + 1, 1ull);
+    if (bad2) atomicAdd(out + 2, 1ull);
+    if (dec) atomicAdd(out + 3, 1ull);
+}
+
 template <bool CULL, bool COUNT>
 __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const RenderParams P) {
     const unsigned lane = threadIdx.x & 31u;
@@ -142,21 +210,10 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const R
                 float ltmin, ltmax, rtmin, rtmax;
                 slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ltmin, ltmax);
                 slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, rtmin, rtmax);
-                // ---- decisions, fp32 shortcuts of the reference's double-precision comparisons ------------
-                //   (double)a < (double)s2 + EPS  ==  a < s2        } when a != s2, b != s2 and |s2| >= 2^-28:
-                //   (double)b > (double)s2 - EPS  ==  b > s2        } s2 +- 1e-16 stays strictly between s2's float neighbours
-                //   (b < s1) || (a < s1)          ==  min(a,b) < sf   when min(a,b) != sf and |sf| >= 2^-27, sf = fl(S1 + ds):
-                //        s1 = (float)(((double)S1 + EPS) + (double)ds) is sf or its upper neighbour, never below sf
-                //   (double)tmax >= (double)tmin - EPS  ==  tmax >= tmin   when |tmin| >= 2^-28
-                // `decidable` is false for ties, tiny operands and NaN; those lanes take the exact path.
-                const float sf = __fadd_rn(S1, ds);
-                const float mab = fminf(a, b);
-                const bool decidable = (fabsf(s2) >= RTB_TINY) & (fabsf(sf) >= 2.0f * RTB_TINY) & ordered_ne(a, s2) & ordered_ne(b, s2) &
-                                       ordered_ne(mab, sf) & (fabsf(ltmin) >= RTB_TINY) & (fabsf(rtmin) >= RTB_TINY);
-                bool left_first = a < s2;
-                bool visit_second = left_first ? (b > s2) : (mab < sf);
-                bool l_in = (ltmax >= ltmin) & (ltmin > -RTB_EPS_UP);
-                bool r_in = (rtmax >= rtmin) & (rtmin > -RTB_EPS_UP);
+                // ---- decisions: fp32 shortcuts of the reference's double-precision comparisons (see
+                // interior_decisions_fast), exact evaluation for the inputs they cannot decide ------------
+                bool decidable, left_first, visit_second, l_in, r_in;
+                interior_decisions_fast(a, b, s2, S1, ds, ltmin, ltmax, rtmin, rtmax, decidable, left_first, visit_second, l_in, r_in);
                 if (!decidable) {
                     const int ex = interior_decisions_exact(a, b, s2, S1, ds, ltmin, ltmax, rtmin, rtmax);
                     left_first = (ex & 1) != 0; visit_second = (ex & 2) != 0; l_in = (ex & 4) != 0; r_in = (ex & 8) != 0;

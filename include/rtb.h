@@ -191,6 +191,12 @@ int rtb_compose_tiles_device_async(rtb_camera* cam, int32_t num_frames, int32_t 
  * lets callers precompute the m12 array for rtb_render_frames_device_async. */
 int rtb_object_transform_host(rtb_object* obj, const float xyzw[4], uint8_t transform_select, float m12_out[12]);
 
+/* Device self-test of the exactness arguments the kernel relies on: `count` pseudo-random
+ * operand sets (random bit patterns, near-ties, tiny values, NaN).  out4[0] = early-exit Newton rsqrt != literal 21
+ * steps, out4[1] = __frcp_rn(f) != (float)(1.0/(double)f), out4[2] = fp32 decision shortcut != exact double
+ * evaluation on an input it declared decidable, out4[3] = number of decidable samples.  All mismatch counts must be 0. */
+int rtb_selftest_exact(uint64_t seed, int64_t count, uint64_t out4[4]);
+
 /* number of kernels this library has launched in this process (render, pack and fill kernels) */
 uint64_t rtb_launch_count(void);
 

@@ -54,6 +54,14 @@ def gpu(rtb):
     return rtb
 
 
+def test_exactness_arguments_hold_on_device(gpu):
+    """the kernel's fp32 shortcuts against the reference's double-precision forms."""
+    for seed in (1, 20261018):
+        r = gpu.selftest_exact(seed, 1 << 26)
+        assert r["rsqrt_mismatch"] == 0 and r["rcp_mismatch"] == 0 and r["decision_mismatch"] == 0, r
+        assert r["decidable"] > (1 << 24)
+
+
 def test_icosphere_frames_cull_and_nocull(gpu, orc):
     pts = gpu.geodesic_mesh(24)
     p = Pair(gpu, orc, pts, 320, 180)
