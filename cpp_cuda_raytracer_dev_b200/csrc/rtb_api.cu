@@ -732,9 +732,8 @@ int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32
     }
     for (int k = std::max(0, chunks - 2); k < chunks; k++) { rc = drain(k); if (rc) return rc; }
     RTB_CUDA(cudaStreamSynchronize(cam->stream));
-    // keep the single-frame view coherent: last frame is also the camera's current frame
-    if (bgra_out) std::memcpy(cam->h_bgra, bgra_out + (size_t)(num_frames - 1) * P, 4 * P);
-    if (ids_out) std::memcpy(cam->h_ids, ids_out + (size_t)(num_frames - 1) * P, 4 * P);
+    // (the camera's single-frame host buffers are not touched by a sweep: copying the last frame into
+    // them would cost more host time than rendering it)
     return RTB_OK;
 }
 

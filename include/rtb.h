@@ -164,7 +164,7 @@ int rtb_render_frame(rtb_object* obj, rtb_camera* cam, uint32_t flags);
  * stream to the host while later ones render.  bgra_out / ids_out are caller buffers of
  * num_frames*W*H elements (pageable or pinned; either may be NULL) -- the only interface here that
  * writes into caller memory.  The object's transform state advances as if the calls had been made
- * one by one. */
+ * one by one; the camera's single-frame buffers (rtb_camera_host_color / _ids) are left untouched. */
 int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32_t steps_per_frame,
                      const float* ops5, uint32_t flags, uint32_t* bgra_out, int32_t* ids_out);
 
