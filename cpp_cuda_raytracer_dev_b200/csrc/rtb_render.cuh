@@ -214,26 +214,32 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const R
                 // interior_decisions_fast), exact evaluation for the inputs they cannot decide ------------
                 bool decidable, left_first, visit_second, l_in, r_in;
                 interior_decisions_fast(a, b, s2, S1, ds, ltmin, ltmax, rtmin, rtmax, decidable, left_first, visit_second, l_in, r_in);
-                if (!decidable) {
+                // The tail is instantiated once per path (not merged) so that on the fast path the four
+                // decisions stay in predicate registers instead of being materialised for a join.
+                auto descend = [&](bool left_first, bool visit_second, bool l_in, bool r_in) {
+                    if (COUNT) c_boxes += 1 + (int)visit_second;
+                    const bool l_ok = ((lref < 0) | l_in) & !culled(ltmin);
+                    const bool r_ok = ((rref < 0) | r_in) & !culled(rtmin);
+                    const bool go_first = (left_first & l_ok) | (!left_first & r_ok);
+                    const bool go_second = ((left_first & r_ok) | (!left_first & l_ok)) & visit_second;
+                    if (go_second) {
+                        if (sp > 0) { stk_ref[sp - 1] = top_ref; stk_tmin[sp - 1] = top_tmin; stk_tmax[sp - 1] = top_tmax; }
+                        top_ref = left_first ? rref : lref;
+                        top_tmin = left_first ? rtmin : ltmin;
+                        top_tmax = left_first ? rtmax : ltmax;
+                        sp++;
+                    }
+                    cur = left_first ? lref : rref;
+                    cur_tmin = left_first ? ltmin : rtmin;
+                    cur_tmax = left_first ? ltmax : rtmax;
+                    want_pop = !go_first;
+                };
+                if (decidable) {
+                    descend(left_first, visit_second, l_in, r_in);
+                } else {
                     const int ex = interior_decisions_exact(a, b, s2, S1, ds, ltmin, ltmax, rtmin, rtmax);
-                    left_first = (ex & 1) != 0; visit_second = (ex & 2) != 0; l_in = (ex & 4) != 0; r_in = (ex & 8) != 0;
+                    descend((ex & 1) != 0, (ex & 2) != 0, (ex & 4) != 0, (ex & 8) != 0);
                 }
-                if (COUNT) c_boxes += 1 + (int)visit_second;
-                const bool l_ok = ((lref < 0) | l_in) & !culled(ltmin);
-                const bool r_ok = ((rref < 0) | r_in) & !culled(rtmin);
-                const bool go_first = (left_first & l_ok) | (!left_first & r_ok);
-                const bool go_second = ((left_first & r_ok) | (!left_first & l_ok)) & visit_second;
-                if (go_second) {
-                    if (sp > 0) { stk_ref[sp - 1] = top_ref; stk_tmin[sp - 1] = top_tmin; stk_tmax[sp - 1] = top_tmax; }
-                    top_ref = left_first ? rref : lref;
-                    top_tmin = left_first ? rtmin : ltmin;
-                    top_tmax = left_first ? rtmax : ltmax;
-                    sp++;
-                }
-                cur = left_first ? lref : rref;
-                cur_tmin = left_first ? ltmin : rtmin;
-                cur_tmax = left_first ? ltmax : rtmax;
-                want_pop = !go_first;
             }
             m_trav = __ballot_sync(0xffffffffu, state == kStateTraverse);
         }
