@@ -218,20 +218,19 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const R
                 // decisions stay in predicate registers instead of being materialised for a join.
                 auto descend = [&](bool left_first, bool visit_second, bool l_in, bool r_in) {
                     if (COUNT) c_boxes += 1 + (int)visit_second;
-                    const bool l_ok = ((lref < 0) | l_in) & !culled(ltmin);
-                    const bool r_ok = ((rref < 0) | r_in) & !culled(rtmin);
-                    const bool go_first = (left_first & l_ok) | (!left_first & r_ok);
-                    const bool go_second = ((left_first & r_ok) | (!left_first & l_ok)) & visit_second;
+                    // order the two children first, then judge them: fewer live predicates
+                    const int first = left_first ? lref : rref, second = left_first ? rref : lref;
+                    const float f_tmin = left_first ? ltmin : rtmin, f_tmax = left_first ? ltmax : rtmax;
+                    const float s_tmin = left_first ? rtmin : ltmin, s_tmax = left_first ? rtmax : ltmax;
+                    const bool f_in = left_first ? l_in : r_in, s_in = left_first ? r_in : l_in;
+                    const bool go_first = ((first < 0) | f_in) & !culled(f_tmin);
+                    const bool go_second = visit_second & ((second < 0) | s_in) & !culled(s_tmin);
                     if (go_second) {
                         if (sp > 0) { stk_ref[sp - 1] = top_ref; stk_tmin[sp - 1] = top_tmin; stk_tmax[sp - 1] = top_tmax; }
-                        top_ref = left_first ? rref : lref;
-                        top_tmin = left_first ? rtmin : ltmin;
-                        top_tmax = left_first ? rtmax : ltmax;
+                        top_ref = second; top_tmin = s_tmin; top_tmax = s_tmax;
                         sp++;
                     }
-                    cur = left_first ? lref : rref;
-                    cur_tmin = left_first ? ltmin : rtmin;
-                    cur_tmax = left_first ? ltmax : rtmax;
+                    cur = first; cur_tmin = f_tmin; cur_tmax = f_tmax;
                     want_pop = !go_first;
                 };
                 if (decidable) {
