@@ -218,6 +218,23 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const R
                 // decisions stay in predicate registers instead of being materialised for a join.
                 auto descend = [&](bool left_first, bool visit_second, bool l_in, bool r_in) {
                     if (COUNT) c_boxes += 1 + (int)visit_second;
+                    if (CULL) {
+                        // A child that may not be entered gets a huge entry distance, so that one culling
+                        // comparison per child decides everything: go <=> !(tmin_eff > cull limit).
+                        // (NaN entries are never "culled", exactly as with the explicit flags.)
+                        const float l_eff = ((lref < 0) | l_in) ? ltmin : 3.0e38f, r_eff = ((rref < 0) | r_in) ? rtmin : 3.0e38f;
+                        const float f_eff = left_first ? l_eff : r_eff, s_eff = left_first ? r_eff : l_eff;
+                        const bool go_first = !culled(f_eff);
+                        const bool go_second = visit_second & !culled(s_eff);
+                        if (go_second) {
+                            if (sp > 0) { stk_ref[sp - 1] = top_ref; stk_tmin[sp - 1] = top_tmin; stk_tmax[sp - 1] = top_tmax; }
+                            top_ref = left_first ? rref : lref; top_tmin = s_eff; top_tmax = left_first ? rtmax : ltmax;
+                            sp++;
+                        }
+                        cur = left_first ? lref : rref; cur_tmin = f_eff; cur_tmax = left_first ? ltmax : rtmax;
+                        want_pop = !go_first;
+                        return;
+                    }
                     // order the two children first, then judge them: fewer live predicates
                     const int first = left_first ? lref : rref, second = left_first ? rref : lref;
                     const float f_tmin = left_first ? ltmin : rtmin, f_tmax = left_first ? ltmax : rtmax;
