@@ -30,7 +30,7 @@ TILE = 32
 
 EXPORTS = [
     "rtb_last_error", "rtb_version", "rtb_device_count", "rtb_set_device", "rtb_read_ply", "rtb_free", "rtb_write_ply",
-    "rtb_mesh_geodesic", "rtb_mesh_create", "rtb_mesh_build_tree", "rtb_mesh_num_triangles", "rtb_mesh_num_nodes",
+    "rtb_mesh_geodesic", "rtb_mesh_create", "rtb_mesh_build_tree", "rtb_mesh_build_tree_on", "rtb_mesh_num_triangles", "rtb_mesh_num_nodes",
     "rtb_mesh_get_tree", "rtb_mesh_build_seconds", "rtb_mesh_destroy", "rtb_camera_create", "rtb_camera_get_basis",
     "rtb_camera_add_object", "rtb_camera_color_pixels", "rtb_camera_host_color", "rtb_camera_host_ids",
     "rtb_camera_counters", "rtb_camera_destroy", "rtb_object_create", "rtb_object_transform", "rtb_object_get_matrix",
@@ -59,6 +59,7 @@ def _load():
     L.rtb_mesh_geodesic.argtypes = [ci, cf, vp, cf, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_uint32)]
     L.rtb_mesh_create.argtypes = [vp, i64, vp, vp, C.POINTER(vp)]
     L.rtb_mesh_build_tree.argtypes = [vp]
+    L.rtb_mesh_build_tree_on.argtypes = [vp, ci]
     L.rtb_mesh_num_triangles.argtypes = [vp]
     L.rtb_mesh_num_triangles.restype = i64
     L.rtb_mesh_num_nodes.argtypes = [vp]
@@ -182,9 +183,9 @@ class Trixel:
         """Trixel.h:386.  The six sorted lists are produced together with the partition in create_kd()."""
         return 0
 
-    def create_kd(self):
-        """Trixel.h:135 (+ set_sorted_voxels): build the 2n-1 node tree."""
-        _check(lib.rtb_mesh_build_tree(self.h), "rtb_mesh_build_tree")
+    def create_kd(self, where=0):
+        """Trixel.h:135 (+ set_sorted_voxels): build the 2n-1 node tree.  where: 0 auto, 1 host, 2 GPU."""
+        _check(lib.rtb_mesh_build_tree_on(self.h, where), "rtb_mesh_build_tree_on")
         return 0
 
     def build_seconds(self):

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librtb.so")
 DRIVER = os.path.join(HERE, "rtb_render")  # headless driver (csrc/rtb_render_main.cpp)
-SOURCES = ["rtb_api.cu", "rtb_host.cpp"]
+SOURCES = ["rtb_api.cu", "rtb_build.cu", "rtb_host.cpp"]
 HEADERS = ["rtb_host.hpp", "rtb_kernels.cuh", "rtb_render.cuh", os.path.join("..", "..", "include", "rtb.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-O3,-ffp-contract=off,-fno-fast-math,-pthread", "-Xptxas", "-v", "-shared", "-cudart", "static"]

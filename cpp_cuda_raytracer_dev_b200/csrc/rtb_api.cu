@@ -48,6 +48,7 @@ struct rtb_mesh {
     float* d_points = nullptr;  // Trixel::d_points_init_data
     rtb::HostTree tree;
     bool built = false;
+    bool built_on_device = false;
 };
 
 struct rtb_camera {
@@ -314,12 +315,24 @@ int rtb_mesh_create(const float* points9, int64_t num_tri, const float* rad3, co
     return e == cudaSuccess ? RTB_OK : RTB_ERR_CUDA;
 }
 
-int rtb_mesh_build_tree(rtb_mesh* mesh) {
+int rtb_mesh_build_tree_on(rtb_mesh* mesh, int where) {
     if (!mesh) return fail(RTB_ERR_ARG, "build_tree: null mesh");
-    rtb::build_tree(mesh->points.data(), mesh->n, mesh->tree, 0);
+    if (where < 0 || where > 2) return fail(RTB_ERR_ARG, "build_tree: where must be 0 (auto), 1 (host) or 2 (device)");
+    const bool device = where == 2 || (where == 0 && mesh->d_points != nullptr);
+    if (device) {
+        if (!mesh->d_points) return fail(RTB_ERR_CUDA, "build_tree: the mesh has no device copy (no usable GPU)");
+        RTB_CUDA(cudaSetDevice(mesh->device));
+        const std::string err = rtb::build_tree_gpu(mesh->d_points, mesh->n, mesh->tree);
+        if (!err.empty()) return fail(RTB_ERR_CUDA, err);
+        g_launches += 1;
+    } else {
+        rtb::build_tree(mesh->points.data(), mesh->n, mesh->tree, 0);
+    }
     mesh->built = true;
+    mesh->built_on_device = device;
     return RTB_OK;
 }
+int rtb_mesh_build_tree(rtb_mesh* mesh) { return rtb_mesh_build_tree_on(mesh, 0); }
 int64_t rtb_mesh_num_triangles(const rtb_mesh* mesh) { return mesh ? mesh->n : 0; }
 int64_t rtb_mesh_num_nodes(const rtb_mesh* mesh) { return mesh ? 2 * mesh->n - 1 : 0; }
 

@@ -36,6 +36,8 @@ struct HostTree {
 };
 // threads <= 0: use all hardware threads
 void build_tree(const float* points9, int64_t num_tri, HostTree& out, int threads = 0);
+// the same tree built on the current CUDA device from device-resident points (rtb_build.cu); returns the error text or ""
+std::string build_tree_gpu(const float* d_points9, int64_t num_tri, HostTree& out);
 
 // ---- camera (Camera.cpp:5-67) ----------------------------------------------------------------
 struct CameraBasis {

@@ -92,6 +92,9 @@ int rtb_mesh_create(const float* points9, int64_t num_tri, const float* rad3, co
 /* Trixel::set_sorted_voxels + Trixel::create_kd (Trixel.h:386, Trixel.h:135; sort.h:11): six sorted
  * AABB lists, object-median split, BFS numbering, 2n-1 nodes.  Same tree as the reference, bit for bit. */
 int rtb_mesh_build_tree(rtb_mesh* mesh);
+/* same, choosing where the build runs: 0 = on the GPU when the mesh has a device copy (default), 1 = host threads,
+ * 2 = GPU (radix-sorted lists + level-synchronous partition, csrc/rtb_build.cu).  Both produce the identical tree. */
+int rtb_mesh_build_tree_on(rtb_mesh* mesh, int where);
 int64_t rtb_mesh_num_triangles(const rtb_mesh* mesh);
 int64_t rtb_mesh_num_nodes(const rtb_mesh* mesh); /* Trixel::num_voxels */
 /* copy the host tree out in the reference's kd_tree_node terms (Trixel.h:68-79): per node

@@ -62,6 +62,36 @@ def test_exactness_arguments_hold_on_device(gpu):
         assert r["decidable"] > (1 << 24)
 
 
+@pytest.mark.parametrize("case", ["one", "two", "seven", "ico16", "ico64", "ties", "bunny", "walls", "ico209"])
+def test_device_tree_build_equals_host_build(gpu, case):
+    """rtb_build.cu (radix sort + level-synchronous partition on the GPU) against the host builder, which
+    tests/test_host_cpu.py pins to the oracle and the reference: every array bit-identical."""
+    base = gpu.geodesic_mesh(2)
+    if case == "bunny":
+        path = mesh_path("rabbit_70k.ply")
+        if path is None:
+            pytest.skip("rabbit_70k.ply not shipped")
+        pts = gpu.read_ply(path, 1)
+    elif case == "walls":
+        path = mesh_path("3_walls.ply")
+        if path is None:
+            pytest.skip("3_walls.ply not shipped")
+        pts = gpu.read_ply(path, -1)
+    else:
+        pts = {"one": base[:1], "two": base[:2], "seven": base[:7], "ico16": gpu.geodesic_mesh(16), "ico64": gpu.geodesic_mesh(64),
+               "ties": np.concatenate([base, base, base[::-1]]), "ico209": gpu.geodesic_mesh(209)}[case]
+    host = gpu.Trixel(pts)
+    host.create_kd(where=1)
+    dev = gpu.Trixel(pts)
+    dev.create_kd(where=2)
+    th, td = host.tree(), dev.tree()
+    for name in ("left", "right", "tri", "cut_flag"):
+        assert np.array_equal(th[name], td[name]), name
+    for name in ("bounds", "s1", "s2"):
+        assert np.array_equal(th[name].view(np.uint32), td[name].view(np.uint32)), name
+    host.close(); dev.close()
+
+
 def test_icosphere_frames_cull_and_nocull(gpu, orc):
     pts = gpu.geodesic_mesh(24)
     p = Pair(gpu, orc, pts, 320, 180)
