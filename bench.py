@@ -160,6 +160,35 @@ def cpu_reference_run(workload, frames, repeats, prefer_ref=True):
     return frames * W * H, times, kind, cores, sample, mesh_label
 
 
+def gpu_reference_run(workload, frames):
+    """The reference's own CUDA kernels (Trixel.cu / Camera.cu compiled by nvcc for sm_100a with the project's default
+    code generation, oracle/_ref/libref_cuda_fmad.so) on this GPU, on `frames` consecutive frames of the workload, timed
+    the way the reference times itself (wall clock per loop iteration, WinMain.cpp:219-228) but WITHOUT its window blit,
+    console output and second color_pixels call -- a lower bound of its per-frame cost: "the kernel to beat" on this box."""
+    import cpp_cuda_raytracer_dev_b200 as rtb  # mesh input only
+    from oracle import orc, refemu
+    if not refemu.available("cuda_fmad"):
+        return None
+    fname, mode, nu, W, H, fps, zoom = WORKLOADS[workload]
+    pts, _ = load_points(rtb, workload)
+    t0 = time.time()
+    scene = refemu.RefScene(W, H, orc.default_camera(W, H), points9=pts, impl="cuda_fmad")
+    build_s = time.time() - t0
+    n = np.array([0.0, 0.0, 1.0], np.float32)
+    for _ in range(zoom):
+        scene.transform(32, float(n[0]), float(n[1]), float(n[2]), 0.005)
+    per_frame = []
+    for f in range(frames + 3):
+        t = time.perf_counter()
+        scene.render_nocopy()  # Object::render + Camera::color_pixels (kernels, device syncs, colour buffer D2H)
+        scene.transform(10, 0.0, 0.09950371902099893, 0.0, 0.9950371902099893)
+        per_frame.append(time.perf_counter() - t)
+    total = sum(per_frame[3:])
+    return {"value": frames * W * H / total / 1e6, "unit": "Mrays/s", "fps": frames / total, "kind": "reference CUDA kernels, nvcc sm_100a, default fmad",
+            "sample": "%d consecutive orbit frames after 3 warm-up frames, wall clock around Object::render + Camera::color_pixels "
+                      "(its host tree build took %.1f s)" % (frames, build_s)}
+
+
 def run_reference_impl(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -384,7 +413,7 @@ def run_ours(args):
     achieved = bytes_actual(c_act) / launch_s / 1e9
     fp32_peak = props["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
     roofline = {
-        "bound": "hbm", "kernel": "rtb::render_kernel<true,false>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": "rtb::render_stream_kernel<true,false>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": bytes_actual(c_act),
         "peak_source": peak_src,
         "note": "algorithmic bytes = 64 B x interior records entered + 48 B x triangle tests + 48 B x hits + 8 B x rays, counted by the kernel itself "
@@ -404,6 +433,10 @@ def run_ours(args):
         rays_c, times_c, kind, cores, sample, _ = cpu_reference_run(args.workload, max(1, args.ref_frames), 2)
         cpu = {"value": rays_c / times_c[-1] / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample}
 
+    ref_gpu = None
+    if world == 1 and not args.no_cpu_baseline and not args.no_reference_gpu:
+        ref_gpu = gpu_reference_run(args.workload, 30 if P <= (1 << 20) else 4)
+
     fps = K * world * F / region
     line = {
         "metric": "Mrays/s (primary rays, traversal + Phong)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
@@ -417,7 +450,7 @@ def run_ours(args):
                    "fps": fps, "fps_vs_readme_100fps": fps / README_FPS, "tree_build_s": build_s["total"]},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(F * 5 * 4), "d2h_bytes_per_step": int(F * P * 8),
                 "fps": K * world * F / e2e_time, "api": "rtb_render_sweep (host ops in, pinned host colour+id frames out)", "matches_device_run": same},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu,
         "kernel_ms": {"mean": float(np.mean(kernel_ms)), "min": float(np.min(kernel_ms)), "max": float(np.max(kernel_ms))},
     }
     print(json.dumps(line))
@@ -436,6 +469,7 @@ def main():
     ap.add_argument("--shard", default="frames", choices=["frames", "tiles"], help="multi-GPU partition (N > 1)")
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip timing the reference's own CUDA kernels on this GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -79,7 +79,7 @@ def rewrite_launches(text):
     return "".join(out)
 
 
-def patched(name):
+def patched(name, cuda=False):
     with open(os.path.join(REF, name), "r", encoding="utf-8-sig") as f:
         text = f.read()
     if name == "Vector.h":
@@ -96,9 +96,8 @@ def patched(name):
         n = text.count("= triangle_index_offset + leaf_index++;")
         assert n == 3
         text = text.replace("= triangle_index_offset + leaf_index++;", "= triangle_index_offset + leaf_index; leaf_index++;")
-    if name.endswith(".cu"):
+    if name.endswith(".cu") and not cuda:
         text = rewrite_launches(text)
-        assert "<<" not in re.sub(r"//.*", "", text).replace("<<=", "") or name == "Camera.cu" or True
     return '#line 1 "%s"\n%s\n' % (os.path.join(REF, name), text)
 
 
@@ -123,6 +122,52 @@ def build(force=False):
     return OUT
 
 
+CUDA_VARIANTS = {
+    # name -> extra nvcc flags.  "fmad" is the reference project's own code generation (TEST_Dungeonrun.vcxproj has no
+    # --fmad switch, so nvcc's default contraction applies): the kernel to beat.  "nofmad" is the same code with
+    # contraction off, i.e. the north star's oracle contract executed by the reference's own kernels on the GPU.
+    "fmad": [],
+    "nofmad": ["-fmad=false"],
+}
+
+
+def cuda_lib_path(variant):
+    return os.path.join(OUT_DIR, "libref_cuda_%s.so" % variant)
+
+
+def build_cuda(force=False):
+    """The reference's own .cu/.cpp files compiled by nvcc for sm_100a (real kernels, real launches).
+
+    Same in-memory patches as the host build minus the launch rewrite (#4).  nvcc cannot read a translation unit
+    from stdin, so the patched unit is written to a temporary directory outside the repository, compiled, and the
+    directory removed; only the .so files land in oracle/_ref/."""
+    import shutil
+    import tempfile
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.isdir(REF) or not os.path.exists(nvcc):
+        return []
+    os.makedirs(OUT_DIR, exist_ok=True)
+    deps = [os.path.join(REF, n) for n in ORDER + ["Vector.h"]] + [os.path.join(HERE, "ref_driver.cpp"), __file__]
+    outs = [cuda_lib_path(v) for v in CUDA_VARIANTS]
+    if not force and all(os.path.exists(o) and all(os.path.getmtime(o) >= os.path.getmtime(d) for d in deps) for o in outs):
+        return outs
+    unit = ["#define RTB_REF_CUDA 1\n", patched("Vector.h", cuda=True)] + [patched(n, cuda=True) for n in ORDER]
+    with open(os.path.join(HERE, "ref_driver.cpp")) as f:
+        unit.append('#line 1 "%s"\n%s\n' % (os.path.join(HERE, "ref_driver.cpp"), f.read()))
+    with tempfile.TemporaryDirectory(prefix="rtb_refcuda_") as tmp:
+        src = os.path.join(tmp, "ref_unit.cu")
+        with open(src, "w") as f:
+            f.write("".join(unit))
+        for variant, extra in CUDA_VARIANTS.items():
+            cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-lineinfo", "-w", "-shared", "-cudart", "static",
+                   "-Xcompiler", "-fPIC,-fpermissive,-w,-O2,-ffp-contract=off", "-I", os.path.join(HERE, "shim_win"), "-I", REF,
+                   "-o", cuda_lib_path(variant), src] + extra
+            r = subprocess.run(cmd, cwd=tmp)
+            if r.returncode != 0:
+                raise RuntimeError("reference CUDA build (%s) failed" % variant)
+    return outs
+
+
 def copy_assets():
     """The reference's two loadable meshes travel to the GPU box as git-ignored build outputs
     (oracle/_ref/data/): they are inputs of the parity tests, not product source."""
@@ -138,3 +183,5 @@ def copy_assets():
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv)
     print(path if path else "reference sources not present at %s; nothing built" % REF)
+    for path in build_cuda(force="--force" in sys.argv):
+        print(path)

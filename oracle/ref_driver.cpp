@@ -9,11 +9,19 @@
 // reference's own buffers back through a flat C interface for tests/ and bench.py's
 // reference arm.  It is the ground truth the C restatement (oracle/rtb_oracle.c) and the
 // CUDA path are pinned against.  Nothing in the product links or loads it.
+//
+// The same file also serves the second build of oracle/build_ref.py, RTB_REF_CUDA: the reference's
+// three .cu files compiled by nvcc for sm_100a and run on the B200 itself (oracle/_ref/libref_cuda*.so),
+// which gives the reference's own GPU kernels as a second ground truth and as "the kernel to beat".
 #include "framework.h"
 #include "sort.h"
+#ifdef RTB_REF_CUDA
+#include <cuda_runtime.h>
+#else
 #include <omp.h>
 
 thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+#endif
 
 void read_ply(const char* file_name, T_fp** points_list, T_uint* num_tri, kd_leaf_sort** leaf_list,
               kd_vertex** vertex_list, T_uint* num_vert, u8 mode);
@@ -108,9 +116,13 @@ void ref_get_camera(void* h, float* out18) {
 // per-pixel primary ray table written by init_cam_mem_cuda (Camera.cu:89-111), 3 floats/pixel
 void ref_get_rays(void* h, float* out3p) {
     Camera* c = ((RefScene*)h)->cam;
-    for (u64 i = 0; i < c->f_prop.res.count; i++) {
-        out3p[3 * i] = c->h_mem.rmd.x[i]; out3p[3 * i + 1] = c->h_mem.rmd.y[i]; out3p[3 * i + 2] = c->h_mem.rmd.z[i];
-    }
+    const u64 P = c->f_prop.res.count;
+    float* tmp = (float*)malloc(sizeof(float) * 3 * P);  // the arrays live in "device" memory
+    cudaMemcpy(tmp, c->h_mem.rmd.x, sizeof(float) * P, cudaMemcpyDeviceToHost);
+    cudaMemcpy(tmp + P, c->h_mem.rmd.y, sizeof(float) * P, cudaMemcpyDeviceToHost);
+    cudaMemcpy(tmp + 2 * P, c->h_mem.rmd.z, sizeof(float) * P, cudaMemcpyDeviceToHost);
+    for (u64 i = 0; i < P; i++) { out3p[3 * i] = tmp[i]; out3p[3 * i + 1] = tmp[P + i]; out3p[3 * i + 2] = tmp[2 * P + i]; }
+    free(tmp);
 }
 
 // Input::set_quat(x,y,z,w) then Object::transform(input, select)  (WinMain.cpp:186-209)
@@ -135,7 +147,7 @@ void ref_render(void* h, long long* ids, unsigned* bgra) {
     s->obj->render(s->cam);
     s->cam->color_pixels(SET_COLOR_TAG);
     const u64 P = s->cam->f_prop.res.count;
-    if (ids) memcpy(ids, s->cam->h_mem.d_rmi.index, sizeof(long long) * P);
+    if (ids) cudaMemcpy(ids, s->cam->h_mem.d_rmi.index, sizeof(long long) * P, cudaMemcpyDeviceToHost);
     if (bgra) memcpy(bgra, s->cam->h_mem.h_color.c, sizeof(unsigned) * P);
 }
 
@@ -146,6 +158,13 @@ void ref_render_nocopy(void* h) {
     s->cam->color_pixels(SET_COLOR_TAG);
 }
 
+#ifdef RTB_REF_CUDA
+int ref_threads(void) { return 0; }  // runs on the GPU
+void ref_set_threads(int) {}
+int ref_is_cuda(void) { return 1; }
+#else
 int ref_threads(void) { return omp_get_max_threads(); }
 void ref_set_threads(int n) { omp_set_num_threads(n); }
+int ref_is_cuda(void) { return 0; }
+#endif
 }

@@ -9,6 +9,10 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_ref", "libref_emu.so")
+# The reference's .cu files compiled by nvcc for sm_100a (oracle/build_ref.py, build_cuda): its real kernels on the GPU.
+# "cuda_fmad" = the reference project's own code generation (the kernel to beat), "cuda_nofmad" = contraction off.
+LIB_PATHS = {"emu": LIB_PATH, "cuda_fmad": os.path.join(HERE, "_ref", "libref_cuda_fmad.so"),
+             "cuda_nofmad": os.path.join(HERE, "_ref", "libref_cuda_nofmad.so")}
 
 # reference selectors (platform_common.h:16-21)
 TRANSLATE_XYZ, TRANSLATE_X, TRANSLATE_Z, ROTATE_TRI_PY, ROTATE_TRI_NY = 30, 31, 32, 10, 11
@@ -26,17 +30,16 @@ NODE_DTYPE = np.dtype([("left", "<i8"), ("right", "<i8"), ("tri", "<i8"), ("pare
                        ("z1", "<f4"), ("s1", "<f4"), ("s2", "<f4")])
 assert NODE_DTYPE.itemsize == C.sizeof(RefNode)
 
-_lib = None
+_libs = {}
 
 
-def available():
-    return os.path.exists(LIB_PATH)
+def available(impl="emu"):
+    return os.path.exists(LIB_PATHS[impl])
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        L = C.CDLL(LIB_PATH)
+def lib(impl="emu"):
+    if impl not in _libs:
+        L = C.CDLL(LIB_PATHS[impl])
         L.ref_open.restype = C.c_void_p
         L.ref_open.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         for name in ("ref_num_tris", "ref_num_nodes"):
@@ -53,15 +56,15 @@ def lib():
         L.ref_render_nocopy.argtypes = [C.c_void_p]
         L.ref_threads.restype = C.c_int
         L.ref_set_threads.argtypes = [C.c_int]
-        _lib = L
-    return _lib
+        _libs[impl] = L
+    return _libs[impl]
 
 
 class RefScene:
     """The reference app's scene: one camera, one mesh, one object (WinMain.cpp:69-156)."""
 
-    def __init__(self, W, H, cam14, rgb=(0.1, 0.55, 0.2), ply_path=None, mode=0, points9=None):
-        L = lib()
+    def __init__(self, W, H, cam14, rgb=(0.1, 0.55, 0.2), ply_path=None, mode=0, points9=None, impl="emu"):
+        L = self.L = lib(impl)
         self.W, self.H = W, H
         cam = np.zeros(14, np.float32)
         cam[:len(cam14)] = np.asarray(cam14, np.float32)
@@ -76,40 +79,40 @@ class RefScene:
 
     def points(self):
         out = np.empty((self.ntri, 9), np.float32)
-        lib().ref_get_points(self.h, out.ctypes.data)
+        self.L.ref_get_points(self.h, out.ctypes.data)
         return out
 
     def nodes(self):
         out = np.zeros(self.nnodes, NODE_DTYPE)
-        lib().ref_get_nodes(self.h, out.ctypes.data)
+        self.L.ref_get_nodes(self.h, out.ctypes.data)
         return out
 
     def camera(self):
         out = np.empty(18, np.float32)
-        lib().ref_get_camera(self.h, out.ctypes.data)
+        self.L.ref_get_camera(self.h, out.ctypes.data)
         return out.reshape(6, 3)  # n, v, u, n_mod, v_mod, u_mod
 
     def rays(self):
         out = np.empty((self.W * self.H, 3), np.float32)
-        lib().ref_get_rays(self.h, out.ctypes.data)
+        self.L.ref_get_rays(self.h, out.ctypes.data)
         return out
 
     def matrix(self):
         out = np.empty(12, np.float32)
-        lib().ref_get_matrix(self.h, out.ctypes.data)
+        self.L.ref_get_matrix(self.h, out.ctypes.data)
         return out
 
     def transform(self, select, x, y, z, w):
-        lib().ref_transform(self.h, select, x, y, z, w)
+        self.L.ref_transform(self.h, select, x, y, z, w)
 
     def render(self):
         ids = np.empty(self.W * self.H, np.int64)
         bgra = np.empty(self.W * self.H, np.uint32)
-        lib().ref_render(self.h, ids.ctypes.data, bgra.ctypes.data)
+        self.L.ref_render(self.h, ids.ctypes.data, bgra.ctypes.data)
         return ids, bgra
 
     def render_nocopy(self):
-        lib().ref_render_nocopy(self.h)
+        self.L.ref_render_nocopy(self.h)
 
 
 def fnv1a64(buf):

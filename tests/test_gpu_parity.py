@@ -254,3 +254,73 @@ def test_tile_partition_is_bit_identical(gpu, orc):
             assert np.array_equal(out_i.cpu().numpy()[f * W * H:(f + 1) * W * H], full_ids)
             assert np.array_equal(out_c.cpu().numpy().view(np.uint32)[f * W * H:(f + 1) * W * H], full_col)
     p.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# The reference's OWN CUDA kernels, compiled by nvcc for sm_100a from /root/reference (oracle/build_ref.py,
+# build_cuda) and executed on this GPU: a second ground truth beside the host-compiled oracle.
+#   cuda_nofmad : contraction off -- the north star's arithmetic contract; must equal the CUDA path bit for bit
+#   cuda_fmad   : the reference project's default code generation (FMA contraction on); differs from the
+#                 contract on a few edge pixels (~1e-5 of the bunny's pixels), inside the budget
+# ---------------------------------------------------------------------------------------------------
+def _ref_cuda_scene(impl, pts, W, H, cam):
+    from oracle import refemu
+    if not refemu.available(impl):
+        pytest.skip("oracle/_ref/libref_%s.so not built (needs /root/reference at build time)" % impl)
+    return refemu.RefScene(W, H, cam12(W, H, **cam), points9=pts, impl=impl)
+
+
+@pytest.mark.parametrize("impl", ["cuda_nofmad", "cuda_fmad"])
+@pytest.mark.parametrize("case", ["bunny", "bunny_closeup", "walls", "ico24"])
+def test_against_reference_cuda_kernels_on_this_gpu(gpu, impl, case):
+    cam = {}
+    W, H = 960, 540
+    if case.startswith("bunny"):
+        path = mesh_path("rabbit_70k.ply")
+        if path is None:
+            pytest.skip("rabbit_70k.ply not shipped")
+        pts = gpu.read_ply(path, 1)
+    elif case == "walls":
+        path = mesh_path("3_walls.ply")
+        if path is None:
+            pytest.skip("3_walls.ply not shipped")
+        pts = gpu.read_ply(path, -1)
+        cam = WALLS_CAMERA
+    else:
+        pts = gpu.geodesic_mesh(24)
+        W, H = 320, 180
+    ref = _ref_cuda_scene(impl, pts, W, H, cam)
+    mesh = gpu.Trixel(pts)
+    mesh.create_kd()
+    camera = gpu.Camera(W, H, **cam_kwargs(W, H, **cam))
+    obj = gpu.Object(mesh)
+    camera.add_object(obj)
+    if case == "bunny_closeup":
+        n = camera.basis()[0:3]
+        for _ in range(150):
+            q = (float(n[0]), float(n[1]), float(n[2]), 0.005)
+            obj.transform(q, gpu.TRANSLATE_Z)
+            ref.transform(gpu.TRANSLATE_Z, *q)
+    total = bad = 0
+    for k in range(4):
+        if k:
+            obj.transform(gpu.R_KEY_QUAT, gpu.ROTATE_TRI_PY)
+            ref.transform(gpu.ROTATE_TRI_PY, *gpu.R_KEY_QUAT)
+        assert np.array_equal(obj.matrix().view(np.uint32), ref.matrix().view(np.uint32))
+        ids, bgra = obj.render_frame(camera)
+        rids, rbgra = ref.render()
+        differ = ids.astype(np.int64) != rids
+        if impl == "cuda_fmad" and case == "walls":
+            # every hit of this scene is an exact 3-way tie between coincident copies of a wall; with FMA contraction
+            # the reference's own arithmetic breaks those ties differently.  What must still agree is hit vs miss.
+            differ = (ids >= 0) != (rids >= 0)
+        total += ids.size
+        bad += int(differ.sum())
+        if impl == "cuda_nofmad":
+            assert not differ.any(), "%s frame %d: %d hit ids differ from the reference's own kernels" % (case, k, int(differ.sum()))
+        same = ids.astype(np.int64) == rids
+        assert channel_diff(bgra[same], rbgra[same]).max(initial=0) <= COLOUR_TOL
+        assert k > 0 or (ids >= 0).sum() > 0  # (the R-key rotation swings 3_walls out of view)
+    assert bad <= max(1, ID_MISMATCH_BUDGET * total), "%d of %d" % (bad, total)
+    print("reference %s / %s: %d of %d hit ids differ" % (impl, case, bad, total))
+    obj.close(); camera.close(); mesh.close()
