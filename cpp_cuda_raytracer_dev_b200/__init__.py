@@ -35,7 +35,7 @@ EXPORTS = [
     "rtb_camera_add_object", "rtb_camera_color_pixels", "rtb_camera_host_color", "rtb_camera_host_ids",
     "rtb_camera_counters", "rtb_camera_destroy", "rtb_object_create", "rtb_object_transform", "rtb_object_get_matrix",
     "rtb_object_set_matrix", "rtb_object_destroy", "rtb_object_render", "rtb_render_frame", "rtb_render_sweep",
-    "rtb_render_frames_device_async", "rtb_object_transform_host", "rtb_device_props", "rtb_launch_count", "rtb_tile_major_elements", "rtb_compose_tiles_device_async", "rtb_selftest_exact",
+    "rtb_render_frames_device_async", "rtb_render_frames_push_async", "rtb_peer_alloc", "rtb_peer_free", "rtb_peer_export", "rtb_peer_open", "rtb_peer_close", "rtb_peer_read", "rtb_object_transform_host", "rtb_device_props", "rtb_launch_count", "rtb_tile_major_elements", "rtb_compose_tiles_device_async", "rtb_selftest_exact",
 ]
 
 
@@ -93,6 +93,13 @@ def _load():
     L.rtb_device_props.argtypes = [vp]
     L.rtb_launch_count.restype = C.c_uint64
     L.rtb_selftest_exact.argtypes = [C.c_uint64, C.c_int64, vp]
+    L.rtb_render_frames_push_async.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_uint32, vp, vp, vp]
+    L.rtb_peer_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.rtb_peer_free.argtypes = [vp]
+    L.rtb_peer_export.argtypes = [vp, vp]
+    L.rtb_peer_open.argtypes = [vp, C.POINTER(vp)]
+    L.rtb_peer_close.argtypes = [vp]
+    L.rtb_peer_read.argtypes = [vp, vp, C.c_size_t]
     L.rtb_tile_major_elements.restype = C.c_int64
     L.rtb_tile_major_elements.argtypes = [vp, C.c_int32]
     L.rtb_compose_tiles_device_async.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp]
@@ -331,10 +338,57 @@ class Object:
                                                   d_bgra_ptr or None, d_ids_ptr or None, stream_ptr or None),
                "rtb_render_frames_device_async")
 
+    def render_frames_push_async(self, camera, m12, frame_bgra_ptr, frame_ids_ptr, stream_ptr=None, tile_first=0, tile_stride=1,
+                                 flags=RENDER_DEFAULT):
+        """Render this rank's tiles and push every finished work unit straight into the final frames, which may be
+        another GPU's memory (peer_open).  See rtb_render_frames_push_async in include/rtb.h."""
+        if stream_ptr == 0:
+            stream_ptr = 1  # cudaStreamLegacy
+        m = np.ascontiguousarray(m12, np.float32).reshape(-1, 12)
+        _check(lib.rtb_render_frames_push_async(self.h, camera.h, m.shape[0], m.ctypes.data, tile_first, tile_stride, flags,
+                                                frame_bgra_ptr or None, frame_ids_ptr or None, stream_ptr or None),
+               "rtb_render_frames_push_async")
+
     def close(self):
         if self.h:
             lib.rtb_object_destroy(self.h)
             self.h = None
+
+
+class PeerBuffer:
+    """A device allocation other ranks' GPUs can write into (rtb_peer_alloc + rtb_peer_export)."""
+
+    def __init__(self, nbytes):
+        p = C.c_void_p()
+        _check(lib.rtb_peer_alloc(nbytes, C.byref(p)), "rtb_peer_alloc")
+        self.ptr, self.nbytes = p.value, nbytes
+
+    def handle(self):
+        h = (C.c_uint8 * 64)()
+        _check(lib.rtb_peer_export(self.ptr, h), "rtb_peer_export")
+        return bytes(h)
+
+    def close(self):
+        if self.ptr:
+            _check(lib.rtb_peer_free(self.ptr), "rtb_peer_free")
+            self.ptr = None
+
+
+def peer_open(handle):
+    """Map a peer rank's PeerBuffer (its 64-byte handle) into this process; returns the device pointer."""
+    h = (C.c_uint8 * 64).from_buffer_copy(handle)
+    p = C.c_void_p()
+    _check(lib.rtb_peer_open(h, C.byref(p)), "rtb_peer_open")
+    return p.value
+
+
+def memcpy_d2h(host_array, device_ptr):
+    """Synchronous device-to-host copy of host_array.nbytes bytes (rtb_peer_read)."""
+    _check(lib.rtb_peer_read(host_array.ctypes.data, device_ptr, host_array.nbytes), "rtb_peer_read")
+
+
+def peer_close(ptr):
+    _check(lib.rtb_peer_close(ptr), "rtb_peer_close")
 
 
 def orbit_ops(num_frames, quat=R_KEY_QUAT, select=ROTATE_TRI_PY, first_frame_identity=True):

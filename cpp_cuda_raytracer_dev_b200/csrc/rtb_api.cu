@@ -68,6 +68,10 @@ struct rtb_camera {
     uint32_t* stage_bgra[2] = {nullptr, nullptr};
     int32_t* stage_ids[2] = {nullptr, nullptr};
     int ring_frames = 0;
+    // peer push: this GPU's tile-major staging of the frames in flight (rtb_render_frames_push_async)
+    uint32_t* push_bgra = nullptr;
+    int32_t* push_ids = nullptr;
+    size_t push_elements = 0;
     rtb_object* bound = nullptr;
     int sm_count = 0;
 };
@@ -157,7 +161,8 @@ void fill_frame_record(const rtb_object* o, const rtb_camera* c, const float m12
 
 // Launch the persistent render kernel over `num_frames` matrices already resident in o->d_frames.
 int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, int num_frames, int tile_first, int tile_stride,
-                  uint32_t flags, uint32_t* d_bgra, int32_t* d_ids, cudaStream_t stream) {
+                  uint32_t flags, uint32_t* d_bgra, int32_t* d_ids, cudaStream_t stream, uint32_t* push_bgra = nullptr,
+                  int32_t* push_ids = nullptr) {
     using namespace rtb;
     RenderParams P;
     std::memset(&P, 0, sizeof P);
@@ -180,7 +185,9 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, int num_f
     P.my_tiles = tile_first < tiles ? (tiles - tile_first + tile_stride - 1) / tile_stride : 0;
     P.total_items = (long long)num_frames * P.my_tiles;
     P.out_bgra = d_bgra; P.out_ids = d_ids;
-    P.tile_major = (flags & RTB_RENDER_TILE_MAJOR) ? 1 : 0;
+    const bool push = push_bgra || push_ids;
+    P.push_bgra = push_bgra; P.push_ids = push_ids;
+    P.tile_major = ((flags & RTB_RENDER_TILE_MAJOR) || push) ? 1 : 0;
     P.frame_stride = P.tile_major ? (long long)((tiles + tile_stride - 1) / tile_stride) * kTile * kTile : (long long)b.W * b.H;
     P.work_counter = o->d_work;
     P.counters = c->d_counters;
@@ -189,8 +196,9 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, int num_f
 
     const bool cull = !(flags & RTB_RENDER_NO_CULL), count = (flags & RTB_RENDER_COUNTERS) != 0;
     auto env_int = [](const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; };
-    void (*kern)(const RenderParams) = cull ? (count ? render_stream_kernel<true, true> : render_stream_kernel<true, false>)
-                                            : (count ? render_stream_kernel<false, true> : render_stream_kernel<false, false>);
+    void (*kern)(const RenderParams) = cull ? (count ? render_stream_kernel<true, true, false> : render_stream_kernel<true, false, false>)
+                                            : (count ? render_stream_kernel<false, true, false> : render_stream_kernel<false, false, false>);
+    if (push) kern = cull ? render_stream_kernel<true, false, true> : render_stream_kernel<false, false, true>;
     int per_sm = 0;
     RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, 0));
     per_sm = std::max(per_sm, 1);
@@ -553,7 +561,7 @@ void rtb_camera_destroy(rtb_camera* cam) {
     cudaSetDevice(cam->device);
     if (cam->stream) cudaStreamSynchronize(cam->stream);
     if (cam->copy_stream) cudaStreamSynchronize(cam->copy_stream);
-    dfree(cam->d_bgra); dfree(cam->d_ids); dfree(cam->d_counters);
+    dfree(cam->d_bgra); dfree(cam->d_ids); dfree(cam->d_counters); dfree(cam->push_bgra); dfree(cam->push_ids);
     if (cam->h_bgra) cudaFreeHost(cam->h_bgra);
     if (cam->h_ids) cudaFreeHost(cam->h_ids);
     for (int k = 0; k < 2; k++) {
@@ -664,6 +672,70 @@ int rtb_render_frames_device_async(rtb_object* obj, rtb_camera* cam, int32_t num
     for (int f = 0; f < num_frames; f++) fill_frame_record(obj, cam, m12 + 12 * (size_t)f, obj->h_frames + rtb::kFrameStride * (size_t)f);
     RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * rtb::kFrameStride * (size_t)num_frames, cudaMemcpyHostToDevice, s));
     return launch_render(obj, cam, obj->d_frames, num_frames, tile_first, tile_stride, flags, d_bgra, d_ids, s);
+}
+
+int rtb_render_frames_push_async(rtb_object* obj, rtb_camera* cam, int32_t num_frames, const float* m12, int32_t tile_first,
+                                 int32_t tile_stride, uint32_t flags, uint32_t* d_frame_bgra, int32_t* d_frame_ids, void* stream) {
+    int rc = check_bound(obj, cam, "render_frames_push");
+    if (rc) return rc;
+    if (num_frames <= 0 || !m12 || (!d_frame_bgra && !d_frame_ids)) return fail(RTB_ERR_ARG, "render_frames_push: bad argument");
+    if (flags & RTB_RENDER_COUNTERS) return fail(RTB_ERR_ARG, "render_frames_push: counters are not available in the push variant");
+    RTB_CUDA(cudaSetDevice(cam->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : cam->stream;
+    RTB_CUDA(cudaStreamSynchronize(s));  // the pinned matrix staging buffer and the tile staging are reused
+    rc = ensure_frames(obj, num_frames);
+    if (rc) return rc;
+    const size_t need = (size_t)num_frames * (size_t)rtb_tile_major_elements(cam, tile_stride);
+    if (cam->push_elements < need) {
+        dfree(cam->push_bgra); dfree(cam->push_ids);
+        cam->push_elements = 0;
+        RTB_CUDA(cudaMalloc(&cam->push_bgra, 4 * need));
+        RTB_CUDA(cudaMalloc(&cam->push_ids, 4 * need));
+        cam->push_elements = need;
+    }
+    for (int f = 0; f < num_frames; f++) fill_frame_record(obj, cam, m12 + 12 * (size_t)f, obj->h_frames + rtb::kFrameStride * (size_t)f);
+    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * rtb::kFrameStride * (size_t)num_frames, cudaMemcpyHostToDevice, s));
+    return launch_render(obj, cam, obj->d_frames, num_frames, tile_first, tile_stride, flags, d_frame_bgra ? cam->push_bgra : nullptr,
+                         d_frame_ids ? cam->push_ids : nullptr, s, d_frame_bgra, d_frame_ids);
+}
+
+// ---- peer memory: frames other processes' GPUs can write into over NVLink ---------------------------
+int rtb_peer_alloc(size_t bytes, void** d_ptr) {
+    if (!d_ptr || bytes == 0) return fail(RTB_ERR_ARG, "peer_alloc: bad argument");
+    RTB_CUDA(cudaSetDevice(g_device));
+    RTB_CUDA(cudaMalloc(d_ptr, bytes));  // a whole allocation of its own: that is what an IPC handle names
+    return RTB_OK;
+}
+int rtb_peer_free(void* d_ptr) {
+    if (d_ptr) RTB_CUDA(cudaFree(d_ptr));
+    return RTB_OK;
+}
+int rtb_peer_export(void* d_ptr, uint8_t handle64[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!d_ptr || !handle64) return fail(RTB_ERR_ARG, "peer_export: bad argument");
+    cudaIpcMemHandle_t h;
+    RTB_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+    std::memcpy(handle64, &h, 64);
+    return RTB_OK;
+}
+int rtb_peer_open(const uint8_t handle64[64], void** d_ptr) {
+    if (!d_ptr || !handle64) return fail(RTB_ERR_ARG, "peer_open: bad argument");
+    RTB_CUDA(cudaSetDevice(g_device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    RTB_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RTB_OK;
+}
+int rtb_peer_read(void* host_dst, const void* d_ptr, size_t bytes) {
+    if (!host_dst || !d_ptr) return fail(RTB_ERR_ARG, "peer_read: bad argument");
+    RTB_CUDA(cudaSetDevice(g_device));
+    RTB_CUDA(cudaDeviceSynchronize());
+    RTB_CUDA(cudaMemcpy(host_dst, d_ptr, bytes, cudaMemcpyDeviceToHost));
+    return RTB_OK;
+}
+int rtb_peer_close(void* d_ptr) {
+    if (d_ptr) RTB_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return RTB_OK;
 }
 
 int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32_t steps_per_frame, const float* ops5,

@@ -33,6 +33,7 @@ constexpr int kTile = 32;        // multi-GPU interleave granularity: 32x32 pixe
 constexpr int kStackDepth = 40;  // >= tree height + 2 (median split: height = ceil(log2 n))
 constexpr int kBlockThreads = 128;
 constexpr int kFrameStride = 16;
+constexpr int kPushSlots = 8;    // work units a warp may have open at once in the peer-push variant
 constexpr unsigned kRefLeaf = 0x80000000u, kRefIndexMask = 0x1fffffffu;
 constexpr int kRefAxisShift = 29;
 
@@ -60,6 +61,11 @@ struct RenderParams {
     int tile_major;          // 1: compact tile-major output (the multi-GPU exchange format), 0: final row-major position
     uint32_t* __restrict__ out_bgra;
     int32_t* __restrict__ out_ids;
+    // peer push (render_stream_kernel<.., PUSH = true>): out_* is this GPU's tile-major staging, and every finished
+    // work unit is copied by its warp, as 16-byte row segments, to its final row-major place in these full-frame
+    // buffers (W*H elements per frame) -- which may be another GPU's memory mapped over NVLink
+    uint32_t* push_bgra;
+    int32_t* push_ids;
     unsigned long long* work_counter;
     unsigned long long* counters;  // [0] rays [1] interior nodes entered [2] nodes popped (reference sense) [3] triangle tests [4] hits
     float cull_rel;

@@ -121,10 +121,22 @@ __global__ void selftest_exact_kernel(uint64_t seed, long long count, unsigned l
     if (dec) atomicAdd(out + 3, 1ull);
 }
 
-template <bool CULL, bool COUNT>
+// PUSH = the multi-GPU tile exchange fused into the render: the warp writes its pixels into a local tile-major
+// staging buffer as usual, keeps a count of the pixels each of its open work units still owes, and the moment a
+// unit is complete copies it -- 16-byte row segments, one load and one store per lane and array for a 128-pixel
+// unit -- to its final row-major place in P.push_*, typically rank 0's frame mapped over NVLink.  The transfer
+// therefore overlaps the rendering unit by unit, and there is no gather, no receive buffer and no reassembly pass.
+// A unit belongs to exactly one warp, so the bookkeeping is warp-local (shared-memory counters, __syncwarp).
+template <bool CULL, bool COUNT, bool PUSH>
 __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const RenderParams P) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanemask_lt = (1u << lane) - 1u;
+    __shared__ int s_owed[PUSH ? kBlockThreads / 32 : 1][PUSH ? kPushSlots : 1];   // pixels of an open unit not yet written
+    __shared__ int4 s_unit[PUSH ? kBlockThreads / 32 : 1][PUSH ? kPushSlots : 1];  // frame, tile slot, x and y offset inside the tile
+    const int wib = threadIdx.x >> 5;
+    unsigned open_mask = 0u;   // warp-uniform: slots of s_owed/s_unit in use
+    int my_pslot = 0, u_pslot = 0;
+    bool blocked = false;      // warp-uniform: no free slot for the next unit -> drain in-flight rays first
     unsigned long long c_nodes = 0, c_boxes = 0, c_tris = 0, c_rays = 0, c_hits = 0;
 
     // Traversal stack: the top entry lives in registers (top_*), deeper entries in local memory.
@@ -165,7 +177,7 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const R
         // ================= traversal: steps until enough lanes have run dry ==========================
         // (while pixels remain, fall out to retire + refill as soon as no more than t_active lanes are
         // still traversing; once the work is exhausted, drain)
-        const int keep_active = exhausted ? 0 : P.t_active;
+        const int keep_active = (exhausted | (PUSH && blocked)) ? 0 : P.t_active;
         while (__popc(m_trav) > keep_active) {
             // ---- lanes that finished a node or leaf take the stack top ------------------------------
             if (want_pop) {
@@ -271,12 +283,14 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const R
             // frames are write-once streams: keep them from displacing the scene in L2
             if (P.out_bgra) __stcs(P.out_bgra + o, color);
             if (P.out_ids) __stcs(P.out_ids + o, id);
+            if (PUSH) atomicSub(&s_owed[wib][my_pslot], 1);
             state = kStateEmpty;
         }
         const unsigned m_empty = ~m_trav;
 
         // ================= refill: next pixels of the warp's unit ====================================
-        if (!exhausted && u_next >= unit_pixels) {
+        if (PUSH && !exhausted && u_next >= unit_pixels) blocked = open_mask == (1u << kPushSlots) - 1u;
+        if (!exhausted && u_next >= unit_pixels && !(PUSH && blocked)) {
             unsigned long long uid = 0;
             if (lane == 0) uid = atomicAdd(P.work_counter, 1ull);
             uid = __shfl_sync(0xffffffffu, uid, 0);
@@ -295,14 +309,23 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const R
                 const float* __restrict__ F = P.frames + (long long)kFrameStride * u_frame;
                 u_rx0 = __float_as_int(__ldg(F + 12)); u_ry0 = __float_as_int(__ldg(F + 13));
                 u_rx1 = __float_as_int(__ldg(F + 14)); u_ry1 = __float_as_int(__ldg(F + 15));
+                if (PUSH) {
+                    u_pslot = __ffs(~open_mask) - 1;
+                    open_mask |= 1u << u_pslot;
+                    if (lane == 0) {
+                        s_owed[wib][u_pslot] = unit_pixels;
+                        s_unit[wib][u_pslot] = make_int4(u_frame, u_slot, (int)compact_even_bits((uint32_t)u_base), (int)compact_even_bits((uint32_t)u_base >> 1));
+                    }
+                    __syncwarp();
+                }
             }
         }
-        if (exhausted) {
-            if (m_trav == 0u) break;  // nothing in flight, nothing left to fetch
-        } else {
+        if (!exhausted) {
             const int slot = __popc(m_empty & lanemask_lt);
             const int avail = unit_pixels - u_next;
+            bool settled = false;  // PUSH: this lane took a pixel that needs no ray (outside the image, or background)
             if (((m_empty >> lane) & 1u) && slot < avail) {
+                settled = true;
                 const uint32_t K = (uint32_t)(u_base + u_next + slot);  // Morton ordinal inside the 32x32 tile
                 const int lx = (int)compact_even_bits(K), ly = (int)compact_even_bits(K >> 1);
                 const int px = u_x0 + lx, py = u_y0 + ly;
@@ -318,6 +341,8 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const R
                     } else {
                         frame = u_frame;
                         pix = opix;
+                        settled = false;
+                        my_pslot = u_pslot;
                         const float* __restrict__ M = P.frames + (long long)kFrameStride * frame;
                         // ---- primary ray, Camera.cu:103-104 (row 0 = bottom) --------------------------
                         const float fxp = (float)px, fyp = (float)py;
@@ -364,7 +389,43 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const R
             }
             const int want = __popc(m_empty);
             u_next += want < avail ? want : avail;
+            if (PUSH) {
+                const int n_settled = __popc(__ballot_sync(0xffffffffu, settled));
+                if (lane == 0 && n_settled) atomicSub(&s_owed[wib][u_pslot], n_settled);
+            }
         }
+        if (PUSH) {
+            // ---- complete units leave for their final place (possibly another GPU's frame) ---------------
+            __syncwarp();  // orders this warp's staged pixel stores and counter updates before the reads below
+            unsigned m_flush = __ballot_sync(0xffffffffu, lane < (unsigned)kPushSlots && ((open_mask >> lane) & 1u) && s_owed[wib][lane & (kPushSlots - 1)] == 0);
+            open_mask &= ~m_flush;
+            while (m_flush) {
+                const int4 d = s_unit[wib][__ffs(m_flush) - 1];
+                m_flush &= m_flush - 1u;
+                const int wshift = (P.unit_shift + 1) >> 1;  // a unit is a (1 << wshift) x (unit_pixels >> wshift) block of its tile
+                const int tile = P.tile_first + d.y * P.tile_stride;
+                const int bx = (tile % P.tiles_x) * kTile + d.z, by = (tile / P.tiles_x) * kTile + d.w;
+                const long long lbase = (long long)d.x * P.frame_stride + ((long long)d.y * kTile + d.w) * kTile + d.z;
+                const long long rbase = (long long)d.x * P.W * P.H;
+                for (int i = (int)lane; i < (unit_pixels >> 2); i += 32) {
+                    const int row = i >> (wshift - 2), col = (i - (row << (wshift - 2))) << 2;
+                    const int px = bx + col, py = by + row;
+                    if (py >= P.H || px >= P.W) continue;
+                    const long long lo = lbase + row * kTile + col, ro = rbase + (long long)py * P.W + px;
+                    if (((P.W & 3) == 0)) {  // whole 16-byte segments (px is a multiple of 4, so px + 3 < W as well)
+                        if (P.push_bgra) *reinterpret_cast<uint4*>(P.push_bgra + ro) = __ldcg(reinterpret_cast<const uint4*>(P.out_bgra + lo));
+                        if (P.push_ids) *reinterpret_cast<int4*>(P.push_ids + ro) = __ldcg(reinterpret_cast<const int4*>(P.out_ids + lo));
+                    } else {
+                        for (int k = 0; k < 4 && px + k < P.W; k++) {
+                            if (P.push_bgra) P.push_bgra[ro + k] = __ldcg(P.out_bgra + lo + k);
+                            if (P.push_ids) P.push_ids[ro + k] = __ldcg(P.out_ids + lo + k);
+                        }
+                    }
+                }
+            }
+            blocked = blocked && open_mask == (1u << kPushSlots) - 1u;
+        }
+        if (exhausted && m_trav == 0u) break;  // nothing in flight, nothing left to fetch
     }
 
     if (COUNT) {

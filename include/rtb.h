@@ -21,6 +21,7 @@
  */
 #ifndef RTB_H
 #define RTB_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -189,6 +190,30 @@ int rtb_render_frames_device_async(rtb_object* obj, rtb_camera* cam, int32_t num
  * pointers to 32-bit elements: colours or ids alike) into the final row-major frames d_out. */
 int64_t rtb_tile_major_elements(const rtb_camera* cam, int32_t tile_stride);
 int rtb_compose_tiles_device_async(rtb_camera* cam, int32_t num_frames, int32_t world, const void* const* d_parts, void* d_out, void* stream);
+
+/* Multi-GPU tile exchange fused into the render kernel (no collective, no reassembly pass).  Like
+ * rtb_render_frames_device_async restricted to tiles t % tile_stride == tile_first, but d_frame_bgra / d_frame_ids are
+ * the FINAL frames (num_frames*W*H elements, row-major; either may be NULL) and may live on ANOTHER GPU: every warp of the
+ * persistent kernel copies each of its work units, the moment its last pixel is shaded, to its place in those frames
+ * with 16-byte stores -- over NVLink when the pointer is peer-mapped (rtb_peer_open) -- so the transfer overlaps the
+ * rendering unit by unit.  The frames are complete once the kernels of all ranks have finished (order a barrier or any
+ * collective after them on `stream`).  This replaces the reference's single-GPU frame buffer (Camera.cpp:78) for the
+ * multi-GPU case; RTB_RENDER_COUNTERS is not available here. */
+int rtb_render_frames_push_async(rtb_object* obj, rtb_camera* cam, int32_t num_frames, const float* m12,
+                                 int32_t tile_first, int32_t tile_stride, uint32_t flags, uint32_t* d_frame_bgra,
+                                 int32_t* d_frame_ids, void* stream);
+/* Frames that other processes' GPUs can write: rtb_peer_alloc = one device allocation on the current device (plays the
+ * role of the cudaMalloc of Camera.cpp:78), rtb_peer_export = its 64-byte inter-process handle (send it to the other
+ * ranks by any means, e.g. torch.distributed.all_gather_object), rtb_peer_open = map a peer's allocation into this
+ * process on the current device (NVLink peer access is enabled on first use), rtb_peer_close / rtb_peer_free undo them. */
+int rtb_peer_alloc(size_t bytes, void** d_ptr);
+int rtb_peer_free(void* d_ptr);
+int rtb_peer_export(void* d_ptr, uint8_t handle64[64]);
+int rtb_peer_open(const uint8_t handle64[64], void** d_ptr);
+int rtb_peer_close(void* d_ptr);
+/* synchronous copy of a (peer) device buffer to host memory after a device-wide synchronisation: the read-out of the
+ * assembled frames (the role of the cudaMemcpy of Camera.cu:84) */
+int rtb_peer_read(void* host_dst, const void* d_ptr, size_t bytes);
 
 /* host-side transform recurrence only (no GPU): advance `obj` by one op and return its matrix;
  * lets callers precompute the m12 array for rtb_render_frames_device_async. */
