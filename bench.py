@@ -256,7 +256,8 @@ def run_ours(args):
         mats[g] = obj.transform_host(rtb.R_KEY_QUAT, rtb.ROTATE_TRI_PY)
 
     tiles_mode = world > 1 and args.shard == "tiles"
-    if tiles_mode:  # the NCCL gather runs beside the persistent render kernel: leave it a few SMs
+    push_mode = tiles_mode and args.exchange == "push"
+    if tiles_mode and not push_mode:  # the NCCL gather runs beside the persistent render kernel: leave it a few SMs
         os.environ.setdefault("RTB_RESERVE_SMS", "8")
     FS = F * world if tiles_mode else F  # frames a rank touches per step
 
@@ -271,10 +272,22 @@ def run_ours(args):
     # per-frame elements of this rank's output: the whole frame, or (tiles mode) only its own tiles in
     # the compact tile-major exchange format
     PE = cam.tile_major_elements(world) if tiles_mode else P
-    d_col = [torch.empty(FS * PE, dtype=torch.int32, device="cuda") for _ in range(2)]
-    d_ids = [torch.empty(FS * PE, dtype=torch.int32, device="cuda") for _ in range(2)]
+    if not (tiles_mode and args.exchange == "push"):
+        d_col = [torch.empty(FS * PE, dtype=torch.int32, device="cuda") for _ in range(2)]
+        d_ids = [torch.empty(FS * PE, dtype=torch.int32, device="cuda") for _ in range(2)]
     gather_col = gather_ids = final_col = final_ids = None
-    if tiles_mode and rank == 0:
+    push_ptr = None
+    if push_mode:
+        # rank 0 owns the final frames (two slots); every rank maps them and its render kernel stores finished work
+        # units straight into them over NVLink -- no gather, no receive buffers, no reassembly pass
+        d_col = d_ids = None
+        bufs = [rtb.PeerBuffer(4 * FS * P) for _ in range(4)] if rank == 0 else None
+        handles = [b.handle() for b in bufs] if rank == 0 else [None] * 4
+        dist.broadcast_object_list(handles, src=0)
+        ptrs = [b.ptr for b in bufs] if rank == 0 else [rtb.peer_open(h) for h in handles]
+        push_ptr = [(ptrs[0], ptrs[1]), (ptrs[2], ptrs[3])]  # per slot: (colours, ids)
+        push_flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    elif tiles_mode and rank == 0:
         gather_col = [[torch.empty(FS * PE, dtype=torch.int32, device="cuda") for _ in range(world)] for _ in range(2)]
         gather_ids = [[torch.empty(FS * PE, dtype=torch.int32, device="cuda") for _ in range(world)] for _ in range(2)]
         final_col = torch.empty(FS * P, dtype=torch.int32, device="cuda")
@@ -313,11 +326,17 @@ def run_ours(args):
                 stream.wait_event(gather_done[slot])
                 compose(slot)
             ev[step][0].record(stream)
-            obj.render_frames_device_async(cam, my_mats(step), d_col[slot].data_ptr(), d_ids[slot].data_ptr(), stream.cuda_stream,
-                                           tile_first=rank if tiles_mode else 0, tile_stride=world if tiles_mode else 1,
-                                           flags=rtb.RENDER_TILE_MAJOR if tiles_mode else 0)
-            ev[step][1].record(stream)
-        if tiles_mode:
+            if push_mode:
+                obj.render_frames_push_async(cam, my_mats(step), push_ptr[slot][0], push_ptr[slot][1], stream.cuda_stream,
+                                             tile_first=rank, tile_stride=world)
+                ev[step][1].record(stream)
+                dist.all_reduce(push_flag)  # completes when every rank's kernel has: the step's frames are whole on rank 0
+            else:
+                obj.render_frames_device_async(cam, my_mats(step), d_col[slot].data_ptr(), d_ids[slot].data_ptr(), stream.cuda_stream,
+                                               tile_first=rank if tiles_mode else 0, tile_stride=world if tiles_mode else 1,
+                                               flags=rtb.RENDER_TILE_MAJOR if tiles_mode else 0)
+                ev[step][1].record(stream)
+        if tiles_mode and not push_mode:
             side.wait_event(ev[step][1])
             with torch.cuda.stream(side):
                 dist.gather(d_col[slot], gather_col[slot] if rank == 0 else None, dst=0)
@@ -347,6 +366,18 @@ def run_ours(args):
     # ---------------- work counters (separate, untimed pass over the timed steps' first block) -------
     cam.counters(reset=True)
     targs = dict(tile_first=rank if tiles_mode else 0, tile_stride=world if tiles_mode else 1)
+    if push_mode:
+        # the last pushed step on rank 0 must equal this rank's own full render of the same frames (sanity, untimed)
+        push_ok = True
+        if rank == 0:
+            chk_c = torch.empty(FS * P, dtype=torch.int32, device="cuda"); chk_i = torch.empty(FS * P, dtype=torch.int32, device="cuda")
+            obj.render_frames_device_async(cam, my_mats(total_steps - 1), chk_c.data_ptr(), chk_i.data_ptr(), stream.cuda_stream)
+            torch.cuda.synchronize()
+            got = np.empty(FS * P, np.int32)
+            slot = (total_steps - 1) & 1
+            rtb.memcpy_d2h(got, push_ptr[slot][1]); push_ok &= bool(np.array_equal(got, chk_i.cpu().numpy()))
+            rtb.memcpy_d2h(got, push_ptr[slot][0]); push_ok &= bool(np.array_equal(got, chk_c.cpu().numpy()))
+            del chk_c, chk_i
     if tiles_mode:  # the untimed passes below write whole row-major frames of this rank's tiles
         d_col = [torch.empty(FS * P, dtype=torch.int32, device="cuda")]
         d_ids = [torch.empty(FS * P, dtype=torch.int32, device="cuda")]
@@ -443,7 +474,9 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "mesh": mesh_label, "triangles": int(len(pts)), "resolution": [W, H], "frames_per_step": F,
                    "frames_total": K * world * F, "camera": "WinMain.cpp:69-74 default, R-key quaternion step per frame", "coverage": coverage,
-                   "parallelism": ("tiles x%d (scene replicated, 32x32 tiles round-robin, NCCL gather to rank 0 + reassembly on a side stream)" % world
+                   "parallelism": (("tiles x%d (scene replicated, 32x32 tiles round-robin, finished work units pushed by the render kernel into rank 0's "
+                                    "frames over NVLink peer memory; pushed frames == single-GPU frames: %s)" % (world, push_ok)) if push_mode else
+                                   "tiles x%d (scene replicated, 32x32 tiles round-robin, NCCL gather to rank 0 + reassembly on a side stream)" % world
                                    if tiles_mode else "frames x%d (scene replicated, blocks of %d frames per rank, no collective)" % (world, F)) if world > 1 else "single GPU",
                    "l2": "explicit flush (160 MB write) before every step; per-step working set = scene %.0f MB + %.0f MB output" % (
                        (64.0 * (len(pts) - 1) + 48.0 * len(pts)) / 1e6, F * P * 8 / 1e6),
@@ -467,6 +500,8 @@ def main():
     ap.add_argument("--workload", default="dragon_orbit_960x540", choices=sorted(WORKLOADS))
     ap.add_argument("--frames-per-step", type=int, default=0)
     ap.add_argument("--shard", default="frames", choices=["frames", "tiles"], help="multi-GPU partition (N > 1)")
+    ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
+                    help="tiles mode: fused peer-memory push from the render kernel (default) or NCCL gather + reassembly")
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip timing the reference's own CUDA kernels on this GPU")

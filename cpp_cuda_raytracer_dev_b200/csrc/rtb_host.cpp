@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cctype>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -57,16 +58,244 @@ inline bool emit_face(std::vector<float>& out, const std::vector<float>& verts, 
 
 }  // namespace
 
+// ---- conforming PLY reader (mode -1) ---------------------------------------------------------------
+// The reference loader (read_ply.cpp:13-153) is a text scanner for four fixed column layouts.  Mode -1 is the
+// header-driven reader SURVEY.md section 8(f) item 2 asks for: `format ascii | binary_little_endian |
+// binary_big_endian`, any element order, any scalar property types, list properties, extra elements and
+// properties skipped by their declared sizes.  Vertices are taken from the properties named x, y, z; faces from the
+// list property `vertex_indices` / `vertex_index` (else the first list property of `face`).  The triangle order
+// rules stay the reference's (read_ply.cpp:92-148): a 3-gon (a,b,c) is stored (c,a,b), a 4-gon becomes
+// (a,b,c),(a,c,d); larger polygons continue that fan: (a,v[k],v[k+1]).
+namespace {
+
+enum PlyType { kI8, kU8, kI16, kU16, kI32, kU32, kF32, kF64, kBadType };
+const int kPlySize[] = {1, 1, 2, 2, 4, 4, 4, 8, 0};
+
+PlyType ply_type(const std::string& t) {
+    if (t == "char" || t == "int8") return kI8;
+    if (t == "uchar" || t == "uint8") return kU8;
+    if (t == "short" || t == "int16") return kI16;
+    if (t == "ushort" || t == "uint16") return kU16;
+    if (t == "int" || t == "int32") return kI32;
+    if (t == "uint" || t == "uint32") return kU32;
+    if (t == "float" || t == "float32") return kF32;
+    if (t == "double" || t == "float64") return kF64;
+    return kBadType;
+}
+
+struct PlyProperty {
+    std::string name;
+    bool is_list = false;
+    PlyType type = kBadType, count_type = kBadType;
+};
+struct PlyElement {
+    std::string name;
+    long count = 0;
+    std::vector<PlyProperty> props;
+};
+
+std::vector<std::string> split_ws(const std::string& line) {
+    std::vector<std::string> out;
+    size_t i = 0;
+    while (i < line.size()) {
+        while (i < line.size() && std::isspace((unsigned char)line[i])) i++;
+        size_t j = i;
+        while (j < line.size() && !std::isspace((unsigned char)line[j])) j++;
+        if (j > i) out.emplace_back(line, i, j - i);
+        i = j;
+    }
+    return out;
+}
+
+// one scalar from the data section, as a double (exact for every PLY type except that float64 -> float
+// narrowing happens at the caller, once)
+struct PlyCursor {
+    const char* p;
+    const char* end;
+    int format;  // 0 ascii, 1 little endian, 2 big endian
+    bool ok = true;
+    double next(PlyType t) {
+        if (format == 0) {
+            char* q = nullptr;
+            double v;
+            if (t == kF32) v = (double)std::strtof(p, &q);  // one correctly rounded conversion, like `istream >> float`
+            else if (t == kF64) v = std::strtod(p, &q);
+            else v = (double)std::strtoll(p, &q, 10);
+            if (q == p || q > end) { ok = false; return 0.0; }
+            p = q;
+            return v;
+        }
+        const int n = kPlySize[t];
+        if (end - p < n) { ok = false; return 0.0; }
+        unsigned char b[8];
+        for (int k = 0; k < n; k++) b[k] = (unsigned char)(format == 1 ? p[k] : p[n - 1 - k]);  // -> little endian
+        p += n;
+        switch (t) {
+            case kI8: return (double)(int8_t)b[0];
+            case kU8: return (double)b[0];
+            case kI16: { int16_t v; std::memcpy(&v, b, 2); return (double)v; }
+            case kU16: { uint16_t v; std::memcpy(&v, b, 2); return (double)v; }
+            case kI32: { int32_t v; std::memcpy(&v, b, 4); return (double)v; }
+            case kU32: { uint32_t v; std::memcpy(&v, b, 4); return (double)v; }
+            case kF32: { float v; std::memcpy(&v, b, 4); return (double)v; }
+            case kF64: { double v; std::memcpy(&v, b, 8); return v; }
+            default: ok = false; return 0.0;
+        }
+    }
+};
+
+std::string load_ply_conforming(const FileBytes& fb, std::vector<float>& points9) {
+    const char* p = fb.data.data();
+    const char* end = p + fb.data.size() - 1;
+    std::vector<PlyElement> elements;
+    int format = -1;
+    bool header_done = false, first = true;
+    while (p < end) {
+        const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
+        std::string line(p, nl ? nl : end);
+        p = nl ? nl + 1 : end;
+        const std::vector<std::string> w = split_ws(line);
+        if (first) {
+            if (w.empty() || w[0] != "ply") return "read_ply: not a PLY file";
+            first = false;
+            continue;
+        }
+        if (w.empty() || w[0] == "comment" || w[0] == "obj_info") continue;
+        if (w[0] == "end_header") { header_done = true; break; }
+        if (w[0] == "format" && w.size() >= 2) {
+            format = w[1] == "ascii" ? 0 : w[1] == "binary_little_endian" ? 1 : w[1] == "binary_big_endian" ? 2 : -1;
+            if (format < 0) return "read_ply: unknown format " + w[1];
+        } else if (w[0] == "element" && w.size() >= 3) {
+            PlyElement e;
+            e.name = w[1];
+            e.count = std::atol(w[2].c_str());
+            if (e.count < 0) return "read_ply: negative element count";
+            elements.push_back(e);
+        } else if (w[0] == "property") {
+            if (elements.empty()) return "read_ply: property before any element";
+            PlyProperty pr;
+            if (w.size() >= 5 && w[1] == "list") {
+                pr.is_list = true; pr.count_type = ply_type(w[2]); pr.type = ply_type(w[3]); pr.name = w[4];
+                if (pr.count_type == kBadType || pr.count_type == kF32 || pr.count_type == kF64) return "read_ply: bad list count type";
+            } else if (w.size() >= 3) {
+                pr.type = ply_type(w[1]); pr.name = w[2];
+            } else {
+                return "read_ply: malformed property line";
+            }
+            if (pr.type == kBadType) return "read_ply: unknown property type in `" + line + "`";
+            elements.back().props.push_back(pr);
+        } else {
+            return "read_ply: unknown header line `" + line + "`";
+        }
+    }
+    if (!header_done) return "read_ply: no end_header";
+    if (format < 0) return "read_ply: header has no format line";
+
+    PlyCursor cur{p, end, format};
+    std::vector<float> verts;
+    std::vector<long> face_idx;      // all polygons' indices back to back
+    std::vector<int> face_count;     // vertices per polygon
+    bool have_vertex = false, have_face = false;
+    for (const PlyElement& e : elements) {
+        if (e.name == "vertex") {
+            int ix = -1, iy = -1, iz = -1;
+            for (size_t k = 0; k < e.props.size(); k++) {
+                if (e.props[k].is_list) continue;
+                if (e.props[k].name == "x") ix = (int)k;
+                if (e.props[k].name == "y") iy = (int)k;
+                if (e.props[k].name == "z") iz = (int)k;
+            }
+            if (ix < 0 || iy < 0 || iz < 0) return "read_ply: vertex element needs scalar properties x, y, z";
+            verts.resize((size_t)e.count * 3);
+            have_vertex = true;
+            for (long i = 0; i < e.count; i++) {
+                for (size_t k = 0; k < e.props.size(); k++) {
+                    const PlyProperty& pr = e.props[k];
+                    if (pr.is_list) {
+                        const long n = (long)cur.next(pr.count_type);
+                        for (long j = 0; j < n && cur.ok; j++) cur.next(pr.type);
+                    } else {
+                        const double v = cur.next(pr.type);
+                        if ((int)k == ix) verts[3 * (size_t)i] = (float)v;
+                        else if ((int)k == iy) verts[3 * (size_t)i + 1] = (float)v;
+                        else if ((int)k == iz) verts[3 * (size_t)i + 2] = (float)v;
+                    }
+                }
+                if (!cur.ok) return "read_ply: truncated or malformed vertex data";
+            }
+        } else if (e.name == "face") {
+            int il = -1;
+            for (size_t k = 0; k < e.props.size(); k++)
+                if (e.props[k].is_list && (e.props[k].name == "vertex_indices" || e.props[k].name == "vertex_index")) il = (int)k;
+            for (size_t k = 0; k < e.props.size() && il < 0; k++)
+                if (e.props[k].is_list) il = (int)k;
+            if (il < 0) return "read_ply: face element has no list property";
+            have_face = true;
+            face_count.reserve((size_t)e.count);
+            face_idx.reserve((size_t)e.count * 3);
+            for (long i = 0; i < e.count; i++) {
+                for (size_t k = 0; k < e.props.size(); k++) {
+                    const PlyProperty& pr = e.props[k];
+                    if (pr.is_list) {
+                        const long n = (long)cur.next(pr.count_type);
+                        if (!cur.ok || n < 0 || n > (1 << 20)) return "read_ply: truncated or malformed face data";
+                        if ((int)k == il) face_count.push_back((int)n);
+                        for (long j = 0; j < n && cur.ok; j++) {
+                            const double v = cur.next(pr.type);
+                            if ((int)k == il) face_idx.push_back((long)v);
+                        }
+                    } else {
+                        cur.next(pr.type);
+                    }
+                }
+                if (!cur.ok) return "read_ply: truncated or malformed face data";
+            }
+        } else {  // an element the path does not use: step over it by its declared layout
+            for (long i = 0; i < e.count; i++) {
+                for (const PlyProperty& pr : e.props) {
+                    if (pr.is_list) {
+                        const long n = (long)cur.next(pr.count_type);
+                        for (long j = 0; j < n && cur.ok; j++) cur.next(pr.type);
+                    } else {
+                        cur.next(pr.type);
+                    }
+                }
+                if (!cur.ok) return "read_ply: truncated or malformed data in element " + e.name;
+            }
+        }
+    }
+    if (!have_vertex || !have_face) return "read_ply: header has no vertex/face counts";
+    if (verts.empty() || face_count.empty()) return "read_ply: header has no vertex/face counts";
+    const long nv = (long)(verts.size() / 3);
+    const float* base = verts.data();
+    size_t at = 0;
+    for (int n : face_count) {
+        const long* idx = face_idx.data() + at;
+        at += (size_t)n;
+        if (n < 3) return "read_ply: a face needs at least three vertices";
+        for (int k = 0; k < n; k++)
+            if (idx[k] < 0 || idx[k] >= nv) return "read_ply: vertex index out of range";
+        if (n == 3) {
+            emit_triangle(points9, base + 3 * idx[2], base + 3 * idx[0], base + 3 * idx[1]);  // stored (c,a,b), read_ply.cpp:138-148
+        } else {
+            for (int k = 1; k + 1 < n; k++) emit_triangle(points9, base + 3 * idx[0], base + 3 * idx[k], base + 3 * idx[k + 1]);
+        }
+    }
+    return "";
+}
+
+}  // namespace
+
 std::string load_ply(const char* path, int mode, std::vector<float>& points9) {
     points9.clear();
     if (mode < -1 || mode > 2) return "read_ply: unsupported mode (0, 1, 2 or -1)";
     FileBytes fb;
     if (!fb.read(path)) return std::string("read_ply: cannot read ") + path;
+    if (mode == -1) return load_ply_conforming(fb, points9);
     const char* p = fb.data.data();
     const char* end = p + fb.data.size() - 1;
     long num_vert = 0, num_face = 0;
-    int vertex_props = 0;
-    bool binary = false, in_vertex_element = false, header_done = false;
+    bool binary = false, header_done = false;
     // header: only `element vertex|face <n>` matter to the reference (read_ply.cpp:19-44)
     while (p < end) {
         const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
@@ -75,36 +304,16 @@ std::string load_ply(const char* path, int mode, std::vector<float>& points9) {
         while (!line.empty() && (line.back() == '\r' || line.back() == ' ')) line.pop_back();
         p = nl ? nl + 1 : end;
         if (line == "end_header") { header_done = true; break; }
-        if (line.rfind("format binary_little_endian", 0) == 0) binary = true;
-        if (line.rfind("element vertex ", 0) == 0) { num_vert = std::atol(line.c_str() + 15); in_vertex_element = true; }
-        else if (line.rfind("element face ", 0) == 0) { num_face = std::atol(line.c_str() + 13); in_vertex_element = false; }
-        else if (line.rfind("element ", 0) == 0) in_vertex_element = false;
-        else if (in_vertex_element && line.rfind("property ", 0) == 0) vertex_props++;
+        if (line.rfind("format binary", 0) == 0) binary = true;
+        if (line.rfind("element vertex ", 0) == 0) num_vert = std::atol(line.c_str() + 15);
+        else if (line.rfind("element face ", 0) == 0) num_face = std::atol(line.c_str() + 13);
     }
     if (!header_done) return "read_ply: no end_header";
     if (num_vert <= 0 || num_face <= 0) return "read_ply: header has no vertex/face counts";
-    if (binary && mode != -1) return "read_ply: binary PLY needs mode -1 (the reference reader only parses text)";
+    if (binary) return "read_ply: binary PLY needs mode -1 (the reference reader only parses text)";
     std::vector<float> verts((size_t)num_vert * 3);
     points9.reserve((size_t)num_face * 9);
-    if (binary) {
-        if (vertex_props < 3) return "read_ply: binary vertex element needs x,y,z";
-        const size_t stride = 4 * (size_t)vertex_props;
-        if ((size_t)(end - p) < stride * (size_t)num_vert) return "read_ply: truncated vertex data";
-        for (long i = 0; i < num_vert; i++, p += stride) std::memcpy(&verts[3 * (size_t)i], p, 12);
-        for (long f = 0; f < num_face; f++) {
-            if (p >= end) return "read_ply: truncated face data";
-            int count = (unsigned char)*p++;
-            if (count != 3 && count != 4) return "read_ply: only triangles and quads are supported";
-            if ((size_t)(end - p) < 4 * (size_t)count) return "read_ply: truncated face data";
-            uint32_t raw[4];
-            std::memcpy(raw, p, 4 * (size_t)count);
-            p += 4 * count;
-            long idx[4] = {(long)raw[0], (long)raw[1], (long)raw[2], count == 4 ? (long)raw[3] : 0};
-            if (!emit_face(points9, verts, count, idx)) return "read_ply: vertex index out of range";
-        }
-        return "";
-    }
-    const int columns = mode == 1 ? 5 : mode == 2 ? 6 : mode == -1 ? std::max(3, vertex_props) : 3;
+    const int columns = mode == 1 ? 5 : mode == 2 ? 6 : 3;
     char* cur = const_cast<char*>(p);
     char* next = nullptr;
     for (long i = 0; i < num_vert; i++) {

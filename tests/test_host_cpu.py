@@ -60,6 +60,89 @@ def test_ply_loader_matches_oracle(rtb, orc, tmp_path):
     assert np.array_equal(orc.read_ply(str(out), 0).view(np.uint32), pts.view(np.uint32))
 
 
+def _write_ply(path, fmt, verts, faces, vertex_layout, count_type, index_type, extra_elements=True):
+    """A PLY file in any of the three formats with a chosen vertex property layout, for the conforming reader."""
+    np_of = {"char": "i1", "uchar": "u1", "short": "i2", "ushort": "u2", "int": "i4", "uint": "u4", "float": "f4", "double": "f8"}
+    end = {"ascii": "=", "binary_little_endian": "<", "binary_big_endian": ">"}[fmt]
+    hdr = ["ply", "format %s 1.0" % fmt, "comment made by tests/test_host_cpu.py"]
+    if extra_elements:
+        hdr += ["element material 2", "property uchar red", "property list uchar float coeffs"]
+    hdr += ["element vertex %d" % len(verts)] + ["property %s %s" % (t, n) for t, n in vertex_layout]
+    hdr += ["element face %d" % len(faces), "property uchar flags", "property list %s %s vertex_indices" % (count_type, index_type)]
+    if extra_elements:
+        hdr += ["element edge 1", "property int vertex1", "property int vertex2"]
+    hdr += ["end_header"]
+    rng = np.random.default_rng(3)
+    with open(path, "wb") as fh:
+        fh.write(("\n".join(hdr) + "\n").encode())
+        def put(values_types):
+            if fmt == "ascii":
+                fh.write((" ".join(repr(float(v)) if t in ("float", "double") else str(int(v)) for v, t in values_types) + "\n").encode())
+            else:
+                for v, t in values_types:
+                    fh.write(np.array(v, dtype=end + np_of[t]).tobytes())
+        if extra_elements:
+            put([(7, "uchar"), (2, "uchar"), (0.5, "float"), (0.25, "float")])
+            put([(9, "uchar"), (0, "uchar")])
+        for v in verts:
+            rec = []
+            for t, n in vertex_layout:
+                rec.append((v["xyz".index(n)] if n in "xyz" else rng.integers(0, 100), t))
+            put(rec)
+        for f in faces:
+            put([(1, "uchar"), (len(f), count_type)] + [(i, index_type) for i in f])
+        if extra_elements:
+            put([(0, "int"), (1, "int")])
+
+
+@pytest.mark.parametrize("fmt", ["ascii", "binary_little_endian", "binary_big_endian"])
+@pytest.mark.parametrize("layout", ["xyz", "normals_first", "double_xyz"])
+def test_conforming_ply_reader(rtb, tmp_path, fmt, layout):
+    """Mode -1: header-driven reader -- three formats, any property order and types, list
+    properties, extra elements; triangle order rules of read_ply.cpp:92-148 kept (3-gon -> (c,a,b), 4-gon -> fan)."""
+    verts = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0.5, 0.5, 1.25], [0.25, -1.5, 3.0]], np.float32)
+    faces = [[0, 1, 2, 3], [0, 1, 4], [2, 3, 4], [0, 1, 2, 3, 5]]
+    vl = {"xyz": [("float", "x"), ("float", "y"), ("float", "z")],
+          "normals_first": [("float", "nx"), ("uchar", "red"), ("float", "z"), ("float", "x"), ("short", "s"), ("float", "y"), ("double", "q")],
+          "double_xyz": [("double", "x"), ("double", "y"), ("double", "z"), ("float", "confidence")]}[layout]
+    ct, it = ("uchar", "int") if layout == "xyz" else ("ushort", "uint") if layout == "normals_first" else ("int", "ushort")
+    f = tmp_path / "c.ply"
+    _write_ply(str(f), fmt, verts, faces, vl, ct, it)
+    got = rtb.read_ply(str(f), -1)
+    V = verts
+    want = np.array([np.concatenate([V[0], V[1], V[2]]), np.concatenate([V[0], V[2], V[3]]),     # quad -> (A,B,C),(A,C,D)
+                     np.concatenate([V[4], V[0], V[1]]), np.concatenate([V[4], V[2], V[3]]),     # (a,b,c) stored (c,a,b)
+                     np.concatenate([V[0], V[1], V[2]]), np.concatenate([V[0], V[2], V[3]]), np.concatenate([V[0], V[3], V[5]])], np.float32)
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_conforming_reader_equals_reference_reader_on_text_files(rtb, tmp_path):
+    """Where both apply (ASCII, x y z first), mode -1 must give what the reference's scanner gives (modes 0/1)."""
+    path = mesh_path("rabbit_70k.ply")
+    if path is not None:
+        # the reference's own text files declare no properties at all (header: counts only), which is why its
+        # scanner needs a column mode; a header-driven reader has to refuse them rather than guess
+        with pytest.raises(rtb.RtbError):
+            rtb.read_ply(path, -1)
+    pts = rtb.geodesic_mesh(5)
+    out = tmp_path / "rt.ply"
+    rtb.write_ply(str(out), pts)
+    assert np.array_equal(rtb.read_ply(str(out), -1).view(np.uint32), pts.view(np.uint32))
+
+
+def test_conforming_reader_rejects_bad_files(rtb, tmp_path):
+    f = tmp_path / "bad.ply"
+    for body in ("plx\n", "ply\nformat ascii 1.0\nelement vertex 1\nproperty float x\nend_header\n0\n",
+                 "ply\nformat binary_little_endian 1.0\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\n"
+                 "element face 1\nproperty list uchar int vertex_indices\nend_header\n\x00\x00",
+                 "ply\nformat ascii 1.0\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\n"
+                 "element face 1\nproperty list uchar int vertex_indices\nend_header\n0 0 0\n1 0 0\n0 1 0\n3 0 1 7\n"):
+        f.write_bytes(body.encode("latin1"))
+        with pytest.raises(rtb.RtbError):
+            rtb.read_ply(str(f), -1)
+
+
 def tree_equal(t, on):
     leaf = on["is_leaf"] == 1
     ok = np.array_equal(t["left"], np.where(leaf, -1, on["left"]).astype(np.int32))

@@ -1,0 +1,40 @@
+"""Sweep the render kernel's scheduling knobs (RTB_T_ACTIVE, RTB_T_LEAF, RTB_UNIT_SHIFT) in one process (development aid).
+The library reads them at every launch, so the scene is built once."""
+import os, sys, itertools
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import cpp_cuda_raytracer_dev_b200 as rtb
+rtb.set_device(0)
+nu, W, H, F = 209, 960, 540, 60
+pts = rtb.geodesic_mesh(nu); mesh = rtb.Trixel(pts); mesh.create_kd()
+cam = rtb.Camera(W, H, **rtb.default_camera_args(W, H)); obj = rtb.Object(mesh); cam.add_object(obj)
+st = torch.cuda.Stream()
+col = torch.empty(F * W * H, dtype=torch.int32, device="cuda"); ids = torch.empty(F * W * H, dtype=torch.int32, device="cuda")
+flush = torch.empty(160 << 20, dtype=torch.uint8, device="cuda")
+def measure(mats, reps=4):
+    ts = []
+    for r in range(reps + 1):
+        with torch.cuda.stream(st):
+            flush.fill_(r)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            obj.render_frames_device_async(cam, mats, col.data_ptr(), ids.data_ptr(), st.cuda_stream)
+            e1.record(st)
+        torch.cuda.synchronize()
+        if r: ts.append(e0.elapsed_time(e1))
+    return float(np.mean(ts)), float(np.min(ts))
+n = cam.basis()[0:3]
+views = {}
+views["default"] = np.stack([obj.matrix()] + [obj.transform_host(rtb.R_KEY_QUAT, rtb.ROTATE_TRI_PY) for _ in range(F - 1)])
+for _ in range(140):
+    obj.transform((float(n[0]), float(n[1]), float(n[2]), 0.005), rtb.TRANSLATE_Z)
+views["closeup"] = np.stack([obj.matrix()] + [obj.transform_host(rtb.R_KEY_QUAT, rtb.ROTATE_TRI_PY) for _ in range(F - 1)])
+grid = {"RTB_T_ACTIVE": (sys.argv[1] if len(sys.argv) > 1 else "12,16,20,24,28").split(","),
+        "RTB_T_LEAF": (sys.argv[2] if len(sys.argv) > 2 else "4,8,12,16").split(","),
+        "RTB_UNIT_SHIFT": (sys.argv[3] if len(sys.argv) > 3 else "7").split(",")}
+keys = list(grid)
+print("%-36s %18s %18s" % ("setting", "default mean/min ms", "closeup mean/min ms"))
+for combo in itertools.product(*[grid[k] for k in keys]):
+    for k, v in zip(keys, combo): os.environ[k] = v
+    a = measure(views["default"]); b = measure(views["closeup"])
+    print("%-36s %8.3f /%8.3f %8.3f /%8.3f" % (" ".join("%s=%s" % (k[4:], v) for k, v in zip(keys, combo)), a[0], a[1], b[0], b[1]), flush=True)
