@@ -413,6 +413,23 @@ def run_ours(args):
     torch.cuda.synchronize()
     same = bool(torch.equal(d_ids[0][:P].cpu(), h_ids[F - 1])) and bool(torch.equal(d_col[0][:P].cpu(), h_col[F - 1]))
 
+    # ---------------- the reference's own frame loop through the drop-in calls (one frame at a time) ----
+    # WinMain.cpp:187-237: Input::set_quat + Object::transform, Object::render, Camera::color_pixels(PHONG), frame in
+    # the camera's host buffer after every iteration (one device synchronisation and one colour+id D2H per frame).
+    frame_loop = None
+    if rank == 0 and world == 1:
+        nloop = 200 if P <= (1 << 20) else 20
+        for it in range(nloop + 10):
+            if it == 10:
+                t_loop = time.perf_counter()
+            obj.transform(rtb.R_KEY_QUAT, rtb.ROTATE_TRI_PY)
+            obj.render(cam)
+            cam.color_pixels(rtb.PHONG_COLOR_TAG)
+        t_loop = time.perf_counter() - t_loop
+        frame_loop = {"fps": nloop / t_loop, "value": nloop * P / t_loop / 1e6, "unit": "Mrays/s", "frames": nloop,
+                      "api": "per frame: rtb_object_transform + rtb_object_render + rtb_camera_color_pixels(PHONG) "
+                             "(the reference's WinMain loop, synchronous, frame + ids in host memory after every iteration)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -483,7 +500,7 @@ def run_ours(args):
                    "fps": fps, "fps_vs_readme_100fps": fps / README_FPS, "tree_build_s": build_s["total"]},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(F * 5 * 4), "d2h_bytes_per_step": int(F * P * 8),
                 "fps": K * world * F / e2e_time, "api": "rtb_render_sweep (host ops in, pinned host colour+id frames out)", "matches_device_run": same},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "frame_loop": frame_loop,
         "kernel_ms": {"mean": float(np.mean(kernel_ms)), "min": float(np.min(kernel_ms)), "max": float(np.max(kernel_ms))},
     }
     print(json.dumps(line))

@@ -31,7 +31,7 @@ TILE = 32
 EXPORTS = [
     "rtb_last_error", "rtb_version", "rtb_device_count", "rtb_set_device", "rtb_read_ply", "rtb_free", "rtb_write_ply",
     "rtb_mesh_geodesic", "rtb_mesh_create", "rtb_mesh_build_tree", "rtb_mesh_build_tree_on", "rtb_mesh_num_triangles", "rtb_mesh_num_nodes",
-    "rtb_mesh_get_tree", "rtb_mesh_build_seconds", "rtb_mesh_destroy", "rtb_camera_create", "rtb_camera_get_basis",
+    "rtb_mesh_get_tree", "rtb_mesh_save_tree", "rtb_mesh_load_tree", "rtb_write_frame", "rtb_mesh_build_seconds", "rtb_mesh_destroy", "rtb_camera_create", "rtb_camera_get_basis",
     "rtb_camera_add_object", "rtb_camera_color_pixels", "rtb_camera_host_color", "rtb_camera_host_ids",
     "rtb_camera_counters", "rtb_camera_destroy", "rtb_object_create", "rtb_object_transform", "rtb_object_get_matrix",
     "rtb_object_set_matrix", "rtb_object_destroy", "rtb_object_render", "rtb_render_frame", "rtb_render_sweep",
@@ -60,6 +60,9 @@ def _load():
     L.rtb_mesh_create.argtypes = [vp, i64, vp, vp, C.POINTER(vp)]
     L.rtb_mesh_build_tree.argtypes = [vp]
     L.rtb_mesh_build_tree_on.argtypes = [vp, ci]
+    L.rtb_mesh_save_tree.argtypes = [vp, C.c_char_p]
+    L.rtb_mesh_load_tree.argtypes = [vp, C.c_char_p]
+    L.rtb_write_frame.argtypes = [C.c_char_p, vp, C.c_int32, C.c_int32]
     L.rtb_mesh_num_triangles.argtypes = [vp]
     L.rtb_mesh_num_triangles.restype = i64
     L.rtb_mesh_num_nodes.argtypes = [vp]
@@ -194,6 +197,13 @@ class Trixel:
         """Trixel.h:135 (+ set_sorted_voxels): build the 2n-1 node tree.  where: 0 auto, 1 host, 2 GPU."""
         _check(lib.rtb_mesh_build_tree_on(self.h, where), "rtb_mesh_build_tree_on")
         return 0
+
+    def save_tree(self, path):
+        _check(lib.rtb_mesh_save_tree(self.h, os.fsencode(path)), "rtb_mesh_save_tree")
+
+    def load_tree(self, path):
+        """Instead of create_kd(): take the tree from a cache file written by save_tree() for this very mesh."""
+        _check(lib.rtb_mesh_load_tree(self.h, os.fsencode(path)), "rtb_mesh_load_tree")
 
     def build_seconds(self):
         out = np.zeros(3, np.float64)
@@ -353,6 +363,12 @@ class Object:
         if self.h:
             lib.rtb_object_destroy(self.h)
             self.h = None
+
+
+def write_frame(path, bgra, W, H):
+    """.ppm or .png by extension; bgra = W*H uint32 0x00RRGGBB, row 0 at the bottom (the reference's frame buffer)."""
+    a = np.ascontiguousarray(bgra, np.uint32)
+    _check(lib.rtb_write_frame(os.fsencode(path), a.ctypes.data, W, H), "rtb_write_frame")
 
 
 class PeerBuffer:

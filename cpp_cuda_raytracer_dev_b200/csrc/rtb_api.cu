@@ -46,9 +46,12 @@ struct rtb_mesh {
     std::vector<float> rad;     // 3 per triangle, or empty when uniform
     float uniform_rgb[3] = {0.1f, 0.55f, 0.2f};
     float* d_points = nullptr;  // Trixel::d_points_init_data
-    rtb::HostTree tree;
+    rtb::HostTree tree;     // host copy; for a device build it is filled on first use (ensure_host_tree)
+    rtb::DeviceTree dtree;  // device build: the tree stays in HBM and feeds the pack kernels directly
     bool built = false;
     bool built_on_device = false;
+    bool host_tree_valid = false;
+    double seconds_sort = 0, seconds_partition = 0;
 };
 
 struct rtb_camera {
@@ -98,6 +101,16 @@ struct rtb_object {
 };
 
 namespace {
+
+int ensure_host_tree(rtb_mesh* m) {
+    if (m->host_tree_valid) return RTB_OK;
+    if (!m->built_on_device) return fail(RTB_ERR_STATE, "tree not built");
+    RTB_CUDA(cudaSetDevice(m->device));
+    const std::string err = rtb::download_tree(m->dtree, m->tree);
+    if (!err.empty()) return fail(RTB_ERR_CUDA, err);
+    m->host_tree_valid = true;
+    return RTB_OK;
+}
 
 int ensure_frames(rtb_object* o, int frames) {
     if (frames <= o->frames_capacity) return RTB_OK;
@@ -208,7 +221,7 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, int num_f
     int shift = 7;  // measured on the dragon stand-in: 128-pixel units beat 32, 64, 256 and 1024
     while (shift > 5 && (pixels >> shift) < warps_total * 4) shift--;
     P.unit_shift = std::min(10, std::max(5, env_int("RTB_UNIT_SHIFT", shift)));
-    P.t_active = std::min(31, std::max(0, env_int("RTB_T_ACTIVE", 20)));
+    P.t_active = std::min(31, std::max(0, env_int("RTB_T_ACTIVE", 12)));
     P.t_leaf = std::max(1, env_int("RTB_T_LEAF", 8));
     P.total_items = (long long)num_frames * P.my_tiles * ((kTile * kTile) >> P.unit_shift);
     const long long fetches = P.total_items;
@@ -330,11 +343,17 @@ int rtb_mesh_build_tree_on(rtb_mesh* mesh, int where) {
     if (device) {
         if (!mesh->d_points) return fail(RTB_ERR_CUDA, "build_tree: the mesh has no device copy (no usable GPU)");
         RTB_CUDA(cudaSetDevice(mesh->device));
-        const std::string err = rtb::build_tree_gpu(mesh->d_points, mesh->n, mesh->tree);
+        rtb::free_device_tree(mesh->dtree);
+        const std::string err = rtb::build_tree_gpu(mesh->d_points, mesh->n, mesh->dtree);
         if (!err.empty()) return fail(RTB_ERR_CUDA, err);
         g_launches += 1;
+        mesh->host_tree_valid = false;
+        mesh->seconds_sort = mesh->dtree.seconds_sort; mesh->seconds_partition = mesh->dtree.seconds_partition;
     } else {
+        if (mesh->d_points) { cudaSetDevice(mesh->device); rtb::free_device_tree(mesh->dtree); }
         rtb::build_tree(mesh->points.data(), mesh->n, mesh->tree, 0);
+        mesh->host_tree_valid = true;
+        mesh->seconds_sort = mesh->tree.seconds_sort; mesh->seconds_partition = mesh->tree.seconds_partition;
     }
     mesh->built = true;
     mesh->built_on_device = device;
@@ -344,9 +363,12 @@ int rtb_mesh_build_tree(rtb_mesh* mesh) { return rtb_mesh_build_tree_on(mesh, 0)
 int64_t rtb_mesh_num_triangles(const rtb_mesh* mesh) { return mesh ? mesh->n : 0; }
 int64_t rtb_mesh_num_nodes(const rtb_mesh* mesh) { return mesh ? 2 * mesh->n - 1 : 0; }
 
-int rtb_mesh_get_tree(const rtb_mesh* mesh, int32_t* left, int32_t* right, int32_t* tri, int32_t* cut_flag, float* bounds6,
+int rtb_mesh_get_tree(const rtb_mesh* mesh_c, int32_t* left, int32_t* right, int32_t* tri, int32_t* cut_flag, float* bounds6,
                       float* s1, float* s2) {
+    rtb_mesh* mesh = const_cast<rtb_mesh*>(mesh_c);  // a device-built tree is downloaded on first use
     if (!mesh || !mesh->built) return fail(RTB_ERR_STATE, "get_tree: tree not built");
+    const int rc = ensure_host_tree(mesh);
+    if (rc) return rc;
     const rtb::HostTree& T = mesh->tree;
     for (int64_t i = 0; i < T.num_nodes; i++) {
         if (left) left[i] = T.left[i];
@@ -359,14 +381,38 @@ int rtb_mesh_get_tree(const rtb_mesh* mesh, int32_t* left, int32_t* right, int32
     if (bounds6) std::memcpy(bounds6, T.bounds.data(), sizeof(float) * 6 * (size_t)T.num_nodes);
     return RTB_OK;
 }
+int rtb_mesh_save_tree(const rtb_mesh* mesh_c, const char* file_name) {
+    rtb_mesh* mesh = const_cast<rtb_mesh*>(mesh_c);
+    if (!mesh || !file_name || !mesh->built) return fail(RTB_ERR_STATE, "save_tree: tree not built");
+    const int rc = ensure_host_tree(mesh);
+    if (rc) return rc;
+    const std::string err = rtb::save_tree(file_name, mesh->tree, mesh->points.data());
+    return err.empty() ? RTB_OK : fail(RTB_ERR_IO, err);
+}
+int rtb_mesh_load_tree(rtb_mesh* mesh, const char* file_name) {
+    if (!mesh || !file_name) return fail(RTB_ERR_ARG, "load_tree: null argument");
+    rtb::HostTree T;
+    const std::string err = rtb::load_tree(file_name, mesh->points.data(), mesh->n, T);
+    if (!err.empty()) return fail(RTB_ERR_IO, err);
+    if (mesh->d_points) { cudaSetDevice(mesh->device); rtb::free_device_tree(mesh->dtree); }
+    mesh->tree = std::move(T);
+    mesh->built = true; mesh->built_on_device = false; mesh->host_tree_valid = true;
+    mesh->seconds_sort = mesh->seconds_partition = 0.0;
+    return RTB_OK;
+}
+int rtb_write_frame(const char* file_name, const uint32_t* bgra, int32_t width, int32_t height) {
+    if (!file_name || !bgra || width <= 0 || height <= 0) return fail(RTB_ERR_ARG, "write_frame: bad argument");
+    const std::string err = rtb::save_frame(file_name, bgra, width, height);
+    return err.empty() ? RTB_OK : fail(RTB_ERR_IO, err);
+}
 int rtb_mesh_build_seconds(const rtb_mesh* mesh, double out3[3]) {
     if (!mesh || !mesh->built || !out3) return fail(RTB_ERR_STATE, "build_seconds: tree not built");
-    out3[0] = mesh->tree.seconds_sort; out3[1] = mesh->tree.seconds_partition; out3[2] = out3[0] + out3[1];
+    out3[0] = mesh->seconds_sort; out3[1] = mesh->seconds_partition; out3[2] = out3[0] + out3[1];
     return RTB_OK;
 }
 void rtb_mesh_destroy(rtb_mesh* mesh) {
     if (!mesh) return;
-    if (mesh->d_points) { cudaSetDevice(mesh->device); cudaFree(mesh->d_points); }
+    if (mesh->d_points) { cudaSetDevice(mesh->device); cudaFree(mesh->d_points); rtb::free_device_tree(mesh->dtree); }
     delete mesh;
 }
 
@@ -430,8 +476,8 @@ int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj) {
     obj->cam = cam;
     cam->bound = obj;
 
-    const rtb::HostTree& T = m->tree;
-    const int64_t N = T.num_nodes, n = m->n, interior = n - 1;
+    const bool dev_tree = m->built_on_device;
+    const int64_t n = m->n, N = 2 * n - 1, interior = n - 1;
     dfree(obj->d_scene); dfree(obj->d_rad);
     obj->d_nodes = obj->d_tris = nullptr;
     const size_t node_bytes = sizeof(float4) * 4 * (size_t)std::max<int64_t>(interior, 1);
@@ -442,13 +488,23 @@ int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj) {
     obj->d_tris = obj->d_scene + node_bytes / sizeof(float4);
     if (!obj->d_work) RTB_CUDA(cudaMalloc(&obj->d_work, sizeof(unsigned long long)));
 
-    // Record index of every interior node.  The host tree is numbered breadth-first (Trixel.h:143);
-    // the device records are laid out depth-first (pre-order, left child first) so that a descent
-    // walks forward through memory: a node and its left child share a 128-byte line, and a subtree
-    // is one contiguous range (better L1/L2 locality for neighbouring rays).  Node identity never
-    // reaches the output, so the order is free.  RTB_NODE_ORDER=bfs keeps the reference numbering.
-    std::vector<int32_t> record_of((size_t)N, -1);
-    {
+    // Record index of every interior node.  The tree is numbered breadth-first (Trixel.h:143); the
+    // device records are laid out depth-first (pre-order, left child first) so that a descent walks
+    // forward through memory: a node and its left child share a 128-byte line, and a subtree is one
+    // contiguous range (better L1/L2 locality for neighbouring rays).  Node identity never reaches
+    // the output, so the order is free.  A device-built tree brings the pre-order ranks with it
+    // (DeviceTree::rec) and never visits the host; a host-built tree is numbered and uploaded here.
+    // RTB_NODE_ORDER=bfs keeps the reference numbering (host-built trees only).
+    float* d_bounds = nullptr; int* d_left = nullptr; int* d_tri = nullptr; unsigned char* d_cut = nullptr; int* d_rec = nullptr;
+    cudaError_t e = cudaSuccess;
+    const float* root_bounds = nullptr;
+    int root_tri = -1;
+    if (dev_tree) {
+        d_bounds = m->dtree.bounds; d_left = m->dtree.left; d_tri = m->dtree.tri; d_cut = m->dtree.cut; d_rec = m->dtree.rec;
+        root_bounds = m->dtree.root_bounds; root_tri = m->dtree.root_tri;
+    } else {
+        const rtb::HostTree& T = m->tree;
+        std::vector<int32_t> record_of((size_t)N, -1);
         const char* order = std::getenv("RTB_NODE_ORDER");
         int32_t next = 0;
         if (order && std::strcmp(order, "bfs") == 0) {
@@ -466,19 +522,18 @@ int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj) {
                 stack.push_back(l);
             }
         }
+        e = cudaMalloc(&d_bounds, sizeof(float) * 6 * (size_t)N);
+        if (e == cudaSuccess) e = cudaMalloc(&d_left, sizeof(int) * (size_t)N);
+        if (e == cudaSuccess) e = cudaMalloc(&d_tri, sizeof(int) * (size_t)N);
+        if (e == cudaSuccess) e = cudaMalloc(&d_cut, (size_t)N);
+        if (e == cudaSuccess) e = cudaMalloc(&d_rec, sizeof(int) * (size_t)N);
+        if (e == cudaSuccess) e = cudaMemcpy(d_bounds, T.bounds.data(), sizeof(float) * 6 * (size_t)N, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_left, T.left.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_tri, T.tri.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_cut, T.cut_flag.data(), (size_t)N, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_rec, record_of.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice);
+        root_bounds = T.bounds.data(); root_tri = T.tri[0];
     }
-
-    float* d_bounds = nullptr; int* d_left = nullptr; int* d_tri = nullptr; unsigned char* d_cut = nullptr; int* d_rec = nullptr;
-    cudaError_t e = cudaMalloc(&d_bounds, sizeof(float) * 6 * (size_t)N);
-    if (e == cudaSuccess) e = cudaMalloc(&d_left, sizeof(int) * (size_t)N);
-    if (e == cudaSuccess) e = cudaMalloc(&d_tri, sizeof(int) * (size_t)N);
-    if (e == cudaSuccess) e = cudaMalloc(&d_cut, (size_t)N);
-    if (e == cudaSuccess) e = cudaMalloc(&d_rec, sizeof(int) * (size_t)N);
-    if (e == cudaSuccess) e = cudaMemcpy(d_bounds, T.bounds.data(), sizeof(float) * 6 * (size_t)N, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_left, T.left.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_tri, T.tri.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_cut, T.cut_flag.data(), (size_t)N, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_rec, record_of.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice);
     const float cx = cam->basis.pos[0], cy = cam->basis.pos[1], cz = cam->basis.pos[2];
     if (e == cudaSuccess) {
         rtb::pack_triangles_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cam->stream>>>(m->d_points, n, cx, cy, cz, obj->d_tris);
@@ -494,15 +549,15 @@ int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj) {
         if (e == cudaSuccess) e = cudaMemcpy(obj->d_rad, rad4.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(cam->stream);
-    cudaFree(d_bounds); cudaFree(d_left); cudaFree(d_tri); cudaFree(d_cut); cudaFree(d_rec);
+    if (!dev_tree) { cudaFree(d_bounds); cudaFree(d_left); cudaFree(d_tri); cudaFree(d_cut); cudaFree(d_rec); }
     if (e != cudaSuccess) return fail(RTB_ERR_CUDA, std::string("add_object: ") + cudaGetErrorString(e));
 
     // root box, camera-relative (same arithmetic as pack_nodes_kernel; host is compiled without FMA)
-    const float* rb = T.bounds.data();
+    const float* rb = root_bounds;
     obj->root_box[0] = (rb[0] - cx) + 0.0f; obj->root_box[3] = (rb[1] - cx) + 0.0f;
     obj->root_box[1] = (rb[2] - cy) + 0.0f; obj->root_box[4] = (rb[3] - cy) + 0.0f;
     obj->root_box[2] = (rb[4] - cz) + 0.0f; obj->root_box[5] = (rb[5] - cz) + 0.0f;
-    obj->root_ref = n == 1 ? (int)(rtb::kRefLeaf | (unsigned)T.tri[0]) : 0;
+    obj->root_ref = n == 1 ? (int)(rtb::kRefLeaf | (unsigned)root_tri) : 0;
 
     // pin nodes + triangles in L2 (the 800k-triangle dragon fits).  The
     // window is attached to every render launch (launch_render).

@@ -126,7 +126,8 @@ __global__ void scatter_kernel(Lists L, int k, const int* __restrict__ node_of_p
 }
 // one thread per node of the level: create the two children (Trixel.h:329-352)
 __global__ void children_kernel(Lists L, int level_begin, int count, int next_begin, const int* __restrict__ child_scan, int* __restrict__ lo,
-                                int* __restrict__ hi, int* __restrict__ parent, int* __restrict__ left, float* __restrict__ bounds) {
+                                int* __restrict__ hi, int* __restrict__ parent, int* __restrict__ left, float* __restrict__ bounds,
+                                int* __restrict__ rec) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= count) return;
     const int node = level_begin + q, l = lo[node], r = hi[node];
@@ -136,6 +137,9 @@ __global__ void children_kernel(Lists L, int level_begin, int count, int next_be
     left[node] = cl;
     lo[cl] = l; hi[cl] = m; parent[cl] = node;
     lo[cr] = m + 1; hi[cr] = r; parent[cr] = node;
+    // pre-order rank among interior nodes: the left subtree [l,m] holds m-l interior nodes and follows its parent directly
+    rec[cl] = m > l ? rec[node] + 1 : -1;
+    rec[cr] = r > m + 1 ? rec[node] + 1 + (m - l) : -1;
     for (int c = 0; c < 2; c++) {
         const int a = c ? m + 1 : l, b = c ? r : m;
         float* B = bounds + 6ll * (c ? cr : cl);  // x0,x1,y0,y1,z0,z1 (Trixel.h:345-350)
@@ -175,9 +179,31 @@ inline unsigned blocks(long long n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace
 
-// Builds the tree of the triangle soup `d_points9` (device, 9 floats per triangle) on the current device and
-// copies it into `T`.  Returns an empty string on success.
-std::string build_tree_gpu(const float* d_points9, int64_t n64, HostTree& T) {
+void free_device_tree(DeviceTree& t) {
+    cudaFree(t.bounds); cudaFree(t.left); cudaFree(t.tri); cudaFree(t.cut); cudaFree(t.s1); cudaFree(t.s2); cudaFree(t.rec);
+    t = DeviceTree();
+}
+
+std::string download_tree(const DeviceTree& D, HostTree& T) {
+    std::string err;
+    const size_t N = (size_t)D.num_nodes;
+    T.num_tri = D.num_tri; T.num_nodes = D.num_nodes;
+    T.bounds.resize(N * 6); T.left.resize(N); T.tri.resize(N); T.cut_flag.resize(N); T.s1.resize(N); T.s2.resize(N);
+    RTB_BUILD_CUDA(cudaMemcpy(T.bounds.data(), D.bounds, sizeof(float) * 6 * N, cudaMemcpyDeviceToHost));
+    RTB_BUILD_CUDA(cudaMemcpy(T.left.data(), D.left, sizeof(int) * N, cudaMemcpyDeviceToHost));
+    RTB_BUILD_CUDA(cudaMemcpy(T.tri.data(), D.tri, sizeof(int) * N, cudaMemcpyDeviceToHost));
+    RTB_BUILD_CUDA(cudaMemcpy(T.cut_flag.data(), D.cut, N, cudaMemcpyDeviceToHost));
+    RTB_BUILD_CUDA(cudaMemcpy(T.s1.data(), D.s1, sizeof(float) * N, cudaMemcpyDeviceToHost));
+    RTB_BUILD_CUDA(cudaMemcpy(T.s2.data(), D.s2, sizeof(float) * N, cudaMemcpyDeviceToHost));
+    T.seconds_sort = D.seconds_sort; T.seconds_partition = D.seconds_partition;
+done:
+    if (!err.empty()) cudaGetLastError();
+    return err;
+}
+
+// Builds the tree of the triangle soup `d_points9` (device, 9 floats per triangle) on the current device and leaves
+// it there (`T`; release with free_device_tree).  Returns an empty string on success.
+std::string build_tree_gpu(const float* d_points9, int64_t n64, DeviceTree& T) {
     using clock = std::chrono::steady_clock;
     std::string err;
     if (n64 <= 0 || n64 > 0x1fffffff) return "build_tree_gpu: bad triangle count";
@@ -189,7 +215,7 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, HostTree& T) {
     float *key = nullptr, *bounds = nullptr, *s1 = nullptr, *s2 = nullptr;
     unsigned *ukey_in = nullptr, *ukey_out = nullptr;
     int *ids_in = nullptr, *order = nullptr, *order_tmp = nullptr, *rank = nullptr, *node_of_pos = nullptr, *flag = nullptr, *scan = nullptr;
-    int *lo = nullptr, *hi = nullptr, *parent = nullptr, *left = nullptr, *tri = nullptr, *interior = nullptr, *child_scan = nullptr;
+    int *lo = nullptr, *hi = nullptr, *parent = nullptr, *left = nullptr, *tri = nullptr, *interior = nullptr, *child_scan = nullptr, *rec = nullptr;
     unsigned char* cut = nullptr;
     void* temp = nullptr;
     size_t temp_bytes = 0, need = 0;
@@ -211,6 +237,7 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, HostTree& T) {
     RTB_BUILD_CUDA(cudaMalloc(&parent, sizeof(int) * (size_t)N));
     RTB_BUILD_CUDA(cudaMalloc(&left, sizeof(int) * (size_t)N));
     RTB_BUILD_CUDA(cudaMalloc(&tri, sizeof(int) * (size_t)N));
+    RTB_BUILD_CUDA(cudaMalloc(&rec, sizeof(int) * (size_t)N));
     RTB_BUILD_CUDA(cudaMalloc(&interior, sizeof(int) * (size_t)n));
     RTB_BUILD_CUDA(cudaMalloc(&child_scan, sizeof(int) * (size_t)n));
     RTB_BUILD_CUDA(cudaMalloc(&cut, (size_t)N));
@@ -242,6 +269,8 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, HostTree& T) {
         RTB_BUILD_CUDA(cudaMemcpy(lo, &zero, sizeof(int), cudaMemcpyHostToDevice));
         RTB_BUILD_CUDA(cudaMemcpy(hi, &last, sizeof(int), cudaMemcpyHostToDevice));
         RTB_BUILD_CUDA(cudaMemcpy(parent, &zero, sizeof(int), cudaMemcpyHostToDevice));
+        const int root_rec = n > 1 ? 0 : -1;
+        RTB_BUILD_CUDA(cudaMemcpy(rec, &root_rec, sizeof(int), cudaMemcpyHostToDevice));
     }
     root_bounds_kernel<<<1, 1>>>(L, bounds);
     while (level_begin < level_end) {
@@ -262,7 +291,7 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, HostTree& T) {
                 RTB_BUILD_CUDA(cudaMemcpyAsync(order + (size_t)k * n, order_tmp, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice));
             }
         }
-        children_kernel<<<blocks(count), 256>>>(L, level_begin, count, level_end, child_scan, lo, hi, parent, left, bounds);
+        children_kernel<<<blocks(count), 256>>>(L, level_begin, count, level_end, child_scan, lo, hi, parent, left, bounds, rec);
         reassign_kernel<<<blocks(n), 256>>>(n, node_of_pos, lo, hi, left);
         level_begin = level_end;
         level_end += 2 * num_interior;
@@ -271,23 +300,19 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, HostTree& T) {
     RTB_BUILD_CUDA(cudaDeviceSynchronize());
     if (level_end != N) { err = "build_tree_gpu: node count mismatch"; goto done; }
 
-    // ---- copy out ---------------------------------------------------------------------------------------
+    // ---- the tree stays on the device ------------------------------------------------------------------
+    RTB_BUILD_CUDA(cudaMemcpy(T.root_bounds, bounds, sizeof(float) * 6, cudaMemcpyDeviceToHost));
+    RTB_BUILD_CUDA(cudaMemcpy(&T.root_tri, tri, sizeof(int), cudaMemcpyDeviceToHost));
     T.num_tri = n; T.num_nodes = N;
-    T.bounds.resize((size_t)N * 6); T.left.resize((size_t)N); T.tri.resize((size_t)N); T.cut_flag.resize((size_t)N);
-    T.s1.resize((size_t)N); T.s2.resize((size_t)N);
-    RTB_BUILD_CUDA(cudaMemcpy(T.bounds.data(), bounds, sizeof(float) * 6 * (size_t)N, cudaMemcpyDeviceToHost));
-    RTB_BUILD_CUDA(cudaMemcpy(T.left.data(), left, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost));
-    RTB_BUILD_CUDA(cudaMemcpy(T.tri.data(), tri, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost));
-    RTB_BUILD_CUDA(cudaMemcpy(T.cut_flag.data(), cut, (size_t)N, cudaMemcpyDeviceToHost));
-    RTB_BUILD_CUDA(cudaMemcpy(T.s1.data(), s1, sizeof(float) * (size_t)N, cudaMemcpyDeviceToHost));
-    RTB_BUILD_CUDA(cudaMemcpy(T.s2.data(), s2, sizeof(float) * (size_t)N, cudaMemcpyDeviceToHost));
+    T.bounds = bounds; T.left = left; T.tri = tri; T.cut = cut; T.s1 = s1; T.s2 = s2; T.rec = rec;
+    bounds = nullptr; left = nullptr; tri = nullptr; cut = nullptr; s1 = nullptr; s2 = nullptr; rec = nullptr;
     T.seconds_sort = std::chrono::duration<double>(t_sorted - t_begin).count();
     T.seconds_partition = std::chrono::duration<double>(clock::now() - t_sorted).count();
 
 done:
     cudaFree(key); cudaFree(ukey_in); cudaFree(ukey_out); cudaFree(ids_in); cudaFree(order); cudaFree(order_tmp); cudaFree(rank);
     cudaFree(node_of_pos); cudaFree(flag); cudaFree(scan); cudaFree(lo); cudaFree(hi); cudaFree(parent); cudaFree(left); cudaFree(tri);
-    cudaFree(interior); cudaFree(child_scan); cudaFree(cut); cudaFree(bounds); cudaFree(s1); cudaFree(s2); cudaFree(temp);
+    cudaFree(interior); cudaFree(child_scan); cudaFree(cut); cudaFree(rec); cudaFree(bounds); cudaFree(s1); cudaFree(s2); cudaFree(temp);
     if (!err.empty()) cudaGetLastError();
     return err;
 }

@@ -355,6 +355,138 @@ std::string save_ply(const char* path, const float* points9, uint32_t num_tri) {
 }
 
 // =================================================================================================
+// frame and tree files
+// =================================================================================================
+namespace {
+uint32_t crc32_update(uint32_t crc, const unsigned char* p, size_t n) {
+    static uint32_t table[256];
+    static bool ready = false;
+    if (!ready) {
+        for (uint32_t i = 0; i < 256; i++) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; k++) c = (c & 1) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+        ready = true;
+    }
+    for (size_t i = 0; i < n; i++) crc = table[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
+    return crc;
+}
+void put_be32(std::vector<unsigned char>& v, uint32_t x) { for (int s = 24; s >= 0; s -= 8) v.push_back((unsigned char)(x >> s)); }
+void png_chunk(FILE* f, const char type[4], const std::vector<unsigned char>& data) {
+    std::vector<unsigned char> head;
+    put_be32(head, (uint32_t)data.size());
+    std::fwrite(head.data(), 1, 4, f);
+    std::fwrite(type, 1, 4, f);
+    if (!data.empty()) std::fwrite(data.data(), 1, data.size(), f);
+    uint32_t crc = crc32_update(0xffffffffu, (const unsigned char*)type, 4);
+    crc = crc32_update(crc, data.data(), data.size()) ^ 0xffffffffu;
+    std::vector<unsigned char> tail;
+    put_be32(tail, crc);
+    std::fwrite(tail.data(), 1, 4, f);
+}
+uint64_t fnv1a64(const void* data, size_t n) {
+    const unsigned char* p = (const unsigned char*)data;
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 0x100000001b3ull; }
+    return h;
+}
+}  // namespace
+
+// The frame buffer is the reference's (Camera.cpp:79, Camera.h:35): W*H little-endian 0x00RRGGBB words, row 0 at the
+// BOTTOM (what StretchDIBits consumes, WinMain.cpp:217); image files are written top row first.
+// .ppm -> binary P6; .png -> 8-bit RGB, zlib "stored" blocks (no compression library needed, any viewer reads it).
+std::string save_frame(const char* path, const uint32_t* bgra, int W, int H) {
+    const std::string name(path);
+    const bool png = name.size() >= 4 && name.compare(name.size() - 4, 4, ".png") == 0;
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return std::string("write_frame: cannot open ") + path;
+    std::vector<unsigned char> row((size_t)W * 3);
+    auto fill_row = [&](int y) {
+        const uint32_t* src = bgra + (size_t)(H - 1 - y) * W;
+        for (int x = 0; x < W; x++) { row[3 * x] = (unsigned char)(src[x] >> 16); row[3 * x + 1] = (unsigned char)(src[x] >> 8); row[3 * x + 2] = (unsigned char)src[x]; }
+    };
+    if (!png) {
+        std::fprintf(f, "P6\n%d %d\n255\n", W, H);
+        for (int y = 0; y < H; y++) { fill_row(y); std::fwrite(row.data(), 1, row.size(), f); }
+        std::fclose(f);
+        return "";
+    }
+    const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    std::fwrite(sig, 1, 8, f);
+    std::vector<unsigned char> ihdr;
+    put_be32(ihdr, (uint32_t)W); put_be32(ihdr, (uint32_t)H);
+    ihdr.push_back(8); ihdr.push_back(2); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);  // 8-bit RGB
+    png_chunk(f, "IHDR", ihdr);
+    std::vector<unsigned char> raw;  // filter byte 0 + RGB per row
+    raw.reserve((size_t)H * (row.size() + 1));
+    for (int y = 0; y < H; y++) { fill_row(y); raw.push_back(0); raw.insert(raw.end(), row.begin(), row.end()); }
+    std::vector<unsigned char> z;
+    z.push_back(0x78); z.push_back(0x01);
+    uint32_t a = 1, b = 0;  // Adler-32 of the raw stream
+    for (size_t at = 0; at < raw.size() || at == 0;) {
+        const size_t n = std::min<size_t>(65535, raw.size() - at);
+        const bool last = at + n >= raw.size();
+        z.push_back(last ? 1 : 0);
+        z.push_back((unsigned char)(n & 0xff)); z.push_back((unsigned char)(n >> 8));
+        z.push_back((unsigned char)(~n & 0xff)); z.push_back((unsigned char)((~n >> 8) & 0xff));
+        z.insert(z.end(), raw.begin() + (long)at, raw.begin() + (long)(at + n));
+        for (size_t i = at; i < at + n; i++) { a = (a + raw[i]) % 65521u; b = (b + a) % 65521u; }
+        at += n;
+        if (last) break;
+    }
+    put_be32(z, (b << 16) | a);
+    png_chunk(f, "IDAT", z);
+    png_chunk(f, "IEND", std::vector<unsigned char>());
+    std::fclose(f);
+    return "";
+}
+
+// Tree cache: the built tree of one mesh as a flat little-endian blob, tied to the mesh by a hash of its points.
+//   "RTBKD1\0\0" | u64 num_tri | u64 num_nodes | u64 fnv1a64(points9) | bounds[6N] f32 | left[N] i32 | tri[N] i32 |
+//   s1[N] f32 | s2[N] f32 | cut_flag[N] u8
+std::string save_tree(const char* path, const HostTree& T, const float* points9) {
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return std::string("save_tree: cannot open ") + path;
+    const uint64_t head[3] = {(uint64_t)T.num_tri, (uint64_t)T.num_nodes, fnv1a64(points9, sizeof(float) * 9 * (size_t)T.num_tri)};
+    const size_t N = (size_t)T.num_nodes;
+    bool ok = std::fwrite("RTBKD1\0\0", 1, 8, f) == 8 && std::fwrite(head, 8, 3, f) == 3;
+    ok = ok && std::fwrite(T.bounds.data(), 4, 6 * N, f) == 6 * N && std::fwrite(T.left.data(), 4, N, f) == N;
+    ok = ok && std::fwrite(T.tri.data(), 4, N, f) == N && std::fwrite(T.s1.data(), 4, N, f) == N && std::fwrite(T.s2.data(), 4, N, f) == N;
+    ok = ok && std::fwrite(T.cut_flag.data(), 1, N, f) == N;
+    std::fclose(f);
+    return ok ? "" : std::string("save_tree: short write to ") + path;
+}
+std::string load_tree(const char* path, const float* points9, int64_t num_tri, HostTree& T) {
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return std::string("load_tree: cannot open ") + path;
+    char magic[8];
+    uint64_t head[3];
+    std::string err;
+    if (std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, "RTBKD1\0\0", 8) != 0 || std::fread(head, 8, 3, f) != 3) err = "load_tree: not a tree file";
+    else if ((int64_t)head[0] != num_tri || head[1] != 2 * head[0] - 1) err = "load_tree: the file holds a tree of a different triangle count";
+    else if (head[2] != fnv1a64(points9, sizeof(float) * 9 * (size_t)num_tri)) err = "load_tree: the file belongs to a different mesh (point hash mismatch)";
+    if (err.empty()) {
+        const size_t N = (size_t)head[1];
+        T.num_tri = num_tri; T.num_nodes = (int64_t)N;
+        T.bounds.resize(6 * N); T.left.resize(N); T.tri.resize(N); T.s1.resize(N); T.s2.resize(N); T.cut_flag.resize(N);
+        bool ok = std::fread(T.bounds.data(), 4, 6 * N, f) == 6 * N && std::fread(T.left.data(), 4, N, f) == N;
+        ok = ok && std::fread(T.tri.data(), 4, N, f) == N && std::fread(T.s1.data(), 4, N, f) == N && std::fread(T.s2.data(), 4, N, f) == N;
+        ok = ok && std::fread(T.cut_flag.data(), 1, N, f) == N;
+        // structural sanity, so that a damaged file cannot send the traversal out of bounds
+        for (size_t i = 0; ok && i < N; i++) {
+            const int32_t l = T.left[i];
+            if (l < 0) ok = T.tri[i] >= 0 && T.tri[i] < num_tri;
+            else ok = (size_t)l + 1 < N && (size_t)l > i && T.cut_flag[i] < 6;
+        }
+        if (!ok) err = "load_tree: truncated or damaged file";
+        T.seconds_sort = T.seconds_partition = 0.0;
+    }
+    std::fclose(f);
+    return err;
+}
+
+// =================================================================================================
 // procedural stand-in mesh
 // =================================================================================================
 namespace {

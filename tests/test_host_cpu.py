@@ -213,3 +213,65 @@ def test_render_without_gpu_fails_loudly(rtb):
         cam.add_object(obj)
     with pytest.raises(rtb.RtbError):
         obj.render(cam)
+
+
+def test_frame_files(rtb, tmp_path):
+    """rtb_write_frame: the headless stand-in of the reference's window blit -- PPM and PNG, bottom-up rows flipped."""
+    import struct
+    import zlib
+    W, H = 5, 3
+    frame = (np.arange(W * H, dtype=np.uint32) * 0x010203 + 0x00f08200) & 0x00ffffff
+    rgb = np.stack([(frame >> 16) & 0xff, (frame >> 8) & 0xff, frame & 0xff], 1).astype(np.uint8).reshape(H, W, 3)[::-1]
+    ppm = tmp_path / "f.ppm"
+    rtb.write_frame(str(ppm), frame, W, H)
+    data = ppm.read_bytes()
+    assert data.startswith(b"P6\n5 3\n255\n") and data[len(b"P6\n5 3\n255\n"):] == rgb.tobytes()
+    png = tmp_path / "f.png"
+    rtb.write_frame(str(png), frame, W, H)
+    data = png.read_bytes()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    at, idat, seen = 8, b"", []
+    while at < len(data):
+        n, kind = struct.unpack(">I4s", data[at:at + 8])
+        body = data[at + 8:at + 8 + n]
+        assert struct.unpack(">I", data[at + 8 + n:at + 12 + n])[0] == zlib.crc32(kind + body)
+        seen.append(kind)
+        if kind == b"IHDR":
+            assert struct.unpack(">IIBBBBB", body) == (W, H, 8, 2, 0, 0, 0)
+        if kind == b"IDAT":
+            idat += body
+        at += 12 + n
+    assert seen[0] == b"IHDR" and seen[-1] == b"IEND"
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(H, 1 + 3 * W)
+    assert (raw[:, 0] == 0).all() and np.array_equal(raw[:, 1:].reshape(H, W, 3), rgb)
+    with pytest.raises(rtb.RtbError):
+        rtb.write_frame(str(tmp_path / "no_such_dir" / "f.ppm"), frame, W, H)
+
+
+def test_tree_cache_round_trip(rtb, tmp_path):
+    pts = rtb.geodesic_mesh(6)
+    a = rtb.Trixel(pts, require_device=False)
+    a.create_kd(where=1)
+    path = tmp_path / "mesh.kd"
+    a.save_tree(str(path))
+    b = rtb.Trixel(pts, require_device=False)
+    b.load_tree(str(path))
+    ta, tb = a.tree(), b.tree()
+    for k in ta:
+        assert np.array_equal(np.asarray(ta[k]).view(np.uint8), np.asarray(tb[k]).view(np.uint8)), k
+    # a cache of another mesh, a truncated file and a damaged child index are refused
+    other = rtb.Trixel(pts[::-1].copy(), require_device=False)
+    with pytest.raises(rtb.RtbError):
+        other.load_tree(str(path))
+    blob = path.read_bytes()
+    (tmp_path / "short.kd").write_bytes(blob[:len(blob) // 2])
+    with pytest.raises(rtb.RtbError):
+        b.load_tree(str(tmp_path / "short.kd"))
+    bad = bytearray(blob)
+    N = 2 * len(pts) - 1
+    off = 32 + 4 * 6 * N  # first entry of left[]
+    bad[off:off + 4] = (N + 5).to_bytes(4, "little")
+    (tmp_path / "bad.kd").write_bytes(bytes(bad))
+    with pytest.raises(rtb.RtbError):
+        b.load_tree(str(tmp_path / "bad.kd"))
+    a.close(); b.close(); other.close()

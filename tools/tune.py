@@ -29,9 +29,13 @@ views["default"] = np.stack([obj.matrix()] + [obj.transform_host(rtb.R_KEY_QUAT,
 for _ in range(140):
     obj.transform((float(n[0]), float(n[1]), float(n[2]), 0.005), rtb.TRANSLATE_Z)
 views["closeup"] = np.stack([obj.matrix()] + [obj.transform_host(rtb.R_KEY_QUAT, rtb.ROTATE_TRI_PY) for _ in range(F - 1)])
-grid = {"RTB_T_ACTIVE": (sys.argv[1] if len(sys.argv) > 1 else "12,16,20,24,28").split(","),
-        "RTB_T_LEAF": (sys.argv[2] if len(sys.argv) > 2 else "4,8,12,16").split(","),
-        "RTB_UNIT_SHIFT": (sys.argv[3] if len(sys.argv) > 3 else "7").split(",")}
+# arguments: KEY=v1,v2,... (RTB_ prefix implied), e.g.  T_ACTIVE=12,20 PREFETCH=0,1,2,3
+grid = {}
+for arg in sys.argv[1:]:
+    k, v = arg.split("=")
+    grid["RTB_" + k] = v.split(",")
+if not grid:
+    grid = {"RTB_T_ACTIVE": ["12", "16", "20", "24"], "RTB_T_LEAF": ["4", "8", "12"]}
 keys = list(grid)
 print("%-36s %18s %18s" % ("setting", "default mean/min ms", "closeup mean/min ms"))
 for combo in itertools.product(*[grid[k] for k in keys]):
