@@ -294,12 +294,11 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MIN_BLOCKS) render_stream_k
         // ================= refill: next pixels of the warp's unit ====================================
         if (PUSH && !exhausted && u_next >= unit_pixels) blocked = open_mask == (1u << kPushSlots) - 1u;
         if (!exhausted && u_next >= unit_pixels && !(PUSH && blocked)) {
-            unsigned long long uid = 0;
-            if (lane == 0) uid = atomicAdd(P.work_counter, 1ull);
-            uid = __shfl_sync(0xffffffffu, uid, 0);
-            if ((long long)uid >= P.total_items) {
-                exhausted = true;
-            } else {
+            for (;;) {
+                unsigned long long uid = 0;
+                if (lane == 0) uid = atomicAdd(P.work_counter, 1ull);
+                uid = __shfl_sync(0xffffffffu, uid, 0);
+                if ((long long)uid >= P.total_items) { exhausted = true; break; }
                 const long long per_frame = (long long)P.my_tiles * units_per_tile;
                 u_frame = (int)((long long)uid / per_frame);
                 const int rem = (int)((long long)uid - (long long)u_frame * per_frame);
@@ -308,19 +307,50 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MIN_BLOCKS) render_stream_k
                 u_base = (rem % units_per_tile) << P.unit_shift;
                 u_x0 = (tile % P.tiles_x) * kTile;
                 u_y0 = (tile / P.tiles_x) * kTile;
-                u_next = 0;
                 const float* __restrict__ F = P.frames + (long long)kFrameStride * u_frame;
                 u_rx0 = __float_as_int(__ldg(F + 12)); u_ry0 = __float_as_int(__ldg(F + 13));
                 u_rx1 = __float_as_int(__ldg(F + 14)); u_ry1 = __float_as_int(__ldg(F + 15));
+                const int xoff = (int)compact_even_bits((uint32_t)u_base), yoff = (int)compact_even_bits((uint32_t)u_base >> 1);
+                if (!COUNT) {
+                    // ---- a unit that lies entirely outside the frame's root-box rectangle is background: the warp
+                    // writes it with 16-byte stores at its final place and goes for the next unit -----------------
+                    const int wshift = (P.unit_shift + 1) >> 1;  // a unit is a (1 << wshift) x (unit_pixels >> wshift) pixel block
+                    const int bx = u_x0 + xoff, by = u_y0 + yoff;
+                    if (bx > u_rx1 || bx + (1 << wshift) - 1 < u_rx0 || by > u_ry1 || by + (unit_pixels >> wshift) - 1 < u_ry0) {
+                        uint32_t* __restrict__ dc = PUSH ? P.push_bgra : P.out_bgra;
+                        int32_t* __restrict__ di = PUSH ? P.push_ids : P.out_ids;
+                        const bool row_major = PUSH || !P.tile_major;
+                        const long long fbase = (long long)u_frame * (PUSH ? (long long)P.W * P.H : P.frame_stride);
+                        const bool vec = !row_major || (P.W & 3) == 0;
+                        for (int i = (int)lane; i < (unit_pixels >> 2); i += 32) {
+                            const int row = i >> (wshift - 2), col = (i - (row << (wshift - 2))) << 2;
+                            const int px = bx + col, py = by + row;
+                            if (py >= P.H || px >= P.W) continue;
+                            const long long o = fbase + (row_major ? (long long)py * P.W + px : ((long long)u_slot * kTile + yoff + row) * kTile + xoff + col);
+                            if (vec && px + 3 < P.W) {
+                                if (dc) __stcs(reinterpret_cast<uint4*>(dc + o), make_uint4(P.background, P.background, P.background, P.background));
+                                if (di) __stcs(reinterpret_cast<int4*>(di + o), make_int4(-1, -1, -1, -1));
+                            } else {
+                                for (int k = 0; k < 4 && px + k < P.W; k++) {
+                                    if (dc) __stcs(dc + o + k, P.background);
+                                    if (di) __stcs(di + o + k, -1);
+                                }
+                            }
+                        }
+                        continue;
+                    }
+                }
+                u_next = 0;
                 if (PUSH) {
                     u_pslot = __ffs(~open_mask) - 1;
                     open_mask |= 1u << u_pslot;
                     if (lane == 0) {
                         s_owed[wib][u_pslot] = unit_pixels;
-                        s_unit[wib][u_pslot] = make_int4(u_frame, u_slot, (int)compact_even_bits((uint32_t)u_base), (int)compact_even_bits((uint32_t)u_base >> 1));
+                        s_unit[wib][u_pslot] = make_int4(u_frame, u_slot, xoff, yoff);
                     }
                     __syncwarp();
                 }
+                break;
             }
         }
         if (!exhausted) {
