@@ -223,7 +223,27 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, int num_f
     P.unit_shift = std::min(10, std::max(5, env_int("RTB_UNIT_SHIFT", shift)));
     P.t_active = std::min(31, std::max(0, env_int("RTB_T_ACTIVE", 12)));
     P.t_leaf = std::max(1, env_int("RTB_T_LEAF", 8));
-    P.total_items = (long long)num_frames * P.my_tiles * ((kTile * kTile) >> P.unit_shift);
+    // Segments of decreasing unit size towards the end of the launch (see RenderParams::seg_*): a unit handed out late
+    // is worked through by ONE warp while the queue is already empty, so late units must be small.  Measured on the
+    // dragon stand-in (60 frames): see DESIGN.md.  RTB_TAIL6 / RTB_TAIL5 = number of trailing frames in 64- / 32-pixel units.
+    {
+        int t5 = 0, t6 = 0;
+        if (P.unit_shift > 5 && num_frames >= 8) t5 = std::max(1, num_frames / 20);  // measured: 3 of 60 frames; a 64-pixel segment adds nothing
+        t5 = std::min(num_frames, std::max(0, env_int("RTB_TAIL5", t5)));
+        t6 = std::min(num_frames - t5, std::max(0, env_int("RTB_TAIL6", t6)));
+        P.seg_frames[0] = num_frames - t6 - t5; P.seg_shift[0] = P.unit_shift;
+        P.seg_frames[1] = t6;                   P.seg_shift[1] = std::min(P.unit_shift, 6);
+        P.seg_frames[2] = t5;                   P.seg_shift[2] = 5;
+        P.total_items = 0;
+        for (int k = 0; k < 3; k++) {
+            P.seg_items[k] = (long long)P.seg_frames[k] * P.my_tiles * ((kTile * kTile) >> P.seg_shift[k]);
+            P.total_items += P.seg_items[k];
+        }
+        if (P.seg_frames[0] == 0) {  // keep segment 0 non-empty: the kernel starts from its unit size
+            P.seg_frames[0] = P.seg_frames[1]; P.seg_shift[0] = P.seg_shift[1]; P.seg_items[0] = P.seg_items[1];
+            P.seg_frames[1] = 0; P.seg_items[1] = 0;
+        }
+    }
     const long long fetches = P.total_items;
     const long long blocks_needed = (fetches + (kBlockThreads / 32) - 1) / (kBlockThreads / 32);
     // RTB_RESERVE_SMS leaves SMs free for kernels that must run beside this persistent one (the NCCL

@@ -54,7 +54,12 @@ struct RenderParams {
     int tiles_x;           // tiles per image row
     int tile_first, tile_stride;
     int my_tiles;          // number of 32x32 tiles of one frame rendered by this launch
-    int unit_shift;        // log2 pixels per work unit: 5..10, a Morton block of a 32x32 tile
+    int unit_shift;        // log2 pixels per work unit: 5..10, a Morton block of a 32x32 tile (first segment)
+    // The frames of a launch form up to three consecutive segments with decreasing unit size, so that the last units
+    // handed out are small and the launch does not end with a few warps grinding through large units while the rest
+    // of the GPU idles.  seg_items[k] = seg_frames[k] * my_tiles * (1024 >> seg_shift[k]).
+    int seg_frames[3], seg_shift[3];
+    long long seg_items[3];
     int t_active, t_leaf;  // refill when <= t_active lanes still traverse; leaf step when >= t_leaf lanes wait at a leaf
     long long total_items; // work units: num_frames * my_tiles * (1024 >> unit_shift)
     long long frame_stride;  // output elements per frame: W*H (row-major) or my_tile_slots*1024 (tile-major)

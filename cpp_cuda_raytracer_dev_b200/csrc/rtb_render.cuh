@@ -160,9 +160,8 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MIN_BLOCKS) render_stream_k
     bool want_pop = false;
 
     // ---- warp-uniform unit state ----------------------------------------------------------------
-    const int unit_pixels = 1 << P.unit_shift;
-    const int units_per_tile = (kTile * kTile) >> P.unit_shift;
-    int u_next = unit_pixels;  // nothing loaded yet
+    int u_shift = P.seg_shift[0];  // log2 pixels of the warp's current unit
+    int u_next = 1 << u_shift;     // nothing loaded yet
     int u_frame = 0, u_x0 = 0, u_y0 = 0, u_base = 0, u_slot = 0;
     int u_rx0 = 0, u_ry0 = 0, u_rx1 = -1, u_ry1 = -1;  // pixel rectangle of the unit's frame that can reach the root box
     bool exhausted = false;
@@ -292,19 +291,30 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MIN_BLOCKS) render_stream_k
         const unsigned m_empty = ~m_trav;
 
         // ================= refill: next pixels of the warp's unit ====================================
-        if (PUSH && !exhausted && u_next >= unit_pixels) blocked = open_mask == (1u << kPushSlots) - 1u;
-        if (!exhausted && u_next >= unit_pixels && !(PUSH && blocked)) {
+        if (PUSH && !exhausted && u_next >= (1 << u_shift)) blocked = open_mask == (1u << kPushSlots) - 1u;
+        if (!exhausted && u_next >= (1 << u_shift) && !(PUSH && blocked)) {
             for (;;) {
                 unsigned long long uid = 0;
                 if (lane == 0) uid = atomicAdd(P.work_counter, 1ull);
                 uid = __shfl_sync(0xffffffffu, uid, 0);
                 if ((long long)uid >= P.total_items) { exhausted = true; break; }
+                // which segment of the launch (unit size), which frame, which tile, which block of the tile
+                long long item = (long long)uid;
+                int frame0 = 0;
+                u_shift = P.seg_shift[0];
+                if (item >= P.seg_items[0]) {
+                    item -= P.seg_items[0]; frame0 = P.seg_frames[0]; u_shift = P.seg_shift[1];
+                    if (item >= P.seg_items[1]) { item -= P.seg_items[1]; frame0 += P.seg_frames[1]; u_shift = P.seg_shift[2]; }
+                }
+                const int unit_pixels = 1 << u_shift;
+                const int units_per_tile = (kTile * kTile) >> u_shift;
                 const long long per_frame = (long long)P.my_tiles * units_per_tile;
-                u_frame = (int)((long long)uid / per_frame);
-                const int rem = (int)((long long)uid - (long long)u_frame * per_frame);
+                const int fseg = (int)(item / per_frame);
+                u_frame = frame0 + fseg;
+                const int rem = (int)(item - (long long)fseg * per_frame);
                 u_slot = rem / units_per_tile;
                 const int tile = P.tile_first + u_slot * P.tile_stride;
-                u_base = (rem % units_per_tile) << P.unit_shift;
+                u_base = (rem % units_per_tile) << u_shift;
                 u_x0 = (tile % P.tiles_x) * kTile;
                 u_y0 = (tile / P.tiles_x) * kTile;
                 const float* __restrict__ F = P.frames + (long long)kFrameStride * u_frame;
@@ -314,7 +324,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MIN_BLOCKS) render_stream_k
                 if (!COUNT) {
                     // ---- a unit that lies entirely outside the frame's root-box rectangle is background: the warp
                     // writes it with 16-byte stores at its final place and goes for the next unit -----------------
-                    const int wshift = (P.unit_shift + 1) >> 1;  // a unit is a (1 << wshift) x (unit_pixels >> wshift) pixel block
+                    const int wshift = (u_shift + 1) >> 1;  // a unit is a (1 << wshift) x (unit_pixels >> wshift) pixel block
                     const int bx = u_x0 + xoff, by = u_y0 + yoff;
                     if (bx > u_rx1 || bx + (1 << wshift) - 1 < u_rx0 || by > u_ry1 || by + (unit_pixels >> wshift) - 1 < u_ry0) {
                         uint32_t* __restrict__ dc = PUSH ? P.push_bgra : P.out_bgra;
@@ -346,7 +356,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MIN_BLOCKS) render_stream_k
                     open_mask |= 1u << u_pslot;
                     if (lane == 0) {
                         s_owed[wib][u_pslot] = unit_pixels;
-                        s_unit[wib][u_pslot] = make_int4(u_frame, u_slot, xoff, yoff);
+                        s_unit[wib][u_pslot] = make_int4(u_frame, u_slot, xoff | (u_shift << 8), yoff);
                     }
                     __syncwarp();
                 }
@@ -355,7 +365,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MIN_BLOCKS) render_stream_k
         }
         if (!exhausted) {
             const int slot = __popc(m_empty & lanemask_lt);
-            const int avail = unit_pixels - u_next;
+            const int avail = (1 << u_shift) - u_next;
             bool settled = false;  // PUSH: this lane took a pixel that needs no ray (outside the image, or background)
             if (((m_empty >> lane) & 1u) && slot < avail) {
                 settled = true;
@@ -433,9 +443,11 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MIN_BLOCKS) render_stream_k
             unsigned m_flush = __ballot_sync(0xffffffffu, lane < (unsigned)kPushSlots && ((open_mask >> lane) & 1u) && s_owed[wib][lane & (kPushSlots - 1)] == 0);
             open_mask &= ~m_flush;
             while (m_flush) {
-                const int4 d = s_unit[wib][__ffs(m_flush) - 1];
+                int4 d = s_unit[wib][__ffs(m_flush) - 1];
                 m_flush &= m_flush - 1u;
-                const int wshift = (P.unit_shift + 1) >> 1;  // a unit is a (1 << wshift) x (unit_pixels >> wshift) block of its tile
+                const int dshift = d.z >> 8, unit_pixels = 1 << dshift;
+                d.z &= 0xff;
+                const int wshift = (dshift + 1) >> 1;  // a unit is a (1 << wshift) x (unit_pixels >> wshift) block of its tile
                 const int tile = P.tile_first + d.y * P.tile_stride;
                 const int bx = (tile % P.tiles_x) * kTile + d.z, by = (tile / P.tiles_x) * kTile + d.w;
                 const long long lbase = (long long)d.x * P.frame_stride + ((long long)d.y * kTile + d.w) * kTile + d.z;
