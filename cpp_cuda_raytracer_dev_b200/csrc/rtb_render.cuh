@@ -130,8 +130,11 @@ __global__ void selftest_exact_kernel(uint64_t seed, long long count, unsigned l
 #ifndef RTB_MIN_BLOCKS
 #define RTB_MIN_BLOCKS 8
 #endif
+#ifndef RTB_MIN_BLOCKS_PUSH
+#define RTB_MIN_BLOCKS_PUSH 7  // the push variant carries more warp state: 72 registers spill nothing
+#endif
 template <bool CULL, bool COUNT, bool PUSH>
-__global__ void __launch_bounds__(kBlockThreads, RTB_MIN_BLOCKS) render_stream_kernel(const RenderParams P) {
+__global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RTB_MIN_BLOCKS) render_stream_kernel(const RenderParams P) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanemask_lt = (1u << lane) - 1u;
     __shared__ int s_owed[PUSH ? kBlockThreads / 32 : 1][PUSH ? kPushSlots : 1];   // pixels of an open unit not yet written
