@@ -290,6 +290,10 @@ def run_ours(args):
         ptrs = [b.ptr for b in bufs] if rank == 0 else [rtb.peer_open(h) for h in handles]
         push_ptr = [(ptrs[0], ptrs[1]), (ptrs[2], ptrs[3])]  # per slot: (colours, ids)
         push_flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        if rank == 0:
+            cam.fill_frames_device_async(FS, push_ptr[0][0], push_ptr[0][1], stream.cuda_stream)
+        torch.cuda.synchronize()
+        dist.barrier()
     elif tiles_mode and rank == 0:
         gather_col = [[torch.empty(FS * PE, dtype=torch.int32, device="cuda") for _ in range(world)] for _ in range(2)]
         gather_ids = [[torch.empty(FS * PE, dtype=torch.int32, device="cuda") for _ in range(world)] for _ in range(2)]
@@ -331,8 +335,12 @@ def run_ours(args):
             ev[step][0].record(stream)
             if push_mode:
                 obj.render_frames_push_async(cam, my_mats(step), push_ptr[slot][0], push_ptr[slot][1], stream.cuda_stream,
-                                             tile_first=rank, tile_stride=world)
+                                             tile_first=rank, tile_stride=world, flags=rtb.RENDER_PUSH_PREFILLED)
                 ev[step][1].record(stream)
+                if rank == 0:
+                    # the NEXT step's frames are pre-filled with background before this step's all-reduce lets any rank
+                    # start pushing into them: work units that hold nothing but background then never cross NVLink
+                    cam.fill_frames_device_async(FS, push_ptr[slot ^ 1][0], push_ptr[slot ^ 1][1], stream.cuda_stream)
                 dist.all_reduce(push_flag)  # completes when every rank's kernel has: the step's frames are whole on rank 0
             else:
                 obj.render_frames_device_async(cam, my_mats(step), d_col[slot].data_ptr(), d_ids[slot].data_ptr(), stream.cuda_stream,

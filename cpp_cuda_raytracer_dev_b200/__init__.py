@@ -22,7 +22,7 @@ LIB_PATH = os.environ.get("RTB_LIB") or os.path.join(HERE, "librtb.so")  # RTB_L
 
 SET_COLOR_TAG, PHONG_COLOR_TAG = 1, 2  # Camera.h:13-14
 TRANSLATE_XYZ, TRANSLATE_X, TRANSLATE_Z, ROTATE_TRI_PY, ROTATE_TRI_NY = 30, 31, 32, 10, 11  # platform_common.h:16-21
-RENDER_DEFAULT, RENDER_NO_CULL, RENDER_COUNTERS, RENDER_TILE_MAJOR = 0, 1, 2, 4
+RENDER_DEFAULT, RENDER_NO_CULL, RENDER_COUNTERS, RENDER_TILE_MAJOR, RENDER_PUSH_PREFILLED = 0, 1, 2, 4, 8
 R_KEY_QUAT = (0.0, 0.09950371902099893, 0.0, 0.9950371902099893)  # WinMain.cpp:187
 T_KEY_QUAT = (0.0, -0.09950371902099893, 0.0, 0.9950371902099893)  # WinMain.cpp:207
 DEFAULT_RGB = (0.1, 0.55, 0.2)  # WinMain.cpp:118-120
@@ -35,7 +35,7 @@ EXPORTS = [
     "rtb_camera_add_object", "rtb_camera_color_pixels", "rtb_camera_host_color", "rtb_camera_host_ids",
     "rtb_camera_counters", "rtb_camera_destroy", "rtb_object_create", "rtb_object_transform", "rtb_object_get_matrix",
     "rtb_object_set_matrix", "rtb_object_destroy", "rtb_object_render", "rtb_render_frame", "rtb_render_sweep",
-    "rtb_render_frames_device_async", "rtb_render_frames_push_async", "rtb_peer_alloc", "rtb_peer_free", "rtb_peer_export", "rtb_peer_open", "rtb_peer_close", "rtb_peer_read", "rtb_object_transform_host", "rtb_device_props", "rtb_launch_count", "rtb_tile_major_elements", "rtb_compose_tiles_device_async", "rtb_selftest_exact",
+    "rtb_render_frames_device_async", "rtb_render_frames_push_async", "rtb_fill_frames_device_async", "rtb_peer_alloc", "rtb_peer_free", "rtb_peer_export", "rtb_peer_open", "rtb_peer_close", "rtb_peer_read", "rtb_object_transform_host", "rtb_device_props", "rtb_launch_count", "rtb_tile_major_elements", "rtb_compose_tiles_device_async", "rtb_selftest_exact",
 ]
 
 
@@ -97,6 +97,7 @@ def _load():
     L.rtb_launch_count.restype = C.c_uint64
     L.rtb_selftest_exact.argtypes = [C.c_uint64, C.c_int64, vp]
     L.rtb_render_frames_push_async.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_uint32, vp, vp, vp]
+    L.rtb_fill_frames_device_async.argtypes = [vp, C.c_int32, vp, vp, vp]
     L.rtb_peer_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.rtb_peer_free.argtypes = [vp]
     L.rtb_peer_export.argtypes = [vp, vp]
@@ -263,6 +264,13 @@ class Camera:
     def tile_major_elements(self, tile_stride):
         """Per-frame element count of a RENDER_TILE_MAJOR buffer when tiles are dealt to `tile_stride` ranks."""
         return int(lib.rtb_tile_major_elements(self.h, tile_stride))
+
+    def fill_frames_device_async(self, num_frames, bgra_ptr, ids_ptr, stream_ptr=None):
+        """Background colour / -1 into `num_frames` device frames (the SET_COLOR_TAG fill, Camera.cu:12-18)."""
+        if stream_ptr == 0:
+            stream_ptr = 1  # cudaStreamLegacy
+        _check(lib.rtb_fill_frames_device_async(self.h, num_frames, bgra_ptr or None, ids_ptr or None, stream_ptr or None),
+               "rtb_fill_frames_device_async")
 
     def compose_tiles_device_async(self, num_frames, part_ptrs, out_ptr, stream_ptr=None):
         """Scatter gathered tile-major buffers (one device pointer per rank) into row-major frames."""

@@ -200,6 +200,7 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, int num_f
     P.out_bgra = d_bgra; P.out_ids = d_ids;
     const bool push = push_bgra || push_ids;
     P.push_bgra = push_bgra; P.push_ids = push_ids;
+    P.push_skip_background = (push && (flags & RTB_RENDER_PUSH_PREFILLED)) ? 1 : 0;
     P.tile_major = ((flags & RTB_RENDER_TILE_MAJOR) || push) ? 1 : 0;
     P.frame_stride = P.tile_major ? (long long)((tiles + tile_stride - 1) / tile_stride) * kTile * kTile : (long long)b.W * b.H;
     P.work_counter = o->d_work;
@@ -772,6 +773,20 @@ int rtb_render_frames_push_async(rtb_object* obj, rtb_camera* cam, int32_t num_f
     RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * rtb::kFrameStride * (size_t)num_frames, cudaMemcpyHostToDevice, s));
     return launch_render(obj, cam, obj->d_frames, num_frames, tile_first, tile_stride, flags, d_frame_bgra ? cam->push_bgra : nullptr,
                          d_frame_ids ? cam->push_ids : nullptr, s, d_frame_bgra, d_frame_ids);
+}
+
+int rtb_fill_frames_device_async(rtb_camera* cam, int32_t num_frames, uint32_t* d_frame_bgra, int32_t* d_frame_ids, void* stream) {
+    if (!cam || num_frames <= 0 || (!d_frame_bgra && !d_frame_ids)) return fail(RTB_ERR_ARG, "fill_frames: bad argument");
+    RTB_CUDA(cudaSetDevice(cam->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : cam->stream;
+    const rtb::CameraBasis& b = cam->basis;
+    const uint32_t bg = ((uint32_t)b.background[3] << 24) | ((uint32_t)b.background[0] << 16) | ((uint32_t)b.background[1] << 8) | b.background[2];
+    const long long count = (long long)num_frames * cam->pixels;
+    const unsigned grid = (unsigned)std::min<long long>((count + 255) / 256, 148ll * 64);
+    if (d_frame_bgra) { rtb::fill_kernel<<<grid, 256, 0, s>>>(d_frame_bgra, count, bg); g_launches++; }
+    if (d_frame_ids) { rtb::fill_ids_kernel<<<grid, 256, 0, s>>>(d_frame_ids, count, -1); g_launches++; }
+    RTB_CUDA(cudaGetLastError());
+    return RTB_OK;
 }
 
 // ---- peer memory: frames other processes' GPUs can write into over NVLink ---------------------------

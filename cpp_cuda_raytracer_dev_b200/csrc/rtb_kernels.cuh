@@ -71,6 +71,7 @@ struct RenderParams {
     // buffers (W*H elements per frame) -- which may be another GPU's memory mapped over NVLink
     uint32_t* push_bgra;
     int32_t* push_ids;
+    int push_skip_background;  // the owner of push_* pre-filled the frames with background / -1: background-only units are not sent
     unsigned long long* work_counter;
     unsigned long long* counters;  // [0] rays [1] interior nodes entered [2] nodes popped (reference sense) [3] triangle tests [4] hits
     float cull_rel;
@@ -243,13 +244,11 @@ __global__ void compose_tiles_kernel(ComposeParts parts, int world, int W, int H
     }
 }
 
-__global__ void fill_kernel(uint32_t* __restrict__ out, long long n, uint32_t value) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = value;
+__global__ void fill_kernel(uint32_t* __restrict__ out, long long n, uint32_t value) {  // grid-stride
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = value;
 }
 __global__ void fill_ids_kernel(int32_t* __restrict__ out, long long n, int32_t value) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = value;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = value;
 }
 
 // ---------------------------------------------------------------------------------------------

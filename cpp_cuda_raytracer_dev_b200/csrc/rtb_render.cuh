@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                     const int wshift = (u_shift + 1) >> 1;  // a unit is a (1 << wshift) x (unit_pixels >> wshift) pixel block
                     const int bx = u_x0 + xoff, by = u_y0 + yoff;
                     if (bx > u_rx1 || bx + (1 << wshift) - 1 < u_rx0 || by > u_ry1 || by + (unit_pixels >> wshift) - 1 < u_ry0) {
+                        if (PUSH && P.push_skip_background) continue;  // the frame's owner has pre-filled it: nothing to send
                         uint32_t* __restrict__ dc = PUSH ? P.push_bgra : P.out_bgra;
                         int32_t* __restrict__ di = PUSH ? P.push_ids : P.out_ids;
                         const bool row_major = PUSH || !P.tile_major;

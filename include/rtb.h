@@ -55,6 +55,7 @@ typedef enum {
 #define RTB_RENDER_DEFAULT 0u
 #define RTB_RENDER_NO_CULL 1u   /* visit exactly the node sequence of Trixel.cu:70-170 (no distance culling) */
 #define RTB_RENDER_COUNTERS 2u  /* accumulate per-launch work counters (rtb_camera_counters) */
+#define RTB_RENDER_PUSH_PREFILLED 8u /* rtb_render_frames_push_async: the owner pre-filled the frames (rtb_fill_frames_device_async): background-only work units are not sent */
 #define RTB_RENDER_TILE_MAJOR 4u /* rtb_render_frames_device_async: compact tile-major output (multi-GPU exchange format) */
 
 const char* rtb_last_error(void);
@@ -211,6 +212,10 @@ int rtb_compose_tiles_device_async(rtb_camera* cam, int32_t num_frames, int32_t 
 int rtb_render_frames_push_async(rtb_object* obj, rtb_camera* cam, int32_t num_frames, const float* m12,
                                  int32_t tile_first, int32_t tile_stride, uint32_t flags, uint32_t* d_frame_bgra,
                                  int32_t* d_frame_ids, void* stream);
+/* set_cam_cuda (Camera.cu:12-18, the SET_COLOR_TAG fill) for `num_frames` device frames at once: background colour into
+ * d_frame_bgra, -1 into d_frame_ids (either may be NULL).  With RTB_RENDER_PUSH_PREFILLED the owner of the final frames
+ * runs this before the ranks push, and work units that contain nothing but background never cross NVLink. */
+int rtb_fill_frames_device_async(rtb_camera* cam, int32_t num_frames, uint32_t* d_frame_bgra, int32_t* d_frame_ids, void* stream);
 /* Frames that other processes' GPUs can write: rtb_peer_alloc = one device allocation on the current device (plays the
  * role of the cudaMalloc of Camera.cpp:78), rtb_peer_export = its 64-byte inter-process handle (send it to the other
  * ranks by any means, e.g. torch.distributed.all_gather_object), rtb_peer_open = map a peer's allocation into this

@@ -363,6 +363,15 @@ def test_push_variant_composes_the_same_frames(gpu, orc, W, H, unit_shift, monke
         assert np.array_equal(got_i, ref_ids.cpu().numpy()), "ids, G=%d" % G
         assert np.array_equal(got_c, ref_col.cpu().numpy()), "colours, G=%d" % G
         assert len(buf_c.handle()) == 64
+        # pre-filled destination: background-only work units are not sent, the frames must still be complete
+        gpu.memcpy_d2h(got_c, buf_c.ptr)  # (synchronises)
+        p.cam.fill_frames_device_async(F, buf_c.ptr, buf_i.ptr, s)
+        for r in range(G):
+            p.obj.render_frames_push_async(p.cam, m, buf_c.ptr, buf_i.ptr, s, tile_first=r, tile_stride=G, flags=gpu.RENDER_PUSH_PREFILLED)
+        gpu.memcpy_d2h(got_c, buf_c.ptr)
+        gpu.memcpy_d2h(got_i, buf_i.ptr)
+        assert np.array_equal(got_i, ref_ids.cpu().numpy()), "prefilled ids, G=%d" % G
+        assert np.array_equal(got_c, ref_col.cpu().numpy()), "prefilled colours, G=%d" % G
         buf_c.close(); buf_i.close()
     p.close()
 
