@@ -44,3 +44,51 @@ def channel_diff(a, b):
 
 def hex32(arr):
     return ["%08x" % v for v in np.ascontiguousarray(arr, np.float32).view(np.uint32).ravel()]
+
+
+# ---- arithmetic edge-case scenes (shared by the CPU oracle-vs-reference test, the golden generator and the GPU test) ----
+AXIS_CAMERA = dict(pos=(0.0, 0.1, -1.0), look_at=(0.0, 0.1, 0.0), up=(0.0, 1.0, 0.0))
+GRID_CAMERA = dict(pos=(0.0, 0.5, -0.5), look_at=(0.0, 0.5, 0.5), up=(0.0, 1.0, 0.0))
+EDGE_FRAMES = [(65, 49), (64, 48), (129, 1), (1, 97)]
+
+
+def axis_aligned_soup():
+    """Axis-aligned quads (zero-thickness boxes on all three axes), stacked copies (ties), slivers and degenerate triangles."""
+    tris = []
+
+    def quad(a, b, c, d):
+        tris.append(a + b + c); tris.append(a + c + d)
+    for z in (0.25, 0.25, 0.5):                       # two coincident walls and one behind them, facing the camera
+        quad([-0.1, 0.0, z], [0.1, 0.0, z], [0.1, 0.2, z], [-0.1, 0.2, z])
+    quad([-0.1, 0.0, 0.0], [-0.1, 0.2, 0.0], [-0.1, 0.2, 0.5], [-0.1, 0.0, 0.5])      # x = const wall (edge-on for the centre column)
+    quad([0.0, 0.0, 0.0], [0.0, 0.2, 0.0], [0.0, 0.2, 0.2], [0.0, 0.0, 0.2])          # x = 0 wall: contains the centre rays' plane
+    quad([-0.1, 0.1, 0.0], [0.1, 0.1, 0.0], [0.1, 0.1, 0.5], [-0.1, 0.1, 0.5])        # y = 0.1 floor: contains the centre row's plane
+    tris.append([0.05, 0.05, 0.1, 0.05, 0.05, 0.1, 0.05, 0.05, 0.1])                  # a point
+    tris.append([0.0, 0.0, 0.1, 0.05, 0.05, 0.1, 0.1, 0.1, 0.1])                      # collinear
+    tris.append([0.02, 0.12, 0.2, 0.02 + 1e-7, 0.12, 0.2, 0.02, 0.12 + 1e-7, 0.2])    # a sliver far below a pixel
+    return np.asarray(tris, np.float32)
+
+
+
+
+def grid_mesh(n=8):
+    """A regular grid of quads on exactly representable coordinates (rays along box planes and triangle edges)."""
+    xs = np.arange(n + 1, dtype=np.float32) / 8 - 0.5
+    tris = []
+    for i in range(n):
+        for j in range(n):
+            a, b = [xs[i], xs[j] + 0.5, 0.5], [xs[i + 1], xs[j] + 0.5, 0.5]
+            c, d = [xs[i + 1], xs[j + 1] + 0.5, 0.5], [xs[i], xs[j + 1] + 0.5, 0.5]
+            tris.append(a + b + c); tris.append(a + c + d)
+    return np.asarray(tris, np.float32)
+
+
+def edge_script():
+    """(select, x, y, z, w) ops applied one by one to the axis-aligned scene, a frame rendered after each."""
+    h = float(np.float32(np.sqrt(0.5)))
+    return [None] + [(10, 0.0, h, 0.0, h)] * 4 + [(32, 0.0, 0.0, 1.0, 0.25)] * 4
+
+
+def golden_edge():
+    with open(os.path.join(GOLDEN_DIR, "golden_edge.json")) as f:
+        return json.load(f)

@@ -6,7 +6,8 @@ Bars (BASELINE.json north star): hit ids bit-exact except documented edge/tie pi
 import numpy as np
 import pytest
 
-from common import WALLS_CAMERA, cam12, cam_kwargs, channel_diff, golden, mesh_path
+from common import (AXIS_CAMERA, EDGE_FRAMES, GRID_CAMERA, WALLS_CAMERA, axis_aligned_soup, cam12, cam_kwargs, channel_diff, edge_script, golden,
+                    golden_edge, grid_mesh, mesh_path)
 
 pytestmark = pytest.mark.gpu
 
@@ -437,3 +438,42 @@ def test_full_size_properties(gpu, nu, W, H):
     #     (a checksum of the frame that does not depend on the oracle): first frame != last frame after a rotation
     assert not np.array_equal(ids_s[0], ids_s[F - 1])
     obj.close(); cam.close(); mesh.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Arithmetic edge cases: rays with exactly zero direction components (1/±0 = ±inf, 0·inf = NaN in the slab test),
+# boxes of zero thickness, degenerate triangles, exact ties, camera on a box plane.  These are the inputs on which
+# the kernel's fp32 shortcuts must hand over to the exact double-precision forms.
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("W,H", EDGE_FRAMES)
+def test_axis_parallel_rays_and_degenerate_geometry(gpu, orc, W, H):
+    pts = axis_aligned_soup()
+    # camera on the z axis looking along +z: with odd W / H the centre column / row has dx == 0 / dy == 0 exactly;
+    # quarter turns put exact zeros and ones into the rotation matrix; the translations slide the camera plane onto
+    # and through box planes.  Every frame is also compared with the hashes recorded from the REFERENCE's own kernels
+    # (tests/golden/golden_edge.json, made by tests/golden/make_golden_edge.py).
+    p = Pair(gpu, orc, pts, W, H, cam=AXIS_CAMERA)
+    want = golden_edge()["axis_%dx%d" % (W, H)]
+    for k, op in enumerate(edge_script()):
+        if op:
+            p.transform(op[0], op[1:])
+        ids, bgra, _, _ = p.check()
+        ids2, bgra2, _, _ = p.check(flags=gpu.RENDER_NO_CULL)
+        assert np.array_equal(ids, ids2) and np.array_equal(bgra, bgra2)
+        assert orc.fnv1a64(ids.astype(np.int64)) == want[k]["id_hash"] and int((ids >= 0).sum()) == want[k]["hits"], (k, op)
+        assert orc.fnv1a64(bgra) == want[k]["colour_hash"], (k, op)
+    p.close()
+
+
+def test_camera_on_axis_planes_of_a_grid_mesh(gpu, orc):
+    """A regular grid of quads whose vertices sit on exactly representable coordinates; the camera looks down an axis
+    from a grid line, so many rays run inside box planes and along triangle edges (u == 0 or v == 0 exactly)."""
+    pts = grid_mesh()
+    for W, H in ((33, 33), (128, 72)):
+        p = Pair(gpu, orc, pts, W, H, cam=GRID_CAMERA)
+        ids, bgra, _, _ = p.check()
+        p.check(flags=gpu.RENDER_NO_CULL)
+        assert (ids >= 0).any()
+        want = golden_edge()["grid_%dx%d" % (W, H)]
+        assert orc.fnv1a64(ids.astype(np.int64)) == want["id_hash"] and orc.fnv1a64(bgra) == want["colour_hash"]
+        p.close()

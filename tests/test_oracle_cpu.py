@@ -170,3 +170,27 @@ def test_oracle_equals_reference_build_when_present(orc, rtb):
         rids, rbgra = ref.render()
         ids, bgra = s.render()
         assert np.array_equal(rids, ids) and np.array_equal(rbgra, bgra)
+
+
+def test_arithmetic_edge_cases_match_reference_golden(orc):
+    """Rays with exactly zero direction components (1/0, 0*inf, 0/0 in the slab test), zero-thickness boxes, coincident
+    and degenerate triangles, quarter-turn rotations, the camera plane sliding through box planes: the restatement
+    against the hashes recorded from the reference's own kernels (tests/golden/make_golden_edge.py)."""
+    from common import AXIS_CAMERA, EDGE_FRAMES, GRID_CAMERA, axis_aligned_soup, edge_script, golden_edge, grid_mesh
+    g = golden_edge()
+    for W, H in EDGE_FRAMES:
+        s = orc.Scene(axis_aligned_soup(), W, H, cam12(W, H, **AXIS_CAMERA))
+        for k, op in enumerate(edge_script()):
+            if op:
+                s.transform(*op)
+            ids, bgra = s.render()
+            want = g["axis_%dx%d" % (W, H)][k]
+            assert int((ids >= 0).sum()) == want["hits"], (W, H, k)
+            assert orc.fnv1a64(ids) == want["id_hash"] and orc.fnv1a64(bgra) == want["colour_hash"], (W, H, k)
+        s.close()
+    for W, H in ((33, 33), (128, 72)):
+        s = orc.Scene(grid_mesh(), W, H, cam12(W, H, **GRID_CAMERA))
+        ids, bgra = s.render()
+        want = g["grid_%dx%d" % (W, H)]
+        assert orc.fnv1a64(ids) == want["id_hash"] and orc.fnv1a64(bgra) == want["colour_hash"]
+        s.close()
