@@ -118,18 +118,9 @@ private:
 inline int Object::render(Camera* c) { return rtb_object_render(handle, c->handle, RTB_RENDER_DEFAULT); }
 
 // Headless replacement of the GDI blit (WinMain.cpp:217): the frame is bottom-up 0x00RRGGBB words.
+// path ending in .png -> PNG, otherwise binary PPM (rtb_write_frame)
 inline bool write_ppm(const std::string& path, const uint32_t* frame, uint32_t w, uint32_t h) {
-    FILE* f = std::fopen(path.c_str(), "wb");
-    if (!f) return false;
-    std::fprintf(f, "P6\n%u %u\n255\n", w, h);
-    std::vector<unsigned char> row(3 * (size_t)w);
-    for (uint32_t y = 0; y < h; y++) {
-        const uint32_t* src = frame + (size_t)(h - 1 - y) * w;
-        for (uint32_t x = 0; x < w; x++) { row[3 * x] = (src[x] >> 16) & 0xff; row[3 * x + 1] = (src[x] >> 8) & 0xff; row[3 * x + 2] = src[x] & 0xff; }
-        std::fwrite(row.data(), 1, row.size(), f);
-    }
-    std::fclose(f);
-    return true;
+    return rtb_write_frame(path.c_str(), frame, (int32_t)w, (int32_t)h) == 0;
 }
 inline bool write_raw_ids(const std::string& path, const int32_t* ids, uint64_t count) {
     FILE* f = std::fopen(path.c_str(), "wb");

@@ -1,7 +1,7 @@
 // rtb_render_main.cpp -- headless Linux driver: the reference's WinMain.cpp:69-237 without the window.
 //
 //   rtb_render --mesh FILE|geodesic:NU [--mode 0|1|2|-1] [--res WxH] [--frames N] [--zoom K]
-//              [--rotate X,Y,Z,W] [--out PREFIX] [--cam px,py,pz,lx,ly,lz,ux,uy,uz] [--sweep]
+//              [--rotate X,Y,Z,W] [--out PREFIX] [--png] [--cam px,py,pz,lx,ly,lz,ux,uy,uz] [--sweep]
 //
 // Same call sequence as the reference app: Camera(...) -> read_ply -> colour table -> Trixel ->
 // set_sorted_voxels -> create_kd -> Object -> add_object -> per frame { [transform]; render;
@@ -24,7 +24,7 @@ static double now_s() { return std::chrono::duration<double>(std::chrono::steady
 int main(int argc, char** argv) {
     std::string mesh = "geodesic:64", out;
     int mode = 0, W = 960, H = 540, frames = 1, zoom = 0;
-    bool sweep = false;
+    bool sweep = false, png = false;
     float quat[4] = {0.0f, 0.09950371902099893f, 0.0f, 0.9950371902099893f};  // WinMain.cpp:187 (R key)
     float cam[9] = {0.0f, 0.10f, -1.0f, 0.0f, 0.10f, 0.0f, 0.0f, 1.0f, 0.0f};  // WinMain.cpp:71-73
     for (int i = 1; i < argc; i++) {
@@ -37,6 +37,7 @@ int main(int argc, char** argv) {
         else if (a == "--zoom") zoom = std::atoi(next());
         else if (a == "--out") out = next();
         else if (a == "--sweep") sweep = true;
+        else if (a == "--png") png = true;
         else if (a == "--rotate") std::sscanf(next(), "%f,%f,%f,%f", &quat[0], &quat[1], &quat[2], &quat[3]);
         else if (a == "--cam") std::sscanf(next(), "%f,%f,%f,%f,%f,%f,%f,%f,%f", &cam[0], &cam[1], &cam[2], &cam[3], &cam[4], &cam[5], &cam[6], &cam[7], &cam[8]);
         else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
@@ -79,7 +80,7 @@ int main(int argc, char** argv) {
         if (out.empty()) return;
         char name[64];
         std::snprintf(name, sizeof name, "_%04d", frame);
-        write_ppm(out + name + ".ppm", c, (uint32_t)W, (uint32_t)H);
+        write_ppm(out + name + (png ? ".png" : ".ppm"), c, (uint32_t)W, (uint32_t)H);
         write_raw_ids(out + name + ".ids", id, (uint64_t)W * H);
     };
 

@@ -3,6 +3,8 @@
 Bars (BASELINE.json north star): hit ids bit-exact except documented edge/tie pixels
 (<= 1e-4 of the pixels; in practice 0 here), colour within 1/255 per channel.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -477,3 +479,124 @@ def test_camera_on_axis_planes_of_a_grid_mesh(gpu, orc):
         want = golden_edge()["grid_%dx%d" % (W, H)]
         assert orc.fnv1a64(ids.astype(np.int64)) == want["id_hash"] and orc.fnv1a64(bgra) == want["colour_hash"]
         p.close()
+
+
+@pytest.mark.parametrize("sweep", [False, True])
+def test_headless_cpp_driver(gpu, orc, tmp_path, sweep):
+    """csrc/rtb_render_main.cpp (the reference's WinMain.cpp:69-237 call sequence in C++ on top of the C ABI, frames
+    written as PPM + raw hit ids): its files against the oracle's frames."""
+    import subprocess
+    from cpp_cuda_raytracer_dev_b200 import build as rtb_build
+    assert os.path.exists(rtb_build.DRIVER), "rtb_render was not built"
+    W, H, F = 320, 180, 3
+    cmd = [rtb_build.DRIVER, "--mesh", "geodesic:24", "--res", "%dx%d" % (W, H), "--frames", str(F), "--out", str(tmp_path / "f")]
+    r = subprocess.run(cmd + (["--sweep"] if sweep else []), capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "primitives: 11520" in r.stdout and "FPS:" in r.stdout
+    ref = orc.Scene(gpu.geodesic_mesh(24), W, H, cam12(W, H))
+    for f in range(F):
+        if f:
+            ref.transform(gpu.ROTATE_TRI_PY, *gpu.R_KEY_QUAT)
+        oids, obgra = ref.render()
+        ids = np.fromfile(tmp_path / ("f_%04d.ids" % f), np.int32)
+        assert np.array_equal(ids.astype(np.int64), oids), "frame %d" % f
+        raw = (tmp_path / ("f_%04d.ppm" % f)).read_bytes()
+        head = ("P6\n%d %d\n255\n" % (W, H)).encode()
+        assert raw.startswith(head)
+        rgb = np.frombuffer(raw[len(head):], np.uint8).reshape(H, W, 3)[::-1].reshape(-1, 3).astype(np.uint32)  # PPM is top-down
+        assert np.array_equal((rgb[:, 0] << 16) | (rgb[:, 1] << 8) | rgb[:, 2], obgra & 0x00ffffff)
+    ref.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Handle lifecycle and misuse through the C ABI: status codes, never a crash (the reference's convention)
+# ---------------------------------------------------------------------------------------------------
+def test_two_cameras_share_one_mesh(gpu, orc):
+    pts = gpu.geodesic_mesh(12)
+    mesh = gpu.Trixel(pts)
+    mesh.create_kd()
+    views = [(320, 180, {}), (200, 150, dict(pos=(0.2, 0.3, -0.8), look_at=(0.0, 0.1, 0.0), up=(0.0, 1.0, 0.1)))]
+    cams, objs = [], []
+    for W, H, kw in views:
+        c = gpu.Camera(W, H, **cam_kwargs(W, H, **kw))
+        o = gpu.Object(mesh)
+        c.add_object(o)
+        cams.append(c); objs.append(o)
+    objs[1].transform(gpu.R_KEY_QUAT, gpu.ROTATE_TRI_PY)   # objects of one mesh move independently
+    for k, (W, H, kw) in enumerate(views):
+        ref = orc.Scene(pts, W, H, cam12(W, H, **kw))
+        if k == 1:
+            ref.transform(gpu.ROTATE_TRI_PY, *gpu.R_KEY_QUAT)
+        ids, bgra = objs[k].render_frame(cams[k])
+        oids, obgra = ref.render()
+        assert np.array_equal(ids.astype(np.int64), oids) and np.array_equal(bgra, obgra)
+        ref.close()
+    # an object rendered with the other camera is refused, not mis-rendered
+    with pytest.raises(gpu.RtbError):
+        objs[0].render(cams[1])
+    for o in objs:
+        o.close()
+    for c in cams:
+        c.close()
+    mesh.close()
+
+
+def test_misuse_returns_status_codes(gpu):
+    pts = gpu.geodesic_mesh(4)
+    mesh = gpu.Trixel(pts)
+    cam = gpu.Camera(64, 48, **cam_kwargs(64, 48))
+    obj = gpu.Object(mesh)
+    with pytest.raises(gpu.RtbError):       # tree not built
+        cam.add_object(obj)
+    mesh.create_kd()
+    with pytest.raises(gpu.RtbError):       # not added to a camera yet
+        obj.render(cam)
+    with pytest.raises(gpu.RtbError):
+        obj.transform(gpu.R_KEY_QUAT, gpu.ROTATE_TRI_PY)
+    cam.add_object(obj)
+    with pytest.raises(gpu.RtbError):       # unknown selector / tag
+        obj.transform(gpu.R_KEY_QUAT, 99)
+    with pytest.raises(gpu.RtbError):
+        cam.color_pixels(7)
+    with pytest.raises(gpu.RtbError):       # nothing to write
+        obj.render_frames_push_async(cam, obj.matrix(), None, None)
+    with pytest.raises(gpu.RtbError):
+        obj.render_frames_device_async(cam, obj.matrix(), None, None, tile_first=3, tile_stride=2)
+    # SET_COLOR_TAG (Camera.cu:12-18): the frame becomes the background colour (240,130,0), ids -1
+    cam.color_pixels(gpu.SET_COLOR_TAG)
+    assert (cam.h_color() == 0x00f08200).all() and (cam.h_ids() == -1).all()
+    obj.render(cam)
+    cam.color_pixels(gpu.PHONG_COLOR_TAG)
+    first = cam.h_ids().copy()
+    assert (first >= 0).any()
+    # rebuilding the tree on the host and re-adding gives the same frame; the camera outlives its object
+    mesh.create_kd(where=1)
+    obj2 = gpu.Object(mesh)
+    cam.add_object(obj2)
+    ids2, _ = obj2.render_frame(cam)
+    assert np.array_equal(ids2, first)
+    ids3, _ = obj.render_frame(cam)         # the first object keeps its own device arrays (the reference overwrites them, Camera.cpp:156,206)
+    assert np.array_equal(ids3, first)
+    obj2.close(); obj.close(); cam.close(); mesh.close()
+
+
+def test_sweep_buffers_pageable_and_pinned_agree(gpu):
+    import torch
+    pts = gpu.geodesic_mesh(10)
+    mesh = gpu.Trixel(pts); mesh.create_kd()
+    W, H, F = 97, 61, 21   # ragged frame, more frames than one copy chunk holds
+    outs = []
+    for pinned in (False, True):
+        cam = gpu.Camera(W, H, **cam_kwargs(W, H)); obj = gpu.Object(mesh); cam.add_object(obj)
+        if pinned:
+            hc = torch.empty((F, W * H), dtype=torch.int32).pin_memory(); hi = torch.empty((F, W * H), dtype=torch.int32).pin_memory()
+            ids, col = obj.render_sweep(cam, gpu.orbit_ops(F), out_color=hc.numpy().view(np.uint32), out_ids=hi.numpy())
+        else:
+            ids, col = obj.render_sweep(cam, gpu.orbit_ops(F))
+        outs.append((ids.copy(), col.copy()))
+        ids_only, none_col = obj.render_sweep(cam, gpu.orbit_ops(2, first_frame_identity=False), want_color=False)
+        assert ids_only.shape == (2, W * H)
+        obj.close(); cam.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert len({outs[0][0][f].tobytes() for f in range(F)}) > F // 2   # the orbit really moves
+    mesh.close()
