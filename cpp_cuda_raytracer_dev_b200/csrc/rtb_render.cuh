@@ -127,6 +127,18 @@ __global__ void selftest_exact_kernel(uint64_t seed, long long count, unsigned l
 // unit -- to its final row-major place in P.push_*, typically rank 0's frame mapped over NVLink.  The transfer
 // therefore overlaps the rendering unit by unit, and there is no gather, no receive buffer and no reassembly pass.
 // A unit belongs to exactly one warp, so the bookkeeping is warp-local (shared-memory counters, __syncwarp).
+// single-pixel stores of retiring rays (4 bytes, scattered over the sectors of an 8x4 pixel block in time)
+// RTB_PIXEL_STORE_MODE: 0 = streaming (st.global.cs), 1 = write-back (plain store), 2 = cache-global (st.global.cg)
+#ifndef RTB_PIXEL_STORE_MODE
+#define RTB_PIXEL_STORE_MODE 0
+#endif
+#if RTB_PIXEL_STORE_MODE == 1
+#define RTB_PIXEL_STORE(ptr, value) (*(ptr) = (value))
+#elif RTB_PIXEL_STORE_MODE == 2
+#define RTB_PIXEL_STORE(ptr, value) __stcg(ptr, value)
+#else
+#define RTB_PIXEL_STORE(ptr, value) __stcs(ptr, value)
+#endif
 #ifndef RTB_MIN_BLOCKS
 #define RTB_MIN_BLOCKS 8
 #endif
@@ -286,8 +298,8 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
             }
             const long long o = (long long)frame * P.frame_stride + pix;
             // frames are write-once streams: keep them from displacing the scene in L2
-            if (P.out_bgra) __stcs(P.out_bgra + o, color);
-            if (P.out_ids) __stcs(P.out_ids + o, id);
+            if (P.out_bgra) RTB_PIXEL_STORE(P.out_bgra + o, color);
+            if (P.out_ids) RTB_PIXEL_STORE(P.out_ids + o, id);
             if (PUSH) atomicSub(&s_owed[wib][my_pslot], 1);
             state = kStateEmpty;
         }
@@ -382,8 +394,8 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                         // outside the (conservatively enlarged) projection of the root box: the ray cannot
                         // pass the root's box test (Trixel.cu:146), the pixel is background
                         const long long o = (long long)u_frame * P.frame_stride + opix;
-                        if (P.out_bgra) __stcs(P.out_bgra + o, P.background);
-                        if (P.out_ids) __stcs(P.out_ids + o, -1);
+                        if (P.out_bgra) RTB_PIXEL_STORE(P.out_bgra + o, P.background);
+                        if (P.out_ids) RTB_PIXEL_STORE(P.out_ids + o, -1);
                         if (COUNT) { c_rays++; c_boxes++; }
                     } else {
                         frame = u_frame;

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import cpp_cuda_raytracer_dev_b200 as rtb
 rtb.set_device(0)
-nu, W, H, F = 209, 960, 540, 60
+nu, W, H, F = 209, 960, 540, int(os.environ.get("RTB_TUNE_FRAMES", "60"))
 pts = rtb.geodesic_mesh(nu); mesh = rtb.Trixel(pts); mesh.create_kd()
 cam = rtb.Camera(W, H, **rtb.default_camera_args(W, H)); obj = rtb.Object(mesh); cam.add_object(obj)
 st = torch.cuda.Stream()
