@@ -275,3 +275,21 @@ def test_tree_cache_round_trip(rtb, tmp_path):
     with pytest.raises(rtb.RtbError):
         b.load_tree(str(tmp_path / "bad.kd"))
     a.close(); b.close(); other.close()
+
+
+def test_bench_reference_arm_contract(tmp_path):
+    """`bench.py --impl reference` (the arm the driver runs beside ours) needs no GPU: one bounded sample of the bunny
+    through the reference's own host-compiled kernels (or the C port), one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    from common import ROOT
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "bunny_960x540", "--steps", "1",
+                        "--warmup", "0", "--ref-frames", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Mrays/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["steps"] == 1 and line["n_gpus"] == 1 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["workload"] == "bunny_960x540"
