@@ -77,6 +77,7 @@ struct rtb_camera {
     size_t push_elements = 0;
     rtb_object* bound = nullptr;
     int sm_count = 0;
+    bool frame_rendered = false;  // the device frame holds a render (background + shaded hits of every pixel)
 };
 
 struct rtb_object {
@@ -604,12 +605,20 @@ int rtb_camera_color_pixels(rtb_camera* cam, uint8_t tag) {
     if (!cam || !cam->d_bgra) return fail(RTB_ERR_CUDA, "color_pixels: camera has no device memory");
     RTB_CUDA(cudaSetDevice(cam->device));
     if (tag == RTB_SET_COLOR_TAG) {
-        const rtb::CameraBasis& b = cam->basis;
-        const uint32_t bg = ((uint32_t)b.background[3] << 24) | ((uint32_t)b.background[0] << 16) | ((uint32_t)b.background[1] << 8) | b.background[2];
-        rtb::fill_kernel<<<(unsigned)((cam->pixels + 255) / 256), 256, 0, cam->stream>>>(cam->d_bgra, cam->pixels, bg);
-        rtb::fill_ids_kernel<<<(unsigned)((cam->pixels + 255) / 256), 256, 0, cam->stream>>>(cam->d_ids, cam->pixels, -1);
-        g_launches += 2;
-        RTB_CUDA(cudaGetLastError());
+        // Camera.cu:77-82: the reference's SET case fills the frame with the background and FALLS THROUGH into the
+        // Phong pass, so what reaches the host is "background + shaded hits of the last render" -- the call exists to
+        // clear pixels that were hit in an earlier frame, because its Phong pass only touches hit pixels.  Here every
+        // render already writes every pixel, so after a render the device frame IS that result; before the first
+        // render there are no hits and the frame is the plain background.
+        if (!cam->frame_rendered) {
+            const rtb::CameraBasis& b = cam->basis;
+            const uint32_t bg = ((uint32_t)b.background[3] << 24) | ((uint32_t)b.background[0] << 16) | ((uint32_t)b.background[1] << 8) | b.background[2];
+            const unsigned grid = (unsigned)std::min<long long>((cam->pixels + 255) / 256, 148ll * 64);
+            rtb::fill_kernel<<<grid, 256, 0, cam->stream>>>(cam->d_bgra, cam->pixels, bg);
+            rtb::fill_ids_kernel<<<grid, 256, 0, cam->stream>>>(cam->d_ids, cam->pixels, -1);
+            g_launches += 2;
+            RTB_CUDA(cudaGetLastError());
+        }
     } else if (tag != RTB_PHONG_COLOR_TAG) {
         return fail(RTB_ERR_ARG, "color_pixels: unknown tag");
     }
@@ -709,6 +718,7 @@ int rtb_object_render(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
     RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * rtb::kFrameStride, cudaMemcpyHostToDevice, cam->stream));
     rc = launch_render(obj, cam, obj->d_frames, 1, 0, 1, flags, cam->d_bgra, cam->d_ids, cam->stream);
     if (rc) return rc;
+    cam->frame_rendered = true;
     // the reference's wrapper synchronises (Trixel.cu:234)
     RTB_CUDA(cudaStreamSynchronize(cam->stream));
     return RTB_OK;
@@ -728,6 +738,7 @@ int rtb_render_frame(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
     RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * rtb::kFrameStride, cudaMemcpyHostToDevice, cam->stream));
     rc = launch_render(obj, cam, obj->d_frames, 1, 0, 1, flags, cam->d_bgra, cam->d_ids, cam->stream);
     if (rc) return rc;
+    cam->frame_rendered = true;
     RTB_CUDA(cudaMemcpyAsync(cam->h_bgra, cam->d_bgra, sizeof(uint32_t) * (size_t)cam->pixels, cudaMemcpyDeviceToHost, cam->stream));
     RTB_CUDA(cudaMemcpyAsync(cam->h_ids, cam->d_ids, sizeof(int32_t) * (size_t)cam->pixels, cudaMemcpyDeviceToHost, cam->stream));
     RTB_CUDA(cudaStreamSynchronize(cam->stream));

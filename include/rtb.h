@@ -131,8 +131,10 @@ int rtb_camera_get_basis(const rtb_camera* cam, float out18[18]);
  * init_camera_voxel_device_memory Camera.cu:163).  Requires rtb_mesh_build_tree. */
 int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj);
 /* Camera::color_pixels(tag) -> color_camera_device (Camera.cpp:229, Camera.cu:70):
- * PHONG: bring the shaded frame of the last render to the host buffer; SET: fill the frame with
- * the background colour (240,130,0) (Camera.cpp:72, Camera.cu:12-18) and copy it. */
+ * PHONG: bring the shaded frame of the last render to the host buffer.  SET: in the reference this case fills the
+ * frame with the background colour (240,130,0) (Camera.cpp:72, Camera.cu:12-18) and FALLS THROUGH into the Phong
+ * pass (Camera.cu:77-82), i.e. the host receives "background + shaded hits of the last render"; same here: the last
+ * rendered frame (every render writes every pixel), or the plain background / ids -1 before the first render. */
 int rtb_camera_color_pixels(rtb_camera* cam, uint8_t color_tag_select);
 /* Camera::h_mem.h_color.c (Camera.cpp:79): W*H little-endian 0x00RRGGBB words, row 0 = bottom.
  * Library-owned pinned memory, valid until the next render / color_pixels on this camera. */

@@ -168,6 +168,40 @@ def build_cuda(force=False):
     return outs
 
 
+def seam_lib_path():
+    return os.path.join(OUT_DIR, "libref_seam.so")
+
+
+def build_seam(force=False):
+    """The drop-in itself: the reference's HOST sources (Camera.cpp, Object.cpp, Quaternion.cpp, Input.cpp, Color.cpp,
+    vector.cpp, read_ply.cpp, Trixel.h -- read in place, same portability patches) compiled WITHOUT its three .cu files;
+    integration/rtb_seam.cpp supplies the seam functions on top of librtb.so.  The host classes' own cudaMalloc /
+    cudaMemcpy calls (dead weight once the seam is in) go to the host shim.  Needs librtb.so."""
+    root = os.path.dirname(HERE)
+    lib_dir = os.path.join(root, "cpp_cuda_raytracer_dev_b200")
+    seam = os.path.join(root, "integration", "rtb_seam.cpp")
+    if not os.path.isdir(REF) or not os.path.exists(os.path.join(lib_dir, "librtb.so")):
+        return None
+    os.makedirs(OUT_DIR, exist_ok=True)
+    host_sources = [n for n in ORDER if not n.endswith(".cu")]
+    out = seam_lib_path()
+    deps = [os.path.join(REF, n) for n in host_sources + ["Vector.h"]] + [os.path.join(HERE, "ref_driver.cpp"), seam, __file__,
+                                                                          os.path.join(root, "include", "rtb.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    unit = ["#define RTB_REF_SEAM 1\n", patched("Vector.h")] + [patched(n) for n in host_sources]
+    for path in (seam, os.path.join(HERE, "ref_driver.cpp")):
+        with open(path) as f:
+            unit.append('#line 1 "%s"\n%s\n' % (path, f.read()))
+    cmd = ["/usr/bin/g++", "-x", "c++", "-", "-std=c++17", "-O2", "-ffp-contract=off", "-fpermissive", "-w", "-fopenmp", "-fPIC", "-shared",
+           "-I", os.path.join(HERE, "shim"), "-I", REF, "-I", os.path.join(root, "include"), "-o", out,
+           "-L", lib_dir, "-lrtb", "-Wl,-rpath,$ORIGIN/../../cpp_cuda_raytracer_dev_b200"]
+    r = subprocess.run(cmd, input="".join(unit).encode(), cwd=OUT_DIR)
+    if r.returncode != 0:
+        raise RuntimeError("reference seam build failed")
+    return out
+
+
 def copy_assets():
     """The reference's two loadable meshes travel to the GPU box as git-ignored build outputs
     (oracle/_ref/data/): they are inputs of the parity tests, not product source."""
@@ -185,3 +219,4 @@ if __name__ == "__main__":
     print(path if path else "reference sources not present at %s; nothing built" % REF)
     for path in build_cuda(force="--force" in sys.argv):
         print(path)
+    print(build_seam(force="--force" in sys.argv))

@@ -22,6 +22,12 @@
 
 thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 #endif
+// Third build, RTB_REF_SEAM (oracle/build_ref.py, build_seam): the reference's HOST classes only, with its three .cu
+// files replaced by integration/rtb_seam.cpp on top of librtb.so -- the drop-in a maintainer would make.
+#ifdef RTB_REF_SEAM
+extern "C" const int* rtb_seam_host_ids(Camera* c);
+extern "C" int rtb_seam_object_matrix(Object* o, float m12[12]);
+#endif
 
 void read_ply(const char* file_name, T_fp** points_list, T_uint* num_tri, kd_leaf_sort** leaf_list,
               kd_vertex** vertex_list, T_uint* num_vert, u8 mode);
@@ -134,6 +140,10 @@ void ref_transform(void* h, int select, float x, float y, float z, float w) {
 
 // 12 floats: rows x,y,z of the object matrix, each (i, j, k, w=translation)  (Quaternion.h:12)
 void ref_get_matrix(void* h, float* m12) {
+#ifdef RTB_REF_SEAM
+    rtb_seam_object_matrix(((RefScene*)h)->obj, m12);  // the recurrence runs inside librtb.so (rtb_object_transform)
+    return;
+#endif
     Quaternion* q = ((RefScene*)h)->obj->quat;
     VEC4<T_fp>* rows[3] = {q->rot_m->x, q->rot_m->y, q->rot_m->z};
     for (int r = 0; r < 3; r++) { m12[4 * r] = rows[r]->i; m12[4 * r + 1] = rows[r]->j; m12[4 * r + 2] = rows[r]->k; m12[4 * r + 3] = rows[r]->w; }
@@ -147,7 +157,11 @@ void ref_render(void* h, long long* ids, unsigned* bgra) {
     s->obj->render(s->cam);
     s->cam->color_pixels(SET_COLOR_TAG);
     const u64 P = s->cam->f_prop.res.count;
+#ifdef RTB_REF_SEAM
+    if (ids) { const int* src = rtb_seam_host_ids(s->cam); for (u64 i = 0; i < P; i++) ids[i] = src[i]; }
+#else
     if (ids) cudaMemcpy(ids, s->cam->h_mem.d_rmi.index, sizeof(long long) * P, cudaMemcpyDeviceToHost);
+#endif
     if (bgra) memcpy(bgra, s->cam->h_mem.h_color.c, sizeof(unsigned) * P);
 }
 
@@ -166,5 +180,10 @@ int ref_is_cuda(void) { return 1; }
 int ref_threads(void) { return omp_get_max_threads(); }
 void ref_set_threads(int n) { omp_set_num_threads(n); }
 int ref_is_cuda(void) { return 0; }
+#endif
+#ifdef RTB_REF_SEAM
+int ref_is_seam(void) { return 1; }
+#else
+int ref_is_seam(void) { return 0; }
 #endif
 }

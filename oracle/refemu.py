@@ -12,7 +12,9 @@ LIB_PATH = os.path.join(HERE, "_ref", "libref_emu.so")
 # The reference's .cu files compiled by nvcc for sm_100a (oracle/build_ref.py, build_cuda): its real kernels on the GPU.
 # "cuda_fmad" = the reference project's own code generation (the kernel to beat), "cuda_nofmad" = contraction off.
 LIB_PATHS = {"emu": LIB_PATH, "cuda_fmad": os.path.join(HERE, "_ref", "libref_cuda_fmad.so"),
-             "cuda_nofmad": os.path.join(HERE, "_ref", "libref_cuda_nofmad.so")}
+             "cuda_nofmad": os.path.join(HERE, "_ref", "libref_cuda_nofmad.so"),
+             # the reference's HOST classes with its .cu files replaced by integration/rtb_seam.cpp over librtb.so
+             "seam": os.path.join(HERE, "_ref", "libref_seam.so")}
 
 # reference selectors (platform_common.h:16-21)
 TRANSLATE_XYZ, TRANSLATE_X, TRANSLATE_Z, ROTATE_TRI_PY, ROTATE_TRI_NY = 30, 31, 32, 10, 11

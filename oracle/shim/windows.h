@@ -12,6 +12,8 @@
 #include <string>
 #include <fstream>
 #include <sstream>
+#include <unordered_map>
+#include <vector>
 typedef void* HWND;
 enum { VK_UP = 0x26, VK_DOWN = 0x28, VK_LEFT = 0x25, VK_RIGHT = 0x27, VK_RETURN = 0x0D, VK_ESCAPE = 0x1B, VK_F1 = 0x70 };
 #ifndef min

@@ -600,3 +600,43 @@ def test_sweep_buffers_pageable_and_pinned_agree(gpu):
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     assert len({outs[0][0][f].tobytes() for f in range(F)}) > F // 2   # the orbit really moves
     mesh.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# The drop-in itself: the reference's OWN host classes (Camera, Trixel, Object, Quaternion, Input, read_ply -- compiled
+# from /root/reference by oracle/build_ref.py, build_seam) with its three .cu files replaced by
+# integration/rtb_seam.cpp on top of librtb.so.  WinMain's call sequence runs through the reference's classes, the
+# frames must be what its own kernels produce.
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["bunny", "walls", "ico24"])
+def test_reference_host_classes_over_librtb(gpu, orc, case):
+    from oracle import refemu
+    if not refemu.available("seam"):
+        pytest.skip("oracle/_ref/libref_seam.so not built (needs /root/reference at build time)")
+    cam, W, H, ply, mode, pts = {}, 960, 540, None, 0, None
+    if case == "bunny":
+        ply, mode = mesh_path("rabbit_70k.ply"), 1
+    elif case == "walls":
+        pts, cam = gpu.read_ply(mesh_path("3_walls.ply"), -1) if mesh_path("3_walls.ply") else None, WALLS_CAMERA
+    else:
+        pts, W, H = gpu.geodesic_mesh(24), 320, 180
+    if ply is None and pts is None:
+        pytest.skip("mesh not shipped")
+    # the reference's loader reads the file itself (read_ply.cpp) when a path is given
+    seam = refemu.RefScene(W, H, cam12(W, H, **cam), ply_path=ply, mode=mode, points9=pts, impl="seam")
+    want_pts = gpu.read_ply(ply, mode) if ply else pts
+    assert np.array_equal(seam.points().view(np.uint32), want_pts.view(np.uint32))
+    ref = orc.Scene(want_pts, W, H, cam12(W, H, **cam))
+    g = golden()
+    for k in range(4):
+        if k:
+            seam.transform(gpu.ROTATE_TRI_PY, *gpu.R_KEY_QUAT)     # Input::set_quat + Object::transform (WinMain.cpp:186-189)
+            ref.transform(gpu.ROTATE_TRI_PY, *gpu.R_KEY_QUAT)
+        assert np.array_equal(seam.matrix().view(np.uint32), ref.matrix().view(np.uint32))
+        ids, bgra = seam.render()                                  # Object::render + Camera::color_pixels (WinMain.cpp:212,237)
+        oids, obgra = ref.render()
+        assert np.array_equal(ids, oids), "frame %d" % k
+        assert np.array_equal(bgra, obgra), "frame %d" % k
+        if case == "bunny":
+            assert orc.fnv1a64(ids) == g["bunny_960x540"]["frames"][k]["id_hash"]   # recorded from the reference's own kernels
+    ref.close()
