@@ -167,21 +167,21 @@ def cpu_reference_run(workload, frames, repeats, prefer_ref=True):
     return frames * W * H, times, kind, cores, sample, mesh_label
 
 
-def gpu_reference_run(workload, frames):
+def gpu_reference_run(workload, frames, impl="cuda_fmad"):
     """The reference's own CUDA kernels (Trixel.cu / Camera.cu compiled by nvcc for sm_100a with the project's default
     code generation, oracle/_ref/libref_cuda_fmad.so) on this GPU, on `frames` consecutive frames of the workload, timed
     the way the reference times itself (wall clock per loop iteration, WinMain.cpp:219-228) but WITHOUT its window blit,
     console output and second color_pixels call -- a lower bound of its per-frame cost: "the kernel to beat" on this box."""
     import cpp_cuda_raytracer_dev_b200 as rtb  # mesh input only
     from oracle import orc, refemu
-    if not refemu.available("cuda_fmad"):
+    if not refemu.available(impl):
         return None
     fname, mode, nu, W, H, fps, zoom = WORKLOADS[workload]
     pts, _ = load_points(rtb, workload)
     if len(pts) > 2_000_000:  # the reference's host-side tree build alone would take minutes (80-byte records x 6 lists)
         return {"skipped": "the reference's own single-threaded tree build is not practical for %d triangles" % len(pts)}
     t0 = time.time()
-    scene = refemu.RefScene(W, H, orc.default_camera(W, H), points9=pts, impl="cuda_fmad")
+    scene = refemu.RefScene(W, H, orc.default_camera(W, H), points9=pts, impl=impl)
     build_s = time.time() - t0
     n = np.array([0.0, 0.0, 1.0], np.float32)
     for _ in range(zoom):
@@ -193,7 +193,9 @@ def gpu_reference_run(workload, frames):
         scene.transform(10, 0.0, 0.09950371902099893, 0.0, 0.9950371902099893)
         per_frame.append(time.perf_counter() - t)
     total = sum(per_frame[3:])
-    return {"value": frames * W * H / total / 1e6, "unit": "Mrays/s", "fps": frames / total, "kind": "reference CUDA kernels, nvcc sm_100a, default fmad",
+    kind = ("reference CUDA kernels, nvcc sm_100a, default fmad" if impl == "cuda_fmad" else
+            "the reference's own host classes with its .cu files replaced by integration/rtb_seam.cpp over librtb.so")
+    return {"value": frames * W * H / total / 1e6, "unit": "Mrays/s", "fps": frames / total, "kind": kind,
             "sample": "%d consecutive orbit frames after 3 warm-up frames, wall clock around Object::render + Camera::color_pixels "
                       "(its host tree build took %.1f s)" % (frames, build_s)}
 
@@ -500,9 +502,10 @@ def run_ours(args):
         rays_c, times_c, kind, cores, sample, _ = cpu_reference_run(args.workload, max(1, args.ref_frames), 2)
         cpu = {"value": rays_c / times_c[-1] / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample}
 
-    ref_gpu = None
+    ref_gpu = ref_seam = None
     if world == 1 and not args.no_cpu_baseline and not args.no_reference_gpu:
         ref_gpu = gpu_reference_run(args.workload, 30 if P <= (1 << 20) else 4)
+        ref_seam = gpu_reference_run(args.workload, 100 if P <= (1 << 20) else 8, impl="seam")
 
     fps = K * world * F / region
     line = {
@@ -519,7 +522,7 @@ def run_ours(args):
                    "fps": fps, "fps_vs_readme_100fps": fps / README_FPS, "tree_build_s": build_s["total"]},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(F * 5 * 4), "d2h_bytes_per_step": int(F * P * 8),
                 "fps": K * world * F / e2e_time, "api": "rtb_render_sweep (host ops in, pinned host colour+id frames out)", "matches_device_run": same},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "frame_loop": frame_loop,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "reference_classes_over_librtb": ref_seam, "frame_loop": frame_loop,
         "kernel_ms": {"mean": float(np.mean(kernel_ms)), "min": float(np.min(kernel_ms)), "max": float(np.max(kernel_ms))},
     }
     print(json.dumps(line))
