@@ -180,9 +180,24 @@ inline unsigned blocks(long long n) { return (unsigned)((n + 255) / 256); }
 }  // namespace
 
 void free_device_tree(DeviceTree& t) {
-    cudaFree(t.bounds); cudaFree(t.left); cudaFree(t.tri); cudaFree(t.cut); cudaFree(t.s1); cudaFree(t.s2); cudaFree(t.rec);
+    cudaFree(t.arena);
     t = DeviceTree();
 }
+
+namespace {
+// bump allocator over one cudaMalloc: the build needs 22 arrays, and 22 cudaMalloc/cudaFree pairs cost more than the
+// kernels of a million-triangle build
+struct Arena {
+    char* base = nullptr;
+    size_t used = 0, size = 0;
+    template <class T> void reserve(size_t count) { size += (sizeof(T) * count + 255) & ~(size_t)255; }
+    template <class T> T* take(size_t count) {
+        T* p = reinterpret_cast<T*>(base + used);
+        used += (sizeof(T) * count + 255) & ~(size_t)255;
+        return p;
+    }
+};
+}  // namespace
 
 std::string download_tree(const DeviceTree& D, HostTree& T) {
     std::string err;
@@ -218,37 +233,45 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, DeviceTree& T) {
     int *lo = nullptr, *hi = nullptr, *parent = nullptr, *left = nullptr, *tri = nullptr, *interior = nullptr, *child_scan = nullptr, *rec = nullptr;
     unsigned char* cut = nullptr;
     void* temp = nullptr;
+    void *keep_base = nullptr, *work_base = nullptr;
     size_t temp_bytes = 0, need = 0;
     Lists L{};
     int level_begin = 0, level_end = 1;
 
-    RTB_BUILD_CUDA(cudaMalloc(&key, sizeof(float) * 6 * (size_t)n));
-    RTB_BUILD_CUDA(cudaMalloc(&ukey_in, sizeof(unsigned) * (size_t)n));
-    RTB_BUILD_CUDA(cudaMalloc(&ukey_out, sizeof(unsigned) * (size_t)n));
-    RTB_BUILD_CUDA(cudaMalloc(&ids_in, sizeof(int) * (size_t)n));
-    RTB_BUILD_CUDA(cudaMalloc(&order, sizeof(int) * 6 * (size_t)n));
-    RTB_BUILD_CUDA(cudaMalloc(&order_tmp, sizeof(int) * (size_t)n));
-    RTB_BUILD_CUDA(cudaMalloc(&rank, sizeof(int) * 6 * (size_t)n));
-    RTB_BUILD_CUDA(cudaMalloc(&node_of_pos, sizeof(int) * (size_t)n));
-    RTB_BUILD_CUDA(cudaMalloc(&flag, sizeof(int) * (size_t)n));
-    RTB_BUILD_CUDA(cudaMalloc(&scan, sizeof(int) * (size_t)n));
-    RTB_BUILD_CUDA(cudaMalloc(&lo, sizeof(int) * (size_t)N));
-    RTB_BUILD_CUDA(cudaMalloc(&hi, sizeof(int) * (size_t)N));
-    RTB_BUILD_CUDA(cudaMalloc(&parent, sizeof(int) * (size_t)N));
-    RTB_BUILD_CUDA(cudaMalloc(&left, sizeof(int) * (size_t)N));
-    RTB_BUILD_CUDA(cudaMalloc(&tri, sizeof(int) * (size_t)N));
-    RTB_BUILD_CUDA(cudaMalloc(&rec, sizeof(int) * (size_t)N));
-    RTB_BUILD_CUDA(cudaMalloc(&interior, sizeof(int) * (size_t)n));
-    RTB_BUILD_CUDA(cudaMalloc(&child_scan, sizeof(int) * (size_t)n));
-    RTB_BUILD_CUDA(cudaMalloc(&cut, (size_t)N));
-    RTB_BUILD_CUDA(cudaMalloc(&bounds, sizeof(float) * 6 * (size_t)N));
-    RTB_BUILD_CUDA(cudaMalloc(&s1, sizeof(float) * (size_t)N));
-    RTB_BUILD_CUDA(cudaMalloc(&s2, sizeof(float) * (size_t)N));
+    // two allocations: the tree itself (kept, DeviceTree::arena) and the work arrays (freed at the end)
+    Arena keep, work;
+    keep.reserve<float>(6 * (size_t)N); keep.reserve<int>((size_t)N); keep.reserve<int>((size_t)N); keep.reserve<int>((size_t)N);
+    keep.reserve<unsigned char>((size_t)N); keep.reserve<float>((size_t)N); keep.reserve<float>((size_t)N);
     cub::DeviceRadixSort::SortPairs(nullptr, need, ukey_in, ukey_out, ids_in, order, n);
     temp_bytes = need;
     cub::DeviceScan::ExclusiveSum(nullptr, need, flag, scan, n);
     temp_bytes = temp_bytes > need ? temp_bytes : need;
-    RTB_BUILD_CUDA(cudaMalloc(&temp, temp_bytes));
+    work.reserve<float>(6 * (size_t)n); work.reserve<unsigned>((size_t)n); work.reserve<unsigned>((size_t)n); work.reserve<int>((size_t)n);
+    work.reserve<int>(6 * (size_t)n); work.reserve<int>((size_t)n); work.reserve<int>(6 * (size_t)n);
+    for (int k = 0; k < 5; k++) work.reserve<int>((size_t)n);  // node_of_pos, flag, scan, interior, child_scan
+    for (int k = 0; k < 3; k++) work.reserve<int>((size_t)N);  // lo, hi, parent
+    work.reserve<char>(temp_bytes);
+    RTB_BUILD_CUDA(cudaMalloc(&keep_base, keep.size));
+    {
+        // The work arrays come from the device's stream-ordered pool, which is told to keep what it is given back:
+        // mapping and unmapping gigabytes costs more than a ten-million-triangle build (measured: up to 0.5 s).
+        int device = 0;
+        cudaMemPool_t pool = nullptr;
+        RTB_BUILD_CUDA(cudaGetDevice(&device));
+        RTB_BUILD_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep_all = ~0ull;
+        RTB_BUILD_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
+        RTB_BUILD_CUDA(cudaMallocAsync(&work_base, work.size, (cudaStream_t)0));
+    }
+    keep.base = (char*)keep_base; work.base = (char*)work_base;
+    bounds = keep.take<float>(6 * (size_t)N); left = keep.take<int>((size_t)N); tri = keep.take<int>((size_t)N); rec = keep.take<int>((size_t)N);
+    cut = keep.take<unsigned char>((size_t)N); s1 = keep.take<float>((size_t)N); s2 = keep.take<float>((size_t)N);
+    key = work.take<float>(6 * (size_t)n); ukey_in = work.take<unsigned>((size_t)n); ukey_out = work.take<unsigned>((size_t)n);
+    ids_in = work.take<int>((size_t)n); order = work.take<int>(6 * (size_t)n); order_tmp = work.take<int>((size_t)n);
+    rank = work.take<int>(6 * (size_t)n); node_of_pos = work.take<int>((size_t)n); flag = work.take<int>((size_t)n); scan = work.take<int>((size_t)n);
+    interior = work.take<int>((size_t)n); child_scan = work.take<int>((size_t)n);
+    lo = work.take<int>((size_t)N); hi = work.take<int>((size_t)N); parent = work.take<int>((size_t)N);
+    temp = work.take<char>(temp_bytes);
 
     // ---- six sorted lists -----------------------------------------------------------------------------
     keys_kernel<<<blocks(n), 256>>>(d_points9, n, key);
@@ -305,14 +328,14 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, DeviceTree& T) {
     RTB_BUILD_CUDA(cudaMemcpy(&T.root_tri, tri, sizeof(int), cudaMemcpyDeviceToHost));
     T.num_tri = n; T.num_nodes = N;
     T.bounds = bounds; T.left = left; T.tri = tri; T.cut = cut; T.s1 = s1; T.s2 = s2; T.rec = rec;
-    bounds = nullptr; left = nullptr; tri = nullptr; cut = nullptr; s1 = nullptr; s2 = nullptr; rec = nullptr;
+    T.arena = keep_base;
+    keep_base = nullptr;
     T.seconds_sort = std::chrono::duration<double>(t_sorted - t_begin).count();
     T.seconds_partition = std::chrono::duration<double>(clock::now() - t_sorted).count();
 
 done:
-    cudaFree(key); cudaFree(ukey_in); cudaFree(ukey_out); cudaFree(ids_in); cudaFree(order); cudaFree(order_tmp); cudaFree(rank);
-    cudaFree(node_of_pos); cudaFree(flag); cudaFree(scan); cudaFree(lo); cudaFree(hi); cudaFree(parent); cudaFree(left); cudaFree(tri);
-    cudaFree(interior); cudaFree(child_scan); cudaFree(cut); cudaFree(rec); cudaFree(bounds); cudaFree(s1); cudaFree(s2); cudaFree(temp);
+    if (work_base) cudaFreeAsync(work_base, (cudaStream_t)0);
+    cudaFree(keep_base);
     if (!err.empty()) cudaGetLastError();
     return err;
 }

@@ -54,6 +54,7 @@ struct DeviceTree {
     float* s1 = nullptr;
     float* s2 = nullptr;
     int* rec = nullptr;
+    void* arena = nullptr;        // the one allocation all seven arrays live in
     float root_bounds[6] = {0, 0, 0, 0, 0, 0};
     int root_tri = -1;
     double seconds_sort = 0, seconds_partition = 0;
