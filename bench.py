@@ -239,6 +239,21 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the ray-cast path has no CPU fallback")
     torch.cuda.set_device(local)
     rtb.set_device(local)
+    numa = None
+    if world > 1:
+        # one process per GPU: run on (and first-touch the pinned frame buffers from) the CPUs next to this GPU, so that
+        # eight ranks' 50 GB/s DMA streams do not all cross the socket interconnect
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            mask_words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local), (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, word in enumerate(mask_words) for b in range(64) if (word >> b) & 1}
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa = "%d CPUs local to GPU %d" % (len(cpus), local)
+        except Exception as exc:  # affinity is an optimisation, never a requirement
+            numa = "not set (%s)" % type(exc).__name__
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -519,7 +534,7 @@ def run_ours(args):
                                    if tiles_mode else "frames x%d (scene replicated, blocks of %d frames per rank, no collective)" % (world, F)) if world > 1 else "single GPU",
                    "l2": "explicit flush (160 MB write) before every step; per-step working set = scene %.0f MB + %.0f MB output" % (
                        (64.0 * (len(pts) - 1) + 48.0 * len(pts)) / 1e6, F * P * 8 / 1e6),
-                   "fps": fps, "fps_vs_readme_100fps": fps / README_FPS, "tree_build_s": build_s["total"]},
+                   "fps": fps, "fps_vs_readme_100fps": fps / README_FPS, "tree_build_s": build_s["total"], "cpu_affinity": numa},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(F * 5 * 4), "d2h_bytes_per_step": int(F * P * 8),
                 "fps": K * world * F / e2e_time, "api": "rtb_render_sweep (host ops in, pinned host colour+id frames out)", "matches_device_run": same},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "reference_classes_over_librtb": ref_seam, "frame_loop": frame_loop,
