@@ -968,6 +968,39 @@ int rtb_selftest_exact(uint64_t seed, int64_t count, uint64_t out4[4]) {
     return RTB_OK;
 }
 
+int rtb_measure_l2_read_bandwidth(size_t bytes, int iters, double* gb_per_s) {
+    if (!gb_per_s || bytes < (1u << 20) || iters < 1) return fail(RTB_ERR_ARG, "measure_l2: bad argument");
+    RTB_CUDA(cudaSetDevice(g_device));
+    cudaDeviceProp prop;
+    RTB_CUDA(cudaGetDeviceProperties(&prop, g_device));
+    const long long n16 = (long long)(bytes / 16);
+    uint4* buf = nullptr;
+    uint4* sink = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = cudaMalloc(&buf, (size_t)n16 * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&sink, 16);
+    if (e == cudaSuccess) e = cudaMemset(buf, 0x5a, (size_t)n16 * 16);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    float ms = 0.0f;
+    if (e == cudaSuccess) {
+        const int grid = prop.multiProcessorCount * 8;
+        rtb::l2_read_kernel<<<grid, 256>>>(buf, n16, 2, sink);  // warm-up: brings the buffer into L2
+        cudaEventRecord(e0);
+        rtb::l2_read_kernel<<<grid, 256>>>(buf, n16, iters, sink);
+        cudaEventRecord(e1);
+        g_launches += 2;
+        e = cudaEventSynchronize(e1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(buf); cudaFree(sink);
+    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, std::string("measure_l2: ") + cudaGetErrorString(e));
+    *gb_per_s = (double)n16 * 16.0 * iters / ((double)ms * 1e-3) / 1e9;
+    return RTB_OK;
+}
+
 uint64_t rtb_launch_count(void) { return g_launches.load(); }
 
 int rtb_device_props(int64_t out7[7]) {

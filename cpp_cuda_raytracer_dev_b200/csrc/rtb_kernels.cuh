@@ -251,6 +251,21 @@ __global__ void fill_ids_kernel(int32_t* __restrict__ out, long long n, int32_t 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = value;
 }
 
+// L2 read-bandwidth probe for the roofline ("L2_BW measured on the box by an L2-resident read
+// microbenchmark"): every thread streams 16-byte loads that bypass L1 (ld.global.cg) over a buffer small enough to
+// stay in L2, `iters` times; the XOR of everything read is stored so that nothing can be optimised away.
+__global__ void l2_read_kernel(const uint4* __restrict__ buf, long long n16, int iters, uint4* __restrict__ sink) {
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (int it = 0; it < iters; it++) {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+            const uint4 v = __ldcg(buf + i);
+            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        }
+    }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9e3779b9u) sink[0] = acc;  // practically never true: keeps the loads alive
+}
+
 // ---------------------------------------------------------------------------------------------
 // the hot kernel
 // ---------------------------------------------------------------------------------------------

@@ -241,6 +241,10 @@ int rtb_object_transform_host(rtb_object* obj, const float xyzw[4], uint8_t tran
  * evaluation on an input it declared decidable, out4[3] = number of decidable samples.  All mismatch counts must be 0. */
 int rtb_selftest_exact(uint64_t seed, int64_t count, uint64_t out4[4]);
 
+/* L2 read bandwidth of the current device for the roofline: `iters` passes of 16-byte L1-bypassing loads over a buffer of
+ * `bytes` (choose it well below the L2 size, e.g. 32 MB) by 8 blocks of 256 threads per SM; result in GB/s. */
+int rtb_measure_l2_read_bandwidth(size_t bytes, int iters, double* gb_per_s);
+
 /* number of kernels this library has launched in this process (render, pack and fill kernels) */
 uint64_t rtb_launch_count(void);
 
