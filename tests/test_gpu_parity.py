@@ -400,6 +400,16 @@ def test_full_size_dragon_standin_against_oracle(gpu, orc):
     p.close()
 
 
+def test_full_size_buddha_standin_4k_against_oracle(gpu, orc):
+    """BASELINE.json configs[3] at its real size: 1 085 780 triangles, 3840x2160, one orbit frame against the oracle."""
+    pts = gpu.geodesic_mesh(233)
+    p = Pair(gpu, orc, pts, 3840, 2160)
+    p.transform(gpu.ROTATE_TRI_PY, gpu.R_KEY_QUAT)
+    ids, _, _, _ = p.check()
+    assert 0.05 * ids.size < (ids >= 0).sum() < 0.07 * ids.size
+    p.close()
+
+
 @pytest.mark.parametrize("nu,W,H", [(233, 3840, 2160), (707, 7680, 4320)])
 def test_full_size_properties(gpu, nu, W, H):
     import torch
