@@ -410,6 +410,17 @@ def test_full_size_buddha_standin_4k_against_oracle(gpu, orc):
     p.close()
 
 
+def test_full_size_synthetic_10m_8k_against_oracle(gpu, orc):
+    """BASELINE.json configs[4] at its real size: 9 996 980 triangles, 7680x4320, one frame against the oracle (its
+    single-threaded tree build takes about half a minute; the GPU build of the same tree 50 ms)."""
+    pts = gpu.geodesic_mesh(707)
+    assert len(pts) == 9996980
+    p = Pair(gpu, orc, pts, 7680, 4320)
+    ids, _, _, _ = p.check()
+    assert 0.05 * ids.size < (ids >= 0).sum() < 0.07 * ids.size
+    p.close()
+
+
 @pytest.mark.parametrize("nu,W,H", [(233, 3840, 2160), (707, 7680, 4320)])
 def test_full_size_properties(gpu, nu, W, H):
     import torch
