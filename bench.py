@@ -286,7 +286,7 @@ def run_ours(args):
     tiles_mode = world > 1 and args.shard == "tiles"
     push_mode = tiles_mode and args.exchange == "push"
     if tiles_mode and not push_mode:  # the NCCL gather runs beside the persistent render kernel: leave it a few SMs
-        os.environ.setdefault("RTB_RESERVE_SMS", "8")
+        rtb.set_knob("reserve_sms", int(os.environ.get("RTB_RESERVE_SMS", "8")))
     FS = F * world if tiles_mode else F  # frames a rank touches per step
 
     def my_mats(step):

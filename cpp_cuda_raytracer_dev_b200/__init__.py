@@ -29,13 +29,13 @@ DEFAULT_RGB = (0.1, 0.55, 0.2)  # WinMain.cpp:118-120
 TILE = 32
 
 EXPORTS = [
-    "rtb_last_error", "rtb_version", "rtb_device_count", "rtb_set_device", "rtb_read_ply", "rtb_free", "rtb_write_ply",
+    "rtb_last_error", "rtb_version", "rtb_device_count", "rtb_set_device", "rtb_set_knob", "rtb_read_ply", "rtb_free", "rtb_write_ply",
     "rtb_mesh_geodesic", "rtb_mesh_create", "rtb_mesh_build_tree", "rtb_mesh_build_tree_on", "rtb_mesh_num_triangles", "rtb_mesh_num_nodes",
     "rtb_mesh_get_tree", "rtb_mesh_save_tree", "rtb_mesh_load_tree", "rtb_write_frame", "rtb_mesh_build_seconds", "rtb_mesh_destroy", "rtb_camera_create", "rtb_camera_get_basis",
     "rtb_camera_add_object", "rtb_camera_color_pixels", "rtb_camera_host_color", "rtb_camera_host_ids",
-    "rtb_camera_counters", "rtb_camera_destroy", "rtb_object_create", "rtb_object_transform", "rtb_object_get_matrix",
+    "rtb_camera_counters", "rtb_camera_counters_ex", "rtb_camera_destroy", "rtb_object_create", "rtb_object_transform", "rtb_object_get_matrix",
     "rtb_object_set_matrix", "rtb_object_destroy", "rtb_object_render", "rtb_render_frame", "rtb_render_sweep",
-    "rtb_render_frames_device_async", "rtb_render_frames_push_async", "rtb_fill_frames_device_async", "rtb_peer_alloc", "rtb_peer_free", "rtb_peer_export", "rtb_peer_open", "rtb_peer_close", "rtb_peer_read", "rtb_object_transform_host", "rtb_device_props", "rtb_launch_count", "rtb_tile_major_elements", "rtb_compose_tiles_device_async", "rtb_selftest_exact", "rtb_measure_l2_read_bandwidth",
+    "rtb_render_frames_device_async", "rtb_render_frames_push_async", "rtb_render_frames_push_striped_async", "rtb_fill_frames_device_async", "rtb_peer_alloc", "rtb_peer_free", "rtb_peer_export", "rtb_peer_open", "rtb_peer_close", "rtb_peer_read", "rtb_object_transform_host", "rtb_transform_sequence_host", "rtb_device_props", "rtb_launch_count", "rtb_tile_major_elements", "rtb_compose_tiles_device_async", "rtb_selftest_exact", "rtb_measure_l2_read_bandwidth",
 ]
 
 
@@ -52,6 +52,7 @@ def _load():
     L.rtb_last_error.restype = C.c_char_p
     L.rtb_version.restype = C.c_char_p
     L.rtb_set_device.argtypes = [ci]
+    L.rtb_set_knob.argtypes = [C.c_char_p, ci]
     L.rtb_read_ply.argtypes = [C.c_char_p, ci, C.POINTER(vp), C.POINTER(C.c_uint32)]
     L.rtb_free.argtypes = [vp]
     L.rtb_free.restype = None
@@ -80,12 +81,14 @@ def _load():
     L.rtb_camera_host_ids.argtypes = [vp]
     L.rtb_camera_host_ids.restype = vp
     L.rtb_camera_counters.argtypes = [vp, vp, ci]
+    L.rtb_camera_counters_ex.argtypes = [vp, vp, ci]
     L.rtb_camera_destroy.argtypes = [vp]
     L.rtb_camera_destroy.restype = None
     L.rtb_object_create.argtypes = [vp, C.POINTER(vp)]
     L.rtb_object_transform.argtypes = [vp, vp, C.c_uint8]
     L.rtb_object_transform_host.argtypes = [vp, vp, C.c_uint8, vp]
     L.rtb_object_get_matrix.argtypes = [vp, vp]
+    L.rtb_transform_sequence_host.argtypes = [vp, C.c_int32, vp, vp]
     L.rtb_object_set_matrix.argtypes = [vp, vp]
     L.rtb_object_destroy.argtypes = [vp]
     L.rtb_object_destroy.restype = None
@@ -97,6 +100,7 @@ def _load():
     L.rtb_launch_count.restype = C.c_uint64
     L.rtb_selftest_exact.argtypes = [C.c_uint64, C.c_int64, vp]
     L.rtb_render_frames_push_async.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_uint32, vp, vp, vp]
+    L.rtb_render_frames_push_striped_async.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_uint32, C.c_int32, vp, vp, vp]
     L.rtb_fill_frames_device_async.argtypes = [vp, C.c_int32, vp, vp, vp]
     L.rtb_measure_l2_read_bandwidth.argtypes = [C.c_size_t, C.c_int, C.POINTER(C.c_double)]
     L.rtb_peer_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -125,6 +129,11 @@ def device_count():
 
 def set_device(i):
     _check(lib.rtb_set_device(i), "rtb_set_device")
+
+
+def set_knob(name, value):
+    """Scheduling knobs of the render kernel (include/rtb.h: rtb_set_knob); process-wide."""
+    _check(lib.rtb_set_knob(name.encode(), int(value)), "rtb_set_knob")
 
 
 def selftest_exact(seed, count):
@@ -282,9 +291,9 @@ class Camera:
                "rtb_compose_tiles_device_async")
 
     def counters(self, reset=True):
-        out = np.zeros(5, np.uint64)
-        _check(lib.rtb_camera_counters(self.h, out.ctypes.data, int(reset)), "rtb_camera_counters")
-        return dict(zip(["rays", "nodes", "boxes", "tris", "hits"], out.tolist()))
+        out = np.zeros(8, np.uint64)
+        _check(lib.rtb_camera_counters_ex(self.h, out.ctypes.data, int(reset)), "rtb_camera_counters_ex")
+        return dict(zip(["rays", "nodes", "boxes", "tris", "hits", "stack_depth_sum", "stack_depth_max"], out.tolist()))
 
     def close(self):
         if self.h:
@@ -368,6 +377,19 @@ class Object:
                                                 frame_bgra_ptr or None, frame_ids_ptr or None, stream_ptr or None),
                "rtb_render_frames_push_async")
 
+    def render_frames_push_striped_async(self, camera, m12, owner_bgra_ptrs, owner_ids_ptrs, stream_ptr=None, tile_first=0, tile_stride=1,
+                                         flags=RENDER_DEFAULT):
+        """Like render_frames_push_async with striped frame ownership: frame f goes to owner f % len(owners) as its frame
+        f // len(owners); owner_*_ptrs are lists of device pointers (one per owner; either list may be None)."""
+        if stream_ptr == 0:
+            stream_ptr = 1  # cudaStreamLegacy
+        m = np.ascontiguousarray(m12, np.float32).reshape(-1, 12)
+        owners = len(owner_bgra_ptrs if owner_bgra_ptrs is not None else owner_ids_ptrs)
+        ac = (C.c_void_p * owners)(*owner_bgra_ptrs) if owner_bgra_ptrs is not None else None
+        ai = (C.c_void_p * owners)(*owner_ids_ptrs) if owner_ids_ptrs is not None else None
+        _check(lib.rtb_render_frames_push_striped_async(self.h, camera.h, m.shape[0], m.ctypes.data, tile_first, tile_stride, flags, owners,
+                                                        ac, ai, stream_ptr or None), "rtb_render_frames_push_striped_async")
+
     def close(self):
         if self.h:
             lib.rtb_object_destroy(self.h)
@@ -421,6 +443,16 @@ def memcpy_d2h(host_array, device_ptr):
 
 def peer_close(ptr):
     _check(lib.rtb_peer_close(ptr), "rtb_peer_close")
+
+
+def transform_sequence(cam_pos, ops):
+    """Matrices of a transform sequence starting from a freshly added object (host only, no GPU): ops (count, 5) ->
+    (count, 12).  rtb_transform_sequence_host."""
+    ops = np.ascontiguousarray(ops, np.float32).reshape(-1, 5)
+    pos = np.asarray(cam_pos, np.float32)
+    out = np.empty((ops.shape[0], 12), np.float32)
+    _check(lib.rtb_transform_sequence_host(pos.ctypes.data, ops.shape[0], ops.ctypes.data, out.ctypes.data), "rtb_transform_sequence_host")
+    return out
 
 
 def orbit_ops(num_frames, quat=R_KEY_QUAT, select=ROTATE_TRI_PY, first_frame_identity=True):

@@ -51,7 +51,29 @@ struct rtb_mesh {
     bool built = false;
     bool built_on_device = false;
     bool host_tree_valid = false;
+    uint64_t generation = 0;  // bumped by every build / load: camera-side arrays made from an older tree are not reused
     double seconds_sort = 0, seconds_partition = 0;
+};
+
+// Camera::voxel_memory + Camera::trixel_memory (Camera.h:64-84) of one (camera, mesh, tree): the camera-relative node
+// and triangle records.  Objects that instance the same mesh on the same camera (WinMain.cpp:152-156 registers two)
+// share one copy -- in the reference the second add_object overwrites the first one's identical arrays (Camera.cpp:156,206).
+struct SceneArrays {
+    const rtb_mesh* mesh = nullptr;  // identity only (never dereferenced after creation)
+    uint64_t generation = 0;
+    int refs = 0;
+    float4* d_scene = nullptr;  // nodes then triangles in ONE allocation
+    float4* d_nodes = nullptr;
+    float4* d_tris = nullptr;
+    float4* d_rad = nullptr;
+    size_t scene_bytes = 0, node_bytes = 0;
+    void* l2_window_base = nullptr;  // persisting access-policy window attached to every render launch (0 bytes = off)
+    size_t l2_window_bytes = 0;
+    float l2_hit_ratio = 0.0f;
+    float root_box[6] = {0, 0, 0, 0, 0, 0};
+    int root_ref = 0;
+    float uniform_rgb[3] = {0, 0, 0};
+    int64_t num_tri = 0;
 };
 
 struct rtb_camera {
@@ -75,33 +97,63 @@ struct rtb_camera {
     uint32_t* push_bgra = nullptr;
     int32_t* push_ids = nullptr;
     size_t push_elements = 0;
-    rtb_object* bound = nullptr;
+    std::vector<SceneArrays*> scenes;   // one per (mesh, tree) in use on this camera
+    std::vector<rtb_object*> objects;   // every object currently added to this camera (Camera::object_list)
     int sm_count = 0;
+    int blocks_per_sm[16] = {0};  // occupancy of the render kernel variants, asked once
     bool frame_rendered = false;  // the device frame holds a render (background + shaded hits of every pixel)
+    bool frame_on_host = false;   // ... and h_bgra / h_ids hold that very frame already
 };
 
 struct rtb_object {
     rtb_mesh* mesh = nullptr;
     rtb_camera* cam = nullptr;
+    int device = 0;
     rtb::Transform xf;
     bool xf_ready = false;
-    // per-(camera, mesh) device arrays: Camera::voxel_memory + Camera::trixel_memory + Trixel::trixel_memory
-    float4* d_scene = nullptr;  // nodes then triangles in ONE allocation (one L2 persisting window)
-    float4* d_nodes = nullptr;
-    float4* d_tris = nullptr;
-    float4* d_rad = nullptr;
-    size_t scene_bytes = 0;
-    size_t l2_window_bytes = 0;  // persisting access-policy window over d_scene (0 = off)
-    float l2_hit_ratio = 0.0f;
-    float root_box[6] = {0, 0, 0, 0, 0, 0};
-    int root_ref = 0;
-    float* d_frames = nullptr;  // matrices of the frames in flight
+    SceneArrays* scene = nullptr;
+    // per-object launch scratch: frame records (matrices + pixel rectangles) of the frames in flight and the work
+    // counter of the persistent kernel.  Launches of one object are ordered on the device through ev_launch, whatever
+    // streams they are issued on; the pinned staging is reused only after ev_upload (the previous upload) has passed.
+    float* d_frames = nullptr;
     float* h_frames = nullptr;  // pinned
     int frames_capacity = 0;
     unsigned long long* d_work = nullptr;
+    unsigned long long work_base = 0;  // value of *d_work once everything issued so far has run
+    cudaEvent_t ev_upload = nullptr, ev_launch = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool upload_pending = false, launch_pending = false;
 };
 
 namespace {
+
+int env_int(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
+// Scheduling knobs of the render kernel (rtb_set_knob).  Initialised once from the environment (RTB_UNIT_SHIFT, ...),
+// so that a launch costs no getenv; tests and the tuning tools change them through rtb_set_knob.
+struct Knobs {
+    int unit_shift = 0;   // log2 pixels per work unit (5..10), 0 = chosen from the launch size
+    int t_active = 12;    // refill when no more than this many lanes still traverse
+    int t_leaf = 8;       // leaf step when at least this many lanes wait at a leaf
+    int tail5 = -1, tail6 = -1;  // trailing frames of a launch in 32- / 64-pixel units, -1 = automatic
+    int reserve_sms = 0;  // SMs left free beside the persistent kernel
+    int l2_window = 1;    // persisting L2 window: 0 off, 1 node records, 2 nodes + triangles (takes effect at add_object)
+    int no_rect = 0;      // 1: frame records carry the whole frame as the root-box rectangle
+};
+Knobs& knobs() {
+    static Knobs k = [] {
+        Knobs v;
+        v.unit_shift = env_int("RTB_UNIT_SHIFT", v.unit_shift); v.t_active = env_int("RTB_T_ACTIVE", v.t_active);
+        v.t_leaf = env_int("RTB_T_LEAF", v.t_leaf); v.tail5 = env_int("RTB_TAIL5", v.tail5); v.tail6 = env_int("RTB_TAIL6", v.tail6);
+        v.reserve_sms = env_int("RTB_RESERVE_SMS", v.reserve_sms); v.l2_window = env_int("RTB_L2_WINDOW", v.l2_window);
+        v.no_rect = env_int("RTB_NO_RECT", v.no_rect);
+        return v;
+    }();
+    return k;
+}
 
 int ensure_host_tree(rtb_mesh* m) {
     if (m->host_tree_valid) return RTB_OK;
@@ -113,8 +165,29 @@ int ensure_host_tree(rtb_mesh* m) {
     return RTB_OK;
 }
 
+// the object's launch scratch exists (work counter, events)
+int ensure_object_scratch(rtb_object* o) {
+    if (!o->d_work) {
+        RTB_CUDA(cudaMalloc(&o->d_work, sizeof(unsigned long long)));
+        RTB_CUDA(cudaMemset(o->d_work, 0, sizeof(unsigned long long)));
+        o->work_base = 0;
+    }
+    if (!o->ev_upload) RTB_CUDA(cudaEventCreateWithFlags(&o->ev_upload, cudaEventDisableTiming));
+    if (!o->ev_launch) RTB_CUDA(cudaEventCreateWithFlags(&o->ev_launch, cudaEventDisableTiming));
+    return RTB_OK;
+}
+
+// Room for `frames` frame records; returns with the pinned staging free to be overwritten.
 int ensure_frames(rtb_object* o, int frames) {
+    if (o->upload_pending) {  // the previous upload still reads h_frames until its event has passed (a few microseconds)
+        RTB_CUDA(cudaEventSynchronize(o->ev_upload));
+        o->upload_pending = false;
+    }
     if (frames <= o->frames_capacity) return RTB_OK;
+    if (o->launch_pending) {  // a kernel in flight may still read the old d_frames
+        RTB_CUDA(cudaEventSynchronize(o->ev_launch));
+        o->launch_pending = false;
+    }
     int cap = std::max(frames, 64);
     if (o->d_frames) cudaFree(o->d_frames);
     if (o->h_frames) cudaFreeHost(o->h_frames);
@@ -125,13 +198,27 @@ int ensure_frames(rtb_object* o, int frames) {
     return RTB_OK;
 }
 
+// Device-side order between launches of one object that arrive on different streams: they share d_frames, the work
+// counter and (push variant) the camera's tile staging.  Same stream: nothing to do.
+int order_after_previous(rtb_object* o, cudaStream_t s) {
+    if (o->launch_pending && o->last_stream != s) RTB_CUDA(cudaStreamWaitEvent(s, o->ev_launch, 0));
+    return RTB_OK;
+}
+
+int upload_frames(rtb_object* o, int num_frames, cudaStream_t s) {
+    RTB_CUDA(cudaMemcpyAsync(o->d_frames, o->h_frames, sizeof(float) * rtb::kFrameStride * (size_t)num_frames, cudaMemcpyHostToDevice, s));
+    RTB_CUDA(cudaEventRecord(o->ev_upload, s));
+    o->upload_pending = true;
+    return RTB_OK;
+}
+
 // One frame record for the kernel: the object's 3x4 matrix followed by the pixel rectangle outside
 // which no primary ray can reach the root box.  The rectangle is the projection of the eight corners
 // of the (camera-relative, translated) root box through the inverse rotation onto the pixel grid,
 // enlarged by 2 pixels -- three orders of magnitude more than the rounding error of the slab test
 // (Trixel.cu:76-95,146) -- so pixels outside it are background exactly as in the reference.  If a
 // corner is not in front of the camera, or the matrix is not invertible, the rectangle is the frame.
-void fill_frame_record(const rtb_object* o, const rtb_camera* c, const float m12[12], float* rec) {
+void fill_frame_record(const SceneArrays* sc, const rtb_camera* c, const float m12[12], float* rec) {
     std::memcpy(rec, m12, sizeof(float) * 12);
     const rtb::CameraBasis& b = c->basis;
     int rect[4] = {0, 0, b.W - 1, b.H - 1};
@@ -141,7 +228,7 @@ void fill_frame_record(const rtb_object* o, const rtb_camera* c, const float m12
     const double det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
                        R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
     const double pw = dotf(b.u_mod, b.u), ph = dotf(b.v_mod, b.v), f = dotf(b.n_mod, b.n);
-    bool ok = std::isfinite(det) && std::fabs(det) > 1e-6 && pw > 0 && ph > 0 && f > 0 && o->root_ref >= 0;
+    bool ok = std::isfinite(det) && std::fabs(det) > 1e-6 && pw > 0 && ph > 0 && f > 0 && sc->root_ref >= 0;
     if (ok) {
         double inv[3][3];
         inv[0][0] = (R[1][1] * R[2][2] - R[1][2] * R[2][1]) / det; inv[0][1] = (R[0][2] * R[2][1] - R[0][1] * R[2][2]) / det; inv[0][2] = (R[0][1] * R[1][2] - R[0][2] * R[1][1]) / det;
@@ -150,9 +237,9 @@ void fill_frame_record(const rtb_object* o, const rtb_camera* c, const float m12
         const double ax = -dotf(b.n_mod, b.u) / pw, ay = -dotf(b.n_mod, b.v) / ph;
         double lo_x = 1e300, hi_x = -1e300, lo_y = 1e300, hi_y = -1e300;
         for (int k = 0; k < 8 && ok; k++) {
-            const double cx = (double)o->root_box[(k & 1) ? 3 : 0] + m12[3];
-            const double cy = (double)o->root_box[(k & 2) ? 4 : 1] + m12[7];
-            const double cz = (double)o->root_box[(k & 4) ? 5 : 2] + m12[11];
+            const double cx = (double)sc->root_box[(k & 1) ? 3 : 0] + m12[3];
+            const double cy = (double)sc->root_box[(k & 2) ? 4 : 1] + m12[7];
+            const double cz = (double)sc->root_box[(k & 4) ? 5 : 2] + m12[11];
             const double p[3] = {inv[0][0] * cx + inv[0][1] * cy + inv[0][2] * cz, inv[1][0] * cx + inv[1][1] * cy + inv[1][2] * cz,
                                  inv[2][0] * cx + inv[2][1] * cy + inv[2][2] * cz};
             const double depth = dot(p, b.n);
@@ -169,27 +256,30 @@ void fill_frame_record(const rtb_object* o, const rtb_camera* c, const float m12
             rect[2] = clampi(std::ceil(hi_x + margin), -1, b.W - 1); rect[3] = clampi(std::ceil(hi_y + margin), -1, b.H - 1);
         }
     }
-    if (std::getenv("RTB_NO_RECT")) { rect[0] = 0; rect[1] = 0; rect[2] = b.W - 1; rect[3] = b.H - 1; }
+    if (knobs().no_rect) { rect[0] = 0; rect[1] = 0; rect[2] = b.W - 1; rect[3] = b.H - 1; }
     std::memcpy(rec + 12, rect, sizeof rect);
 }
 
-// Launch the persistent render kernel over `num_frames` matrices already resident in o->d_frames.
-int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, int num_frames, int tile_first, int tile_stride,
-                  uint32_t flags, uint32_t* d_bgra, int32_t* d_ids, cudaStream_t stream, uint32_t* push_bgra = nullptr,
-                  int32_t* push_ids = nullptr) {
+// Launch the persistent render kernel over `num_frames` frame records: resident in device memory at `d_frames`, or --
+// single frame -- handed over as `inline_record` and carried in the kernel's parameters (no upload, d_frames == nullptr).
+int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, const float* inline_record, int num_frames, int tile_first,
+                  int tile_stride, uint32_t flags, uint32_t* d_bgra, int32_t* d_ids, cudaStream_t stream, int push_owners = 0,
+                  uint32_t* const* push_bgra = nullptr, int32_t* const* push_ids = nullptr) {
     using namespace rtb;
+    const SceneArrays* sc = o->scene;
     RenderParams P;
     std::memset(&P, 0, sizeof P);
     const CameraBasis& b = c->basis;
     P.W = b.W; P.H = b.H;
     for (int k = 0; k < 3; k++) { P.n_mod[k] = b.n_mod[k]; P.u_mod[k] = b.u_mod[k]; P.v_mod[k] = b.v_mod[k]; }
-    for (int k = 0; k < 6; k++) P.root_box[k] = o->root_box[k];
+    for (int k = 0; k < 6; k++) P.root_box[k] = sc->root_box[k];
     P.draw_distance = b.draw_distance;
     P.background = ((uint32_t)b.background[3] << 24) | ((uint32_t)b.background[0] << 16) | ((uint32_t)b.background[1] << 8) | b.background[2];
-    P.root_ref = o->root_ref;
-    P.nodes = o->d_nodes; P.tris = o->d_tris; P.rad = o->d_rad;
-    for (int k = 0; k < 3; k++) P.uniform_rad[k] = o->mesh->uniform_rgb[k];
+    P.root_ref = sc->root_ref;
+    P.nodes = sc->d_nodes; P.tris = sc->d_tris; P.rad = sc->d_rad;
+    for (int k = 0; k < 3; k++) P.uniform_rad[k] = sc->uniform_rgb[k];
     P.frames = d_frames;
+    if (inline_record) std::memcpy(P.frame0, inline_record, sizeof P.frame0);
     P.num_frames = num_frames;
     P.tiles_x = (b.W + kTile - 1) / kTile;
     const int tiles_y = (b.H + kTile - 1) / kTile;
@@ -199,40 +289,54 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, int num_f
     P.my_tiles = tile_first < tiles ? (tiles - tile_first + tile_stride - 1) / tile_stride : 0;
     P.total_items = (long long)num_frames * P.my_tiles;
     P.out_bgra = d_bgra; P.out_ids = d_ids;
-    const bool push = push_bgra || push_ids;
-    P.push_bgra = push_bgra; P.push_ids = push_ids;
+    const bool push = push_owners > 0;
+    P.push_owners = std::max(push_owners, 1);
+    for (int k = 0; k < push_owners; k++) { P.push_bgra[k] = push_bgra ? push_bgra[k] : nullptr; P.push_ids[k] = push_ids ? push_ids[k] : nullptr; }
     P.push_skip_background = (push && (flags & RTB_RENDER_PUSH_PREFILLED)) ? 1 : 0;
     P.tile_major = ((flags & RTB_RENDER_TILE_MAJOR) || push) ? 1 : 0;
     P.frame_stride = P.tile_major ? (long long)((tiles + tile_stride - 1) / tile_stride) * kTile * kTile : (long long)b.W * b.H;
     P.work_counter = o->d_work;
+    P.work_base = o->work_base;
     P.counters = c->d_counters;
     P.cull_rel = 1e-5f;
     if (P.total_items == 0) return RTB_OK;
 
     const bool cull = !(flags & RTB_RENDER_NO_CULL), count = (flags & RTB_RENDER_COUNTERS) != 0;
-    auto env_int = [](const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; };
-    void (*kern)(const RenderParams) = cull ? (count ? render_stream_kernel<true, true, false> : render_stream_kernel<true, false, false>)
-                                            : (count ? render_stream_kernel<false, true, false> : render_stream_kernel<false, false, false>);
-    if (push) kern = cull ? render_stream_kernel<true, false, true> : render_stream_kernel<false, false, true>;
-    int per_sm = 0;
-    RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, 0));
-    per_sm = std::max(per_sm, 1);
+    const bool inl = inline_record != nullptr && !count && !push;
+    if (inline_record && !inl) return fail(RTB_ERR_ARG, "render: inline frame records are for plain single-frame launches");
+    void (*kern)(const RenderParams);
+    int variant;
+    if (push) { kern = cull ? render_stream_kernel<true, false, true> : render_stream_kernel<false, false, true>; variant = 4 + (cull ? 1 : 0); }
+    else if (inl) { kern = cull ? render_stream_kernel<true, false, false, true> : render_stream_kernel<false, false, false, true>; variant = 6 + (cull ? 1 : 0); }
+    else {
+        kern = cull ? (count ? render_stream_kernel<true, true, false> : render_stream_kernel<true, false, false>)
+                    : (count ? render_stream_kernel<false, true, false> : render_stream_kernel<false, false, false>);
+        variant = (cull ? 1 : 0) + (count ? 2 : 0);
+    }
+    if (c->blocks_per_sm[variant] == 0) {
+        int per_sm = 0;
+        RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, 0));
+        c->blocks_per_sm[variant] = std::max(per_sm, 1);
+    }
+    const int per_sm = c->blocks_per_sm[variant];
     const long long warps_total = (long long)c->sm_count * per_sm * (kBlockThreads / 32);
     // work unit: Morton block of 2^shift pixels; small launches get small units so every warp has work
     const long long pixels = (long long)num_frames * P.my_tiles * kTile * kTile;
     int shift = 7;  // measured on the dragon stand-in: 128-pixel units beat 32, 64, 256 and 1024
     while (shift > 5 && (pixels >> shift) < warps_total * 4) shift--;
-    P.unit_shift = std::min(10, std::max(5, env_int("RTB_UNIT_SHIFT", shift)));
-    P.t_active = std::min(31, std::max(0, env_int("RTB_T_ACTIVE", 12)));
-    P.t_leaf = std::max(1, env_int("RTB_T_LEAF", 8));
+    const Knobs& K = knobs();
+    P.unit_shift = std::min(10, std::max(5, K.unit_shift > 0 ? K.unit_shift : shift));
+    P.t_active = std::min(31, std::max(0, K.t_active));
+    P.t_leaf = std::max(1, K.t_leaf);
     // Segments of decreasing unit size towards the end of the launch (see RenderParams::seg_*): a unit handed out late
     // is worked through by ONE warp while the queue is already empty, so late units must be small.  Measured on the
     // dragon stand-in (60 frames): see DESIGN.md.  RTB_TAIL6 / RTB_TAIL5 = number of trailing frames in 64- / 32-pixel units.
     {
         int t5 = 0, t6 = 0;
         if (P.unit_shift > 5 && num_frames >= 8) t5 = std::max(1, num_frames / 20);  // measured: 3 of 60 frames; a 64-pixel segment adds nothing
-        t5 = std::min(num_frames, std::max(0, env_int("RTB_TAIL5", t5)));
-        t6 = std::min(num_frames - t5, std::max(0, env_int("RTB_TAIL6", t6)));
+        const int e5 = K.tail5, e6 = K.tail6;
+        t5 = std::min(num_frames, std::max(0, e5 >= 0 ? e5 : t5));
+        t6 = std::min(num_frames - t5, std::max(0, e6 >= 0 ? e6 : t6));
         P.seg_frames[0] = num_frames - t6 - t5; P.seg_shift[0] = P.unit_shift;
         P.seg_frames[1] = t6;                   P.seg_shift[1] = std::min(P.unit_shift, 6);
         P.seg_frames[2] = t5;                   P.seg_shift[2] = 5;
@@ -250,35 +354,64 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, int num_f
     const long long blocks_needed = (fetches + (kBlockThreads / 32) - 1) / (kBlockThreads / 32);
     // RTB_RESERVE_SMS leaves SMs free for kernels that must run beside this persistent one (the NCCL
     // gather of the multi-GPU tile exchange); the default keeps the whole GPU.
-    const int sms = std::max(1, c->sm_count - std::max(0, env_int("RTB_RESERVE_SMS", 0)));
+    const int sms = std::max(1, c->sm_count - std::max(0, K.reserve_sms));
     const int grid = (int)std::max(1ll, std::min<long long>((long long)sms * per_sm, blocks_needed));
-    RTB_CUDA(cudaMemsetAsync(o->d_work, 0, sizeof(unsigned long long), stream));
-    // per-launch L2 policy: the scene (nodes + triangles) persists, everything else streams.  Set
-    // on the launch so that it also holds on streams the caller owns.
+    // per-launch L2 policy: the scene's node records persist, everything else streams.  Set on the launch so that it
+    // also holds on streams the caller owns.
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kBlockThreads); cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     int nattr = 0;
-    if (o->l2_window_bytes > 0) {
+    if (sc->l2_window_bytes > 0) {
         attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[0].val.accessPolicyWindow.base_ptr = o->d_scene;
-        attr[0].val.accessPolicyWindow.num_bytes = o->l2_window_bytes;
-        attr[0].val.accessPolicyWindow.hitRatio = o->l2_hit_ratio;
+        attr[0].val.accessPolicyWindow.base_ptr = sc->l2_window_base;
+        attr[0].val.accessPolicyWindow.num_bytes = sc->l2_window_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = sc->l2_hit_ratio;
         attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         nattr = 1;
     }
     cfg.attrs = attr; cfg.numAttrs = nattr;
-    RTB_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
+    int rc = order_after_previous(o, stream);
+    if (rc) return rc;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, P);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(RTB_ERR_CUDA, std::string("render launch: ") + cudaGetErrorString(e));
+    }
     g_launches++;
-    RTB_CUDA(cudaGetLastError());
+    // every warp of the grid fetches until its first miss: the counter ends at base + units + warps
+    o->work_base += (unsigned long long)P.total_items + (unsigned long long)grid * (kBlockThreads / 32);
+    RTB_CUDA(cudaEventRecord(o->ev_launch, stream));
+    o->launch_pending = true;
+    o->last_stream = stream;
     return RTB_OK;
+}
+
+void release_scene(rtb_camera* c, SceneArrays* sc) {
+    if (!sc || --sc->refs > 0) return;
+    cudaFree(sc->d_scene);
+    cudaFree(sc->d_rad);
+    c->scenes.erase(std::remove(c->scenes.begin(), c->scenes.end(), sc), c->scenes.end());
+    delete sc;
+}
+
+// the object leaves its camera (Camera::object_list loses it; its share of the camera-side arrays is released)
+void detach_object(rtb_object* o) {
+    rtb_camera* c = o->cam;
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (o->launch_pending) { cudaEventSynchronize(o->ev_launch); o->launch_pending = false; }  // kernels still read the arrays
+    c->objects.erase(std::remove(c->objects.begin(), c->objects.end(), o), c->objects.end());
+    release_scene(c, o->scene);
+    o->scene = nullptr;
+    o->cam = nullptr;
 }
 
 int check_bound(rtb_object* o, rtb_camera* c, const char* who) {
     if (!o || !c) return fail(RTB_ERR_ARG, std::string(who) + ": null handle");
-    if (o->cam != c || !o->d_scene) return fail(RTB_ERR_STATE, std::string(who) + ": object was not added to this camera (rtb_camera_add_object)");
+    if (o->cam != c || !o->scene) return fail(RTB_ERR_STATE, std::string(who) + ": object was not added to this camera (rtb_camera_add_object)");
     return RTB_OK;
 }
 
@@ -297,6 +430,22 @@ int rtb_device_count(void) {
 int rtb_set_device(int device) {
     RTB_CUDA(cudaSetDevice(device));
     g_device = device;
+    return RTB_OK;
+}
+
+int rtb_set_knob(const char* name, int value) {
+    if (!name) return fail(RTB_ERR_ARG, "set_knob: null name");
+    Knobs& k = knobs();
+    const std::string n(name);
+    if (n == "unit_shift") k.unit_shift = value;
+    else if (n == "t_active") k.t_active = value;
+    else if (n == "t_leaf") k.t_leaf = value;
+    else if (n == "tail5") k.tail5 = value;
+    else if (n == "tail6") k.tail6 = value;
+    else if (n == "reserve_sms") k.reserve_sms = value;
+    else if (n == "l2_window") k.l2_window = value;
+    else if (n == "no_rect") k.no_rect = value;
+    else return fail(RTB_ERR_ARG, "set_knob: unknown knob " + n);
     return RTB_OK;
 }
 
@@ -368,7 +517,7 @@ int rtb_mesh_build_tree_on(rtb_mesh* mesh, int where) {
         rtb::free_device_tree(mesh->dtree);
         const std::string err = rtb::build_tree_gpu(mesh->d_points, mesh->n, mesh->dtree);
         if (!err.empty()) return fail(RTB_ERR_CUDA, err);
-        g_launches += 1;
+        g_launches += (uint64_t)mesh->dtree.launches;
         mesh->host_tree_valid = false;
         mesh->seconds_sort = mesh->dtree.seconds_sort; mesh->seconds_partition = mesh->dtree.seconds_partition;
     } else {
@@ -379,6 +528,7 @@ int rtb_mesh_build_tree_on(rtb_mesh* mesh, int where) {
     }
     mesh->built = true;
     mesh->built_on_device = device;
+    mesh->generation++;
     return RTB_OK;
 }
 int rtb_mesh_build_tree(rtb_mesh* mesh) { return rtb_mesh_build_tree_on(mesh, 0); }
@@ -419,6 +569,7 @@ int rtb_mesh_load_tree(rtb_mesh* mesh, const char* file_name) {
     if (mesh->d_points) { cudaSetDevice(mesh->device); rtb::free_device_tree(mesh->dtree); }
     mesh->tree = std::move(T);
     mesh->built = true; mesh->built_on_device = false; mesh->host_tree_valid = true;
+    mesh->generation++;
     mesh->seconds_sort = mesh->seconds_partition = 0.0;
     return RTB_OK;
 }
@@ -485,31 +636,42 @@ int rtb_camera_get_basis(const rtb_camera* cam, float out18[18]) {
     return RTB_OK;
 }
 
-int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj) {
-    if (!cam || !obj) return fail(RTB_ERR_ARG, "add_object: null handle");
-    rtb_mesh* m = obj->mesh;
-    if (!m->built) return fail(RTB_ERR_STATE, "add_object: rtb_mesh_build_tree has not been called");
-    if (!m->d_points || !cam->d_bgra) return fail(RTB_ERR_CUDA, "add_object: mesh or camera has no device memory (no usable GPU)");
-    if (m->device != cam->device) return fail(RTB_ERR_ARG, "add_object: mesh and camera live on different devices");
-    RTB_CUDA(cudaSetDevice(cam->device));
-    // Camera.cpp:131-134: faces = -camera position, identity quaternion
-    obj->xf.reset(cam->basis.pos);
-    obj->xf_ready = true;
-    obj->cam = cam;
-    cam->bound = obj;
+namespace {
+// L2 residency (the 800k-triangle dragon fits the B200's L2).  The persisting window is
+// attached to every render launch (launch_render).  Measured on the dragon stand-in (873 620 triangles, 600-frame
+// launches): a window over nodes + triangles (98 MB against a 79 MB carve-out, hit ratio 0.81) changes nothing
+// (12.95 ms vs 12.89 ms without), a window over the node records alone (56 MB, hit ratio 1) gives 11.9 ms.
+void choose_l2_window(const rtb_camera* cam, SceneArrays* sc) {
+    sc->l2_window_bytes = 0;
+    const int mode = knobs().l2_window;
+    if (mode <= 0) return;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cam->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, cam->device);
+    if (max_persist > 0 && max_window > 0) {
+        const size_t span = mode == 2 ? sc->scene_bytes : sc->node_bytes;
+        size_t limit = 0;
+        cudaDeviceGetLimit(&limit, cudaLimitPersistingL2CacheSize);
+        if (limit >= (size_t)max_persist || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess) {
+            sc->l2_window_base = sc->d_scene;
+            sc->l2_window_bytes = std::min<size_t>(span, (size_t)max_window);
+            sc->l2_hit_ratio = (float)std::min(1.0, (double)max_persist / (double)sc->l2_window_bytes);
+        }
+    }
+    cudaGetLastError();
+}
 
+// The camera-relative device arrays of one mesh for one camera (init_camera_trixel_device_memory Trixel.cu:244 +
+// init_camera_voxel_device_memory Camera.cu:163).  Every temporary is released on every path.
+int make_scene_arrays(rtb_camera* cam, rtb_mesh* m, SceneArrays** out) {
     const bool dev_tree = m->built_on_device;
     const int64_t n = m->n, N = 2 * n - 1, interior = n - 1;
-    dfree(obj->d_scene); dfree(obj->d_rad);
-    obj->d_nodes = obj->d_tris = nullptr;
-    const size_t node_bytes = sizeof(float4) * 4 * (size_t)std::max<int64_t>(interior, 1);
+    SceneArrays* sc = new SceneArrays();
+    sc->mesh = m; sc->generation = m->generation; sc->num_tri = n;
+    std::memcpy(sc->uniform_rgb, m->uniform_rgb, sizeof sc->uniform_rgb);
+    sc->node_bytes = sizeof(float4) * 4 * (size_t)std::max<int64_t>(interior, 1);
     const size_t tri_bytes = sizeof(float4) * 3 * (size_t)n;
-    obj->scene_bytes = node_bytes + tri_bytes;
-    RTB_CUDA(cudaMalloc(&obj->d_scene, obj->scene_bytes));
-    obj->d_nodes = obj->d_scene;
-    obj->d_tris = obj->d_scene + node_bytes / sizeof(float4);
-    if (!obj->d_work) RTB_CUDA(cudaMalloc(&obj->d_work, sizeof(unsigned long long)));
-
+    sc->scene_bytes = sc->node_bytes + tri_bytes;
     // Record index of every interior node.  The tree is numbered breadth-first (Trixel.h:143); the
     // device records are laid out depth-first (pre-order, left child first) so that a descent walks
     // forward through memory: a node and its left child share a 128-byte line, and a subtree is one
@@ -518,9 +680,13 @@ int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj) {
     // (DeviceTree::rec) and never visits the host; a host-built tree is numbered and uploaded here.
     // RTB_NODE_ORDER=bfs keeps the reference numbering (host-built trees only).
     float* d_bounds = nullptr; int* d_left = nullptr; int* d_tri = nullptr; unsigned char* d_cut = nullptr; int* d_rec = nullptr;
-    cudaError_t e = cudaSuccess;
     const float* root_bounds = nullptr;
     int root_tri = -1;
+    cudaError_t e = cudaMalloc(&sc->d_scene, sc->scene_bytes);
+    if (e == cudaSuccess) {
+        sc->d_nodes = sc->d_scene;
+        sc->d_tris = sc->d_scene + sc->node_bytes / sizeof(float4);
+    }
     if (dev_tree) {
         d_bounds = m->dtree.bounds; d_left = m->dtree.left; d_tri = m->dtree.tri; d_cut = m->dtree.cut; d_rec = m->dtree.rec;
         root_bounds = m->dtree.root_bounds; root_tri = m->dtree.root_tri;
@@ -544,7 +710,7 @@ int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj) {
                 stack.push_back(l);
             }
         }
-        e = cudaMalloc(&d_bounds, sizeof(float) * 6 * (size_t)N);
+        if (e == cudaSuccess) e = cudaMalloc(&d_bounds, sizeof(float) * 6 * (size_t)N);
         if (e == cudaSuccess) e = cudaMalloc(&d_left, sizeof(int) * (size_t)N);
         if (e == cudaSuccess) e = cudaMalloc(&d_tri, sizeof(int) * (size_t)N);
         if (e == cudaSuccess) e = cudaMalloc(&d_cut, (size_t)N);
@@ -558,46 +724,67 @@ int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj) {
     }
     const float cx = cam->basis.pos[0], cy = cam->basis.pos[1], cz = cam->basis.pos[2];
     if (e == cudaSuccess) {
-        rtb::pack_triangles_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cam->stream>>>(m->d_points, n, cx, cy, cz, obj->d_tris);
+        rtb::pack_triangles_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cam->stream>>>(m->d_points, n, cx, cy, cz, sc->d_tris);
         if (interior > 0)
-            rtb::pack_nodes_kernel<<<(unsigned)((N + 255) / 256), 256, 0, cam->stream>>>(d_bounds, d_left, d_tri, d_cut, d_rec, N, cx, cy, cz, obj->d_nodes);
+            rtb::pack_nodes_kernel<<<(unsigned)((N + 255) / 256), 256, 0, cam->stream>>>(d_bounds, d_left, d_tri, d_cut, d_rec, N, cx, cy, cz, sc->d_nodes);
         g_launches += interior > 0 ? 2 : 1;
         e = cudaGetLastError();
     }
     if (e == cudaSuccess && !m->rad.empty()) {
         std::vector<float4> rad4((size_t)n);
         for (int64_t i = 0; i < n; i++) rad4[(size_t)i] = make_float4(m->rad[3 * i], m->rad[3 * i + 1], m->rad[3 * i + 2], 0.0f);
-        e = cudaMalloc(&obj->d_rad, sizeof(float4) * (size_t)n);
-        if (e == cudaSuccess) e = cudaMemcpy(obj->d_rad, rad4.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice);
+        e = cudaMalloc(&sc->d_rad, sizeof(float4) * (size_t)n);
+        if (e == cudaSuccess) e = cudaMemcpy(sc->d_rad, rad4.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(cam->stream);
     if (!dev_tree) { cudaFree(d_bounds); cudaFree(d_left); cudaFree(d_tri); cudaFree(d_cut); cudaFree(d_rec); }
-    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, std::string("add_object: ") + cudaGetErrorString(e));
-
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(sc->d_scene); cudaFree(sc->d_rad);
+        delete sc;
+        return fail(RTB_ERR_CUDA, std::string("add_object: ") + cudaGetErrorString(e));
+    }
     // root box, camera-relative (same arithmetic as pack_nodes_kernel; host is compiled without FMA)
     const float* rb = root_bounds;
-    obj->root_box[0] = (rb[0] - cx) + 0.0f; obj->root_box[3] = (rb[1] - cx) + 0.0f;
-    obj->root_box[1] = (rb[2] - cy) + 0.0f; obj->root_box[4] = (rb[3] - cy) + 0.0f;
-    obj->root_box[2] = (rb[4] - cz) + 0.0f; obj->root_box[5] = (rb[5] - cz) + 0.0f;
-    obj->root_ref = n == 1 ? (int)(rtb::kRefLeaf | (unsigned)root_tri) : 0;
+    sc->root_box[0] = (rb[0] - cx) + 0.0f; sc->root_box[3] = (rb[1] - cx) + 0.0f;
+    sc->root_box[1] = (rb[2] - cy) + 0.0f; sc->root_box[4] = (rb[3] - cy) + 0.0f;
+    sc->root_box[2] = (rb[4] - cz) + 0.0f; sc->root_box[5] = (rb[5] - cz) + 0.0f;
+    sc->root_ref = n == 1 ? (int)(rtb::kRefLeaf | (unsigned)root_tri) : 0;
 
-    // pin nodes + triangles in L2 (the 800k-triangle dragon fits).  The
-    // window is attached to every render launch (launch_render).
-    obj->l2_window_bytes = 0;
-    const char* env = std::getenv("RTB_L2_PERSIST");
-    if (!(env && env[0] == '0')) {
-        int max_persist = 0, max_window = 0;
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cam->device);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, cam->device);
-        if (max_persist > 0 && max_window > 0) {
-            const size_t want = std::min<size_t>(obj->scene_bytes, (size_t)max_persist);
-            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
-                obj->l2_window_bytes = std::min<size_t>(obj->scene_bytes, (size_t)max_window);
-                obj->l2_hit_ratio = (float)std::min(1.0, (double)want / (double)obj->l2_window_bytes);
-            }
-            cudaGetLastError();
-        }
+    *out = sc;
+    return RTB_OK;
+}
+}  // namespace
+
+int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj) {
+    if (!cam || !obj) return fail(RTB_ERR_ARG, "add_object: null handle");
+    rtb_mesh* m = obj->mesh;
+    if (!m->built) return fail(RTB_ERR_STATE, "add_object: rtb_mesh_build_tree has not been called");
+    if (!m->d_points || !cam->d_bgra) return fail(RTB_ERR_CUDA, "add_object: mesh or camera has no device memory (no usable GPU)");
+    if (m->device != cam->device) return fail(RTB_ERR_ARG, "add_object: mesh and camera live on different devices");
+    RTB_CUDA(cudaSetDevice(cam->device));
+    // the camera-side arrays of this (mesh, tree): shared with the other objects that instance it on this camera
+    SceneArrays* sc = nullptr;
+    for (SceneArrays* have : cam->scenes)
+        if (have->mesh == m && have->generation == m->generation) sc = have;
+    if (!sc) {
+        const int rc = make_scene_arrays(cam, m, &sc);
+        if (rc) return rc;
+        cam->scenes.push_back(sc);
     }
+    choose_l2_window(cam, sc);
+    sc->refs++;
+    detach_object(obj);  // re-added, or moved over from another camera: leaves the old list, drops the old arrays
+    RTB_CUDA(cudaSetDevice(cam->device));
+    obj->device = cam->device;
+    const int rc = ensure_object_scratch(obj);
+    if (rc) { release_scene(cam, sc); return rc; }
+    obj->scene = sc;
+    obj->cam = cam;
+    cam->objects.push_back(obj);
+    // Camera.cpp:131-134: faces = -camera position, identity quaternion
+    obj->xf.reset(cam->basis.pos);
+    obj->xf_ready = true;
     return RTB_OK;
 }
 
@@ -618,28 +805,36 @@ int rtb_camera_color_pixels(rtb_camera* cam, uint8_t tag) {
             rtb::fill_ids_kernel<<<grid, 256, 0, cam->stream>>>(cam->d_ids, cam->pixels, -1);
             g_launches += 2;
             RTB_CUDA(cudaGetLastError());
+            cam->frame_on_host = false;
         }
     } else if (tag != RTB_PHONG_COLOR_TAG) {
         return fail(RTB_ERR_ARG, "color_pixels: unknown tag");
     }
-    RTB_CUDA(cudaMemcpyAsync(cam->h_bgra, cam->d_bgra, sizeof(uint32_t) * (size_t)cam->pixels, cudaMemcpyDeviceToHost, cam->stream));
-    RTB_CUDA(cudaMemcpyAsync(cam->h_ids, cam->d_ids, sizeof(int32_t) * (size_t)cam->pixels, cudaMemcpyDeviceToHost, cam->stream));
+    if (!cam->frame_on_host) {
+        RTB_CUDA(cudaMemcpyAsync(cam->h_bgra, cam->d_bgra, sizeof(uint32_t) * (size_t)cam->pixels, cudaMemcpyDeviceToHost, cam->stream));
+        RTB_CUDA(cudaMemcpyAsync(cam->h_ids, cam->d_ids, sizeof(int32_t) * (size_t)cam->pixels, cudaMemcpyDeviceToHost, cam->stream));
+    }
+    // the one synchronisation of a frame: the reference's wrappers synchronise after every launch (Trixel.cu:234,
+    // Camera.cu:83), but nothing can observe the frame before this call returns it
     RTB_CUDA(cudaStreamSynchronize(cam->stream));
+    cam->frame_on_host = true;
     return RTB_OK;
 }
 const uint32_t* rtb_camera_host_color(const rtb_camera* cam) { return cam ? cam->h_bgra : nullptr; }
 const int32_t* rtb_camera_host_ids(const rtb_camera* cam) { return cam ? cam->h_ids : nullptr; }
 
-int rtb_camera_counters(rtb_camera* cam, uint64_t out5[5], int reset) {
-    if (!cam || !cam->d_counters || !out5) return fail(RTB_ERR_ARG, "counters: bad argument");
+static int read_counters(rtb_camera* cam, uint64_t* out, int count, int reset) {
+    if (!cam || !cam->d_counters || !out) return fail(RTB_ERR_ARG, "counters: bad argument");
     RTB_CUDA(cudaSetDevice(cam->device));
     unsigned long long h[8];
     RTB_CUDA(cudaStreamSynchronize(cam->stream));
     RTB_CUDA(cudaMemcpy(h, cam->d_counters, sizeof h, cudaMemcpyDeviceToHost));
-    for (int k = 0; k < 5; k++) out5[k] = h[k];
+    for (int k = 0; k < count; k++) out[k] = h[k];
     if (reset) RTB_CUDA(cudaMemset(cam->d_counters, 0, sizeof h));
     return RTB_OK;
 }
+int rtb_camera_counters(rtb_camera* cam, uint64_t out5[5], int reset) { return read_counters(cam, out5, 5, reset); }
+int rtb_camera_counters_ex(rtb_camera* cam, uint64_t out8[8], int reset) { return read_counters(cam, out8, 8, reset); }
 
 void rtb_camera_destroy(rtb_camera* cam) {
     if (!cam) return;
@@ -656,9 +851,11 @@ void rtb_camera_destroy(rtb_camera* cam) {
         if (cam->ev_render[k]) cudaEventDestroy(cam->ev_render[k]);
         if (cam->ev_copy[k]) cudaEventDestroy(cam->ev_copy[k]);
     }
+    // every object still on this camera loses it (and its share of the camera-side arrays) but stays a valid handle
+    while (!cam->objects.empty()) detach_object(cam->objects.back());
+    for (SceneArrays* sc : cam->scenes) { cudaFree(sc->d_scene); cudaFree(sc->d_rad); delete sc; }  // (none left unless refs leaked)
     if (cam->stream) cudaStreamDestroy(cam->stream);
     if (cam->copy_stream) cudaStreamDestroy(cam->copy_stream);
-    if (cam->bound) cam->bound->cam = nullptr;
     delete cam;
 }
 
@@ -684,6 +881,18 @@ int rtb_object_transform(rtb_object* obj, const float xyzw[4], uint8_t select) {
     // replaces the reference's two 1-thread kernels per transform (Quaternion.cu:21, Camera.cu:279,322)
     return rtb_object_transform_host(obj, xyzw, select, nullptr);
 }
+int rtb_transform_sequence_host(const float cam_pos[3], int32_t count, const float* ops5, float* m12_out) {
+    if (!cam_pos || count < 0 || (count > 0 && (!ops5 || !m12_out))) return fail(RTB_ERR_ARG, "transform_sequence: bad argument");
+    rtb::Transform xf;
+    xf.reset(cam_pos);
+    for (int32_t k = 0; k < count; k++) {
+        const float* op = ops5 + 5 * (size_t)k;
+        const int select = (int)op[0];
+        if (select != 0 && !xf.apply((uint8_t)select, op[1], op[2], op[3], op[4])) return fail(RTB_ERR_ARG, "transform_sequence: unknown selector");
+        xf.matrix(m12_out + 12 * (size_t)k);
+    }
+    return RTB_OK;
+}
 int rtb_object_get_matrix(const rtb_object* obj, float m12[12]) {
     if (!obj || !m12 || !obj->xf_ready) return fail(RTB_ERR_STATE, "get_matrix: object was not added to a camera");
     obj->xf.matrix(m12);
@@ -696,53 +905,56 @@ int rtb_object_set_matrix(rtb_object* obj, const float m12[12]) {
 }
 void rtb_object_destroy(rtb_object* obj) {
     if (!obj) return;
-    if (obj->cam) { cudaSetDevice(obj->cam->device); if (obj->cam->bound == obj) obj->cam->bound = nullptr; }
-    dfree(obj->d_scene); dfree(obj->d_rad); dfree(obj->d_frames); dfree(obj->d_work);
+    detach_object(obj);
+    cudaSetDevice(obj->device);
+    if (obj->launch_pending) cudaEventSynchronize(obj->ev_launch);
+    if (obj->upload_pending) cudaEventSynchronize(obj->ev_upload);
+    dfree(obj->d_frames); dfree(obj->d_work);
     if (obj->h_frames) cudaFreeHost(obj->h_frames);
+    if (obj->ev_upload) cudaEventDestroy(obj->ev_upload);
+    if (obj->ev_launch) cudaEventDestroy(obj->ev_launch);
     delete obj;
 }
 
 // ---- render --------------------------------------------------------------------------------------
 
+namespace {
+// One frame of the object's current transform into the camera's device frame, no synchronisation: the record travels
+// in the kernel parameters, the work counter is never reset -- the launch is the only stream operation.
+int render_current(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
+    float m12[12], record[rtb::kFrameStride];
+    obj->xf.matrix(m12);
+    fill_frame_record(obj->scene, cam, m12, record);
+    int rc;
+    if (flags & RTB_RENDER_COUNTERS) {  // the counting variants read their records from device memory
+        rc = ensure_frames(obj, 1);
+        if (rc) return rc;
+        std::memcpy(obj->h_frames, record, sizeof record);
+        rc = order_after_previous(obj, cam->stream);
+        if (!rc) rc = upload_frames(obj, 1, cam->stream);
+        if (!rc) rc = launch_render(obj, cam, obj->d_frames, nullptr, 1, 0, 1, flags, cam->d_bgra, cam->d_ids, cam->stream);
+    } else {
+        rc = launch_render(obj, cam, nullptr, record, 1, 0, 1, flags, cam->d_bgra, cam->d_ids, cam->stream);
+    }
+    if (rc) return rc;
+    cam->frame_rendered = true;
+    cam->frame_on_host = false;
+    return RTB_OK;
+}
+}  // namespace
+
 int rtb_object_render(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
     int rc = check_bound(obj, cam, "render");
     if (rc) return rc;
     RTB_CUDA(cudaSetDevice(cam->device));
-    rc = ensure_frames(obj, 1);
-    if (rc) return rc;
-    {
-        float m12[12];
-        obj->xf.matrix(m12);
-        fill_frame_record(obj, cam, m12, obj->h_frames);
-    }
-    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * rtb::kFrameStride, cudaMemcpyHostToDevice, cam->stream));
-    rc = launch_render(obj, cam, obj->d_frames, 1, 0, 1, flags, cam->d_bgra, cam->d_ids, cam->stream);
-    if (rc) return rc;
-    cam->frame_rendered = true;
-    // the reference's wrapper synchronises (Trixel.cu:234)
-    RTB_CUDA(cudaStreamSynchronize(cam->stream));
-    return RTB_OK;
+    // The reference's wrapper synchronises here (Trixel.cu:234); the frame it waits for cannot be observed before
+    // Camera::color_pixels brings it to the host, which is where this library synchronises -- once per frame.
+    return render_current(obj, cam, flags);
 }
 
 int rtb_render_frame(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
-    int rc = check_bound(obj, cam, "render_frame");
-    if (rc) return rc;
-    RTB_CUDA(cudaSetDevice(cam->device));
-    rc = ensure_frames(obj, 1);
-    if (rc) return rc;
-    {
-        float m12[12];
-        obj->xf.matrix(m12);
-        fill_frame_record(obj, cam, m12, obj->h_frames);
-    }
-    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * rtb::kFrameStride, cudaMemcpyHostToDevice, cam->stream));
-    rc = launch_render(obj, cam, obj->d_frames, 1, 0, 1, flags, cam->d_bgra, cam->d_ids, cam->stream);
-    if (rc) return rc;
-    cam->frame_rendered = true;
-    RTB_CUDA(cudaMemcpyAsync(cam->h_bgra, cam->d_bgra, sizeof(uint32_t) * (size_t)cam->pixels, cudaMemcpyDeviceToHost, cam->stream));
-    RTB_CUDA(cudaMemcpyAsync(cam->h_ids, cam->d_ids, sizeof(int32_t) * (size_t)cam->pixels, cudaMemcpyDeviceToHost, cam->stream));
-    RTB_CUDA(cudaStreamSynchronize(cam->stream));
-    return RTB_OK;
+    const int rc = rtb_object_render(obj, cam, flags);
+    return rc ? rc : rtb_camera_color_pixels(cam, RTB_PHONG_COLOR_TAG);
 }
 
 int rtb_render_frames_device_async(rtb_object* obj, rtb_camera* cam, int32_t num_frames, const float* m12, int32_t tile_first,
@@ -752,38 +964,58 @@ int rtb_render_frames_device_async(rtb_object* obj, rtb_camera* cam, int32_t num
     if (num_frames <= 0 || !m12) return fail(RTB_ERR_ARG, "render_frames_device: bad argument");
     RTB_CUDA(cudaSetDevice(cam->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : cam->stream;
-    // the pinned matrix staging buffer is reused: wait for the previous upload on it
-    RTB_CUDA(cudaStreamSynchronize(s));
-    rc = ensure_frames(obj, num_frames);
+    if (num_frames == 1 && !(flags & RTB_RENDER_COUNTERS)) {
+        float record[rtb::kFrameStride];
+        fill_frame_record(obj->scene, cam, m12, record);
+        return launch_render(obj, cam, nullptr, record, 1, tile_first, tile_stride, flags, d_bgra, d_ids, s);
+    }
+    rc = ensure_frames(obj, num_frames);  // (waits for the previous upload from the pinned staging, never for a kernel)
     if (rc) return rc;
-    for (int f = 0; f < num_frames; f++) fill_frame_record(obj, cam, m12 + 12 * (size_t)f, obj->h_frames + rtb::kFrameStride * (size_t)f);
-    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * rtb::kFrameStride * (size_t)num_frames, cudaMemcpyHostToDevice, s));
-    return launch_render(obj, cam, obj->d_frames, num_frames, tile_first, tile_stride, flags, d_bgra, d_ids, s);
+    for (int f = 0; f < num_frames; f++) fill_frame_record(obj->scene, cam, m12 + 12 * (size_t)f, obj->h_frames + rtb::kFrameStride * (size_t)f);
+    rc = order_after_previous(obj, s);
+    if (!rc) rc = upload_frames(obj, num_frames, s);
+    if (rc) return rc;
+    return launch_render(obj, cam, obj->d_frames, nullptr, num_frames, tile_first, tile_stride, flags, d_bgra, d_ids, s);
 }
 
 int rtb_render_frames_push_async(rtb_object* obj, rtb_camera* cam, int32_t num_frames, const float* m12, int32_t tile_first,
                                  int32_t tile_stride, uint32_t flags, uint32_t* d_frame_bgra, int32_t* d_frame_ids, void* stream) {
+    if (!d_frame_bgra && !d_frame_ids) return fail(RTB_ERR_ARG, "render_frames_push: bad argument");
+    return rtb_render_frames_push_striped_async(obj, cam, num_frames, m12, tile_first, tile_stride, flags, 1, d_frame_bgra ? &d_frame_bgra : nullptr,
+                                                d_frame_ids ? &d_frame_ids : nullptr, stream);
+}
+
+int rtb_render_frames_push_striped_async(rtb_object* obj, rtb_camera* cam, int32_t num_frames, const float* m12, int32_t tile_first,
+                                         int32_t tile_stride, uint32_t flags, int32_t owners, uint32_t* const* d_frame_bgra,
+                                         int32_t* const* d_frame_ids, void* stream) {
     int rc = check_bound(obj, cam, "render_frames_push");
     if (rc) return rc;
-    if (num_frames <= 0 || !m12 || (!d_frame_bgra && !d_frame_ids)) return fail(RTB_ERR_ARG, "render_frames_push: bad argument");
+    if (num_frames <= 0 || !m12 || (!d_frame_bgra && !d_frame_ids) || owners < 1 || owners > rtb::kMaxPushOwners)
+        return fail(RTB_ERR_ARG, "render_frames_push: bad argument");
+    for (int k = 0; k < owners; k++)
+        if ((d_frame_bgra && !d_frame_bgra[k]) || (d_frame_ids && !d_frame_ids[k])) return fail(RTB_ERR_ARG, "render_frames_push: null owner buffer");
     if (flags & RTB_RENDER_COUNTERS) return fail(RTB_ERR_ARG, "render_frames_push: counters are not available in the push variant");
     RTB_CUDA(cudaSetDevice(cam->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : cam->stream;
-    RTB_CUDA(cudaStreamSynchronize(s));  // the pinned matrix staging buffer and the tile staging are reused
     rc = ensure_frames(obj, num_frames);
     if (rc) return rc;
     const size_t need = (size_t)num_frames * (size_t)rtb_tile_major_elements(cam, tile_stride);
     if (cam->push_elements < need) {
+        // the tile staging grows: kernels of any object of this camera that still stage into the old one must finish
+        for (rtb_object* other : cam->objects)
+            if (other->launch_pending) { RTB_CUDA(cudaEventSynchronize(other->ev_launch)); other->launch_pending = false; }
         dfree(cam->push_bgra); dfree(cam->push_ids);
         cam->push_elements = 0;
         RTB_CUDA(cudaMalloc(&cam->push_bgra, 4 * need));
         RTB_CUDA(cudaMalloc(&cam->push_ids, 4 * need));
         cam->push_elements = need;
     }
-    for (int f = 0; f < num_frames; f++) fill_frame_record(obj, cam, m12 + 12 * (size_t)f, obj->h_frames + rtb::kFrameStride * (size_t)f);
-    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * rtb::kFrameStride * (size_t)num_frames, cudaMemcpyHostToDevice, s));
-    return launch_render(obj, cam, obj->d_frames, num_frames, tile_first, tile_stride, flags, d_frame_bgra ? cam->push_bgra : nullptr,
-                         d_frame_ids ? cam->push_ids : nullptr, s, d_frame_bgra, d_frame_ids);
+    for (int f = 0; f < num_frames; f++) fill_frame_record(obj->scene, cam, m12 + 12 * (size_t)f, obj->h_frames + rtb::kFrameStride * (size_t)f);
+    rc = order_after_previous(obj, s);
+    if (!rc) rc = upload_frames(obj, num_frames, s);
+    if (rc) return rc;
+    return launch_render(obj, cam, obj->d_frames, nullptr, num_frames, tile_first, tile_stride, flags, d_frame_bgra ? cam->push_bgra : nullptr,
+                         d_frame_ids ? cam->push_ids : nullptr, s, owners, d_frame_bgra, d_frame_ids);
 }
 
 int rtb_fill_frames_device_async(rtb_camera* cam, int32_t num_frames, uint32_t* d_frame_bgra, int32_t* d_frame_ids, void* stream) {
@@ -848,6 +1080,8 @@ int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32
     RTB_CUDA(cudaStreamSynchronize(cam->stream));
     rc = ensure_frames(obj, num_frames);
     if (rc) return rc;
+    rc = order_after_previous(obj, cam->stream);
+    if (rc) return rc;
     // host recurrence for every frame (Camera.cu:254-335), exactly as if the calls were made one by one
     for (int f = 0; f < num_frames; f++) {
         for (int s = 0; s < steps_per_frame; s++) {
@@ -858,9 +1092,10 @@ int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32
         }
         float m12[12];
         obj->xf.matrix(m12);
-        fill_frame_record(obj, cam, m12, obj->h_frames + rtb::kFrameStride * (size_t)f);
+        fill_frame_record(obj->scene, cam, m12, obj->h_frames + rtb::kFrameStride * (size_t)f);
     }
-    RTB_CUDA(cudaMemcpyAsync(obj->d_frames, obj->h_frames, sizeof(float) * rtb::kFrameStride * (size_t)num_frames, cudaMemcpyHostToDevice, cam->stream));
+    rc = upload_frames(obj, num_frames, cam->stream);
+    if (rc) return rc;
 
     // ring of two device chunks; chunk k+1 renders while chunk k streams to the host
     const size_t P = (size_t)cam->pixels;
@@ -905,7 +1140,7 @@ int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32
             if (rc) return rc;
             RTB_CUDA(cudaStreamWaitEvent(cam->stream, cam->ev_copy[slot], 0));
         }
-        rc = launch_render(obj, cam, obj->d_frames + rtb::kFrameStride * (size_t)f0, nf, 0, 1, flags, bgra_out ? cam->ring_bgra[slot] : nullptr,
+        rc = launch_render(obj, cam, obj->d_frames + rtb::kFrameStride * (size_t)f0, nullptr, nf, 0, 1, flags, bgra_out ? cam->ring_bgra[slot] : nullptr,
                            ids_out ? cam->ring_ids[slot] : nullptr, cam->stream);
         if (rc) return rc;
         RTB_CUDA(cudaEventRecord(cam->ev_render[slot], cam->stream));

@@ -237,6 +237,7 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, DeviceTree& T) {
     size_t temp_bytes = 0, need = 0;
     Lists L{};
     int level_begin = 0, level_end = 1;
+    int launches = 0;
 
     // two allocations: the tree itself (kept, DeviceTree::arena) and the work arrays (freed at the end)
     Arena keep, work;
@@ -274,12 +275,12 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, DeviceTree& T) {
     temp = work.take<char>(temp_bytes);
 
     // ---- six sorted lists -----------------------------------------------------------------------------
-    keys_kernel<<<blocks(n), 256>>>(d_points9, n, key);
+    keys_kernel<<<blocks(n), 256>>>(d_points9, n, key); launches++;
     for (int k = 0; k < 6; k++) {
-        sort_input_kernel<<<blocks(n), 256>>>(key + (size_t)k * n, n, ukey_in, ids_in);
+        sort_input_kernel<<<blocks(n), 256>>>(key + (size_t)k * n, n, ukey_in, ids_in); launches++;
         size_t tb = temp_bytes;
-        RTB_BUILD_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, ukey_in, ukey_out, ids_in, order + (size_t)k * n, n));
-        rank_kernel<<<blocks(n), 256>>>(order + (size_t)k * n, n, rank + (size_t)k * n);
+        RTB_BUILD_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, ukey_in, ukey_out, ids_in, order + (size_t)k * n, n)); launches += 5;  // histogram + four onesweep passes
+        rank_kernel<<<blocks(n), 256>>>(order + (size_t)k * n, n, rank + (size_t)k * n); launches++;
     }
     RTB_BUILD_CUDA(cudaDeviceSynchronize());
     t_sorted = clock::now();
@@ -295,31 +296,31 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, DeviceTree& T) {
         const int root_rec = n > 1 ? 0 : -1;
         RTB_BUILD_CUDA(cudaMemcpy(rec, &root_rec, sizeof(int), cudaMemcpyHostToDevice));
     }
-    root_bounds_kernel<<<1, 1>>>(L, bounds);
+    root_bounds_kernel<<<1, 1>>>(L, bounds); launches++;
     while (level_begin < level_end) {
         const int count = level_end - level_begin;
-        level_nodes_kernel<<<blocks(count), 256>>>(L, level_begin, count, lo, hi, parent, cut, tri, interior);
+        level_nodes_kernel<<<blocks(count), 256>>>(L, level_begin, count, lo, hi, parent, cut, tri, interior); launches++;
         size_t tb = temp_bytes;
-        RTB_BUILD_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, interior, child_scan, count));
+        RTB_BUILD_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, interior, child_scan, count)); launches += 2;
         int last_flag = 0, last_scan = 0;
         RTB_BUILD_CUDA(cudaMemcpy(&last_flag, interior + (count - 1), sizeof(int), cudaMemcpyDeviceToHost));
         RTB_BUILD_CUDA(cudaMemcpy(&last_scan, child_scan + (count - 1), sizeof(int), cudaMemcpyDeviceToHost));
         const int num_interior = last_flag + last_scan;
         if (num_interior > 0) {
             for (int k = 0; k < 6; k++) {
-                flags_kernel<<<blocks(n), 256>>>(L, k, node_of_pos, lo, hi, cut, flag);
+                flags_kernel<<<blocks(n), 256>>>(L, k, node_of_pos, lo, hi, cut, flag); launches++;
                 tb = temp_bytes;
-                RTB_BUILD_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, flag, scan, n));
-                scatter_kernel<<<blocks(n), 256>>>(L, k, node_of_pos, lo, hi, cut, flag, scan, order_tmp);
+                RTB_BUILD_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, flag, scan, n)); launches += 2;
+                scatter_kernel<<<blocks(n), 256>>>(L, k, node_of_pos, lo, hi, cut, flag, scan, order_tmp); launches++;
                 RTB_BUILD_CUDA(cudaMemcpyAsync(order + (size_t)k * n, order_tmp, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice));
             }
         }
-        children_kernel<<<blocks(count), 256>>>(L, level_begin, count, level_end, child_scan, lo, hi, parent, left, bounds, rec);
-        reassign_kernel<<<blocks(n), 256>>>(n, node_of_pos, lo, hi, left);
+        children_kernel<<<blocks(count), 256>>>(L, level_begin, count, level_end, child_scan, lo, hi, parent, left, bounds, rec); launches++;
+        reassign_kernel<<<blocks(n), 256>>>(n, node_of_pos, lo, hi, left); launches++;
         level_begin = level_end;
         level_end += 2 * num_interior;
     }
-    split_planes_kernel<<<blocks(N), 256>>>(N, left, cut, bounds, s1, s2);
+    split_planes_kernel<<<blocks(N), 256>>>(N, left, cut, bounds, s1, s2); launches++;
     RTB_BUILD_CUDA(cudaDeviceSynchronize());
     if (level_end != N) { err = "build_tree_gpu: node count mismatch"; goto done; }
 
@@ -332,6 +333,7 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, DeviceTree& T) {
     keep_base = nullptr;
     T.seconds_sort = std::chrono::duration<double>(t_sorted - t_begin).count();
     T.seconds_partition = std::chrono::duration<double>(clock::now() - t_sorted).count();
+    T.launches = launches;
 
 done:
     if (work_base) cudaFreeAsync(work_base, (cudaStream_t)0);

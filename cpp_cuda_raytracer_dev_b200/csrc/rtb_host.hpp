@@ -58,6 +58,7 @@ struct DeviceTree {
     float root_bounds[6] = {0, 0, 0, 0, 0, 0};
     int root_tri = -1;
     double seconds_sort = 0, seconds_partition = 0;
+    int launches = 0;             // kernels the build launched (counted into rtb_launch_count)
 };
 // all three return the error text or ""
 std::string build_tree_gpu(const float* d_points9, int64_t num_tri, DeviceTree& out);

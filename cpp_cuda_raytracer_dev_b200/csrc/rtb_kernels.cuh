@@ -34,6 +34,7 @@ constexpr int kStackDepth = 40;  // >= tree height + 2 (median split: height = c
 constexpr int kBlockThreads = 128;
 constexpr int kFrameStride = 16;
 constexpr int kPushSlots = 8;    // work units a warp may have open at once in the peer-push variant
+constexpr int kMaxPushOwners = 8;  // GPUs that may own final frames of one pushed launch (one NVSwitch domain)
 constexpr unsigned kRefLeaf = 0x80000000u, kRefIndexMask = 0x1fffffffu;
 constexpr int kRefAxisShift = 29;
 
@@ -50,6 +51,8 @@ struct RenderParams {
     float uniform_rad[3];
     const float* __restrict__ frames;  // kFrameStride floats per frame: rows x,y,z = (i,j,k,w), then the pixel rectangle
                                        // x0,y0,x1,y1 (int bits, inclusive) outside which no ray can reach the root box
+    float frame0[kFrameStride];        // render_stream_kernel<.., INLINE = true>: the record of a single-frame launch travels
+                                       // with the kernel parameters (constant bank) instead of through device memory
     int num_frames;
     int tiles_x;           // tiles per image row
     int tile_first, tile_stride;
@@ -69,11 +72,16 @@ struct RenderParams {
     // peer push (render_stream_kernel<.., PUSH = true>): out_* is this GPU's tile-major staging, and every finished
     // work unit is copied by its warp, as 16-byte row segments, to its final row-major place in these full-frame
     // buffers (W*H elements per frame) -- which may be another GPU's memory mapped over NVLink
-    uint32_t* push_bgra;
-    int32_t* push_ids;
+    // frame f of the launch belongs to owner f % push_owners and is frame f / push_owners of that owner's buffers (striped
+    // ownership: every GPU's NVLink ingest and HBM take 1/N of the finished frames; one owner = everything to one GPU)
+    uint32_t* push_bgra[kMaxPushOwners];
+    int32_t* push_ids[kMaxPushOwners];
+    int push_owners;
     int push_skip_background;  // the owner of push_* pre-filled the frames with background / -1: background-only units are not sent
-    unsigned long long* work_counter;
+    unsigned long long* work_counter;  // never reset: a launch hands out units work_base, work_base + 1, ... and every warp
+    unsigned long long work_base;      // overshoots exactly once, so the host knows the counter's value after the launch
     unsigned long long* counters;  // [0] rays [1] interior nodes entered [2] nodes popped (reference sense) [3] triangle tests [4] hits
+                                   // [5] sum over traced rays of their deepest stack (entries incl. the register top) [6] deepest stack of any ray
     float cull_rel;
 };
 
@@ -271,6 +279,12 @@ __global__ void l2_read_kernel(const uint4* __restrict__ buf, long long n16, int
 // ---------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+// the same read-only 16-byte load carrying an L2 eviction policy made by createpolicy (evict_last: scene records)
+__device__ __forceinline__ float4 ldg4_keep(const float4* p, unsigned long long policy) {
+    float4 v;
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy));
+    return v;
+}
 
 // Moller-Trumbore, Trixel.cu:98-145.  Returns true and updates best/id on acceptance.
 __device__ __forceinline__ bool moller_trumbore(const Ray& r, const float4* __restrict__ tris, int tri, float& best, int& id) {
@@ -299,8 +313,9 @@ __device__ __forceinline__ bool moller_trumbore(const Ray& r, const float4* __re
 }
 
 // Camera.cu:19-69 color_cam_cuda for a hit pixel; returns 0x00RRGGBB.
-__device__ __forceinline__ uint32_t phong(const RenderParams& P, const float* __restrict__ M, const Ray& r, float best, int id,
-                                          float cmx, float cmy, float cmz) {
+// M = the rotation part of the object's matrix: rows (m0 m1 m2), (m4 m5 m6), (m8 m9 m10)
+__device__ __forceinline__ uint32_t phong(const RenderParams& P, float m0, float m1, float m2, float m4, float m5, float m6, float m8, float m9,
+                                          float m10, const Ray& r, float best, int id, float cmx, float cmy, float cmz) {
     // hit record as written at Trixel.cu:134-140
     const float pntx = __fadd_rn(__fmul_rn(best, r.dx), r.ox);
     const float pnty = __fadd_rn(__fmul_rn(best, r.dy), r.oy);
@@ -308,9 +323,9 @@ __device__ __forceinline__ uint32_t phong(const RenderParams& P, const float* __
     const float n0 = ldg4(P.tris + 3ll * id).w, n1 = ldg4(P.tris + 3ll * id + 1).w, n2 = ldg4(P.tris + 3ll * id + 2).w;
     // VEC3_CUDA::device_rotate(rot_m, i, -1), vector.cuh:25-33
     const float ax = __fmul_rn(-1.0f, n0), ay = __fmul_rn(-1.0f, n1), az = __fmul_rn(-1.0f, n2);
-    float nx = __fadd_rn(__fadd_rn(__fmul_rn(ax, M[0]), __fmul_rn(ay, M[1])), __fmul_rn(az, M[2]));
-    float ny = __fadd_rn(__fadd_rn(__fmul_rn(ax, M[4]), __fmul_rn(ay, M[5])), __fmul_rn(az, M[6]));
-    float nz = __fadd_rn(__fadd_rn(__fmul_rn(ax, M[8]), __fmul_rn(ay, M[9])), __fmul_rn(az, M[10]));
+    float nx = __fadd_rn(__fadd_rn(__fmul_rn(ax, m0), __fmul_rn(ay, m1)), __fmul_rn(az, m2));
+    float ny = __fadd_rn(__fadd_rn(__fmul_rn(ax, m4), __fmul_rn(ay, m5)), __fmul_rn(az, m6));
+    float nz = __fadd_rn(__fadd_rn(__fmul_rn(ax, m8), __fmul_rn(ay, m9)), __fmul_rn(az, m10));
     nx = __fmul_rn(nx, -1.0f); ny = __fmul_rn(ny, -1.0f); nz = __fmul_rn(nz, -1.0f);
     float cr, cg, cb;
     if (P.rad) { const float4 c = ldg4(P.rad + id); cr = c.x; cg = c.y; cb = c.z; }

@@ -31,6 +31,30 @@ __device__ __forceinline__ uint32_t compact_even_bits(uint32_t x) {
     return x;
 }
 
+// Order of the 1024 pixels of a 32x32 tile in which a warp consumes them, and with it the shape of a work unit (2^s
+// consecutive ordinals).  RTB_TILE_ORDER 0: Morton (units 8x4, 8x8, 16x8, 16x16, ...).  1: Morton inside 4x4 blocks, then
+// the blocks of a row of blocks, then the rows: ordinal bits x0 y0 x1 y1 x2 x3 x4 y2 y3 y4 -- units are 8x4, 16x4, 32x4,
+// 32x8, ...: a 128-pixel unit is four whole 128-byte rows of its tile, which is what the peer push wants to send.
+#ifndef RTB_TILE_ORDER
+#define RTB_TILE_ORDER 1
+#endif
+__device__ __forceinline__ void tile_xy(uint32_t k, int& x, int& y) {
+#if RTB_TILE_ORDER == 0
+    x = (int)compact_even_bits(k); y = (int)compact_even_bits(k >> 1);
+#else
+    x = (int)((k & 1u) | ((k >> 1) & 2u) | ((k >> 2) & 0x1cu));
+    y = (int)(((k >> 1) & 1u) | ((k >> 2) & 2u) | ((k >> 5) & 0x1cu));
+#endif
+}
+// log2 of the width in pixels of a unit of 2^shift pixels (shift 5..10); its height is 2^(shift - this)
+__device__ __forceinline__ int unit_wshift(int shift) {
+#if RTB_TILE_ORDER == 0
+    return (shift + 1) >> 1;
+#else
+    return shift - 2 < 5 ? shift - 2 : 5;
+#endif
+}
+
 // ordered "not equal": false when either operand is NaN
 __device__ __forceinline__ bool ordered_ne(float x, float y) { return (x < y) | (x > y); }
 
@@ -142,10 +166,25 @@ __global__ void selftest_exact_kernel(uint64_t seed, long long count, unsigned l
 #ifndef RTB_MIN_BLOCKS
 #define RTB_MIN_BLOCKS 8
 #endif
+// RTB_STACK_PACKED 1: a stack entry is one 16-byte local-memory word (ref, tmin, tmax, -): one LDL.128 / STL.128 per pop /
+// push instead of three 4-byte accesses to three arrays.
+#ifndef RTB_STACK_PACKED
+#define RTB_STACK_PACKED 0
+#endif
+// RTB_LOOP_REDUX 1: the three ballots + popcounts that steer a traversal iteration become one warp-wide integer sum
+#ifndef RTB_LOOP_REDUX
+#define RTB_LOOP_REDUX 0
+#endif
+// RTB_NODE_LOAD_HINT 1: node records are loaded with an L2 evict_last policy (createpolicy), frames are written evict_first
+#ifndef RTB_NODE_LOAD_HINT
+#define RTB_NODE_LOAD_HINT 0
+#endif
 #ifndef RTB_MIN_BLOCKS_PUSH
 #define RTB_MIN_BLOCKS_PUSH 7  // the push variant carries more warp state: 72 registers spill nothing
 #endif
-template <bool CULL, bool COUNT, bool PUSH>
+// INLINE: single-frame launch whose frame record is P.frame0 (kernel parameter space) -- the per-frame path of the
+// reference's loop (Object::render, WinMain.cpp:212) then needs no upload before the launch.
+template <bool CULL, bool COUNT, bool PUSH, bool INLINE = false>
 __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RTB_MIN_BLOCKS) render_stream_kernel(const RenderParams P) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanemask_lt = (1u << lane) - 1u;
@@ -155,16 +194,33 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
     unsigned open_mask = 0u;   // warp-uniform: slots of s_owed/s_unit in use
     int my_pslot = 0, u_pslot = 0;
     bool blocked = false;      // warp-uniform: no free slot for the next unit -> drain in-flight rays first
-    unsigned long long c_nodes = 0, c_boxes = 0, c_tris = 0, c_rays = 0, c_hits = 0;
+    unsigned long long c_nodes = 0, c_boxes = 0, c_tris = 0, c_rays = 0, c_hits = 0, c_depth = 0;
+    int ray_depth = 0, c_depth_max = 0;  // COUNT: deepest stack of the lane's current ray / of any ray of this lane
 
     // Traversal stack: the top entry lives in registers (top_*), deeper entries in local memory.
     // A pop hands out the register copy at once and re-loads the new top in the background, so the
     // memory latency of the stack is off the dependent chain.
+#if RTB_STACK_PACKED
+    float4 stk[kStackDepth];
+#else
     int stk_ref[kStackDepth];
     float stk_tmin[kStackDepth], stk_tmax[kStackDepth];
+#endif
     int top_ref = 0;
     float top_tmin = 0.0f, top_tmax = 0.0f;
+    // entry i of this thread's stack (0 = oldest), below the register-cached top
+#if RTB_STACK_PACKED
+#define RTB_STACK_LOAD(i, ref, tmin, tmax) do { const float4 e_ = stk[i]; ref = __float_as_int(e_.x); tmin = e_.y; tmax = e_.z; } while (0)
+#define RTB_STACK_STORE(i, ref, tmin, tmax) stk[i] = make_float4(__int_as_float(ref), tmin, tmax, 0.0f)
+#else
+#define RTB_STACK_LOAD(i, ref, tmin, tmax) do { ref = stk_ref[i]; tmin = stk_tmin[i]; tmax = stk_tmax[i]; } while (0)
+#define RTB_STACK_STORE(i, ref, tmin, tmax) do { stk_ref[i] = ref; stk_tmin[i] = tmin; stk_tmax[i] = tmax; } while (0)
+#endif
 
+#if RTB_NODE_LOAD_HINT
+    unsigned long long l2_keep;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(l2_keep));
+#endif
     // ---- per-lane ray state ---------------------------------------------------------------------
     Ray r;
     r.dx = r.dy = r.dz = r.ix = r.iy = r.iz = r.fx = r.fy = r.fz = r.ox = r.oy = r.oz = 0.0f;
@@ -189,27 +245,44 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
     auto culled = [&](float tmin) -> bool { return CULL && (tmin > __fmaf_rn(P.cull_rel, fabsf(tmin), cull_base)); };
 
     for (;;) {
+#if RTB_LOOP_REDUX
+        int n_trav = __reduce_add_sync(0xffffffffu, state == kStateTraverse ? 1 : 0);
+#else
         unsigned m_trav = __ballot_sync(0xffffffffu, state == kStateTraverse);
+#endif
 
         // ================= traversal: steps until enough lanes have run dry ==========================
         // (while pixels remain, fall out to retire + refill as soon as no more than t_active lanes are
         // still traversing; once the work is exhausted, drain)
         const int keep_active = (exhausted | (PUSH && blocked)) ? 0 : P.t_active;
+#if RTB_LOOP_REDUX
+        while (n_trav > keep_active) {
+#else
         while (__popc(m_trav) > keep_active) {
+#endif
             // ---- lanes that finished a node or leaf take the stack top ------------------------------
             if (want_pop) {
                 if (sp == 0) { state = kStateDone; want_pop = false; }
                 else {
                     if (!culled(top_tmin)) { cur = top_ref; cur_tmin = top_tmin; cur_tmax = top_tmax; want_pop = false; }
                     sp--;
-                    if (sp > 0) { top_ref = stk_ref[sp - 1]; top_tmin = stk_tmin[sp - 1]; top_tmax = stk_tmax[sp - 1]; }
+                    if (sp > 0) RTB_STACK_LOAD(sp - 1, top_ref, top_tmin, top_tmax);
                 }
             }
             const bool ready = (state == kStateTraverse) & !want_pop;
             const bool at_leaf = ready & (cur < 0);
+#if RTB_LOOP_REDUX
+            // one warp-wide sum carries the three lane counts that steer the iteration: rays in flight (after the pops
+            // above, the only place a ray can finish), lanes waiting at a leaf, lanes ready for an interior step
+            const int votes = __reduce_add_sync(0xffffffffu, (state == kStateTraverse ? 1 : 0) | (at_leaf ? 0x100 : 0) | ((ready & !at_leaf) ? 0x10000 : 0));
+            n_trav = votes & 0xff;
+            const int n_leaf = (votes >> 8) & 0xff, n_int = votes >> 16;
+            if (n_leaf != 0 && (n_leaf >= P.t_leaf || n_int == 0)) {
+#else
             const unsigned m_ready = __ballot_sync(0xffffffffu, ready);
             const unsigned m_leaf = __ballot_sync(0xffffffffu, at_leaf);
             if (m_leaf != 0u && (__popc(m_leaf) >= P.t_leaf || m_leaf == m_ready)) {
+#endif
                 // ---- leaf step: always intersected when popped (Trixel.cu:98) -----------------------
                 if (at_leaf) {
                     if (COUNT) c_tris++;
@@ -221,7 +294,11 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                 if (COUNT) c_nodes++;
                 const float4* rec;  // P.nodes + 64 bytes * record index, as one IMAD.WIDE
                 asm("mad.wide.u32 %0, %1, 64, %2;" : "=l"(rec) : "r"((unsigned)cur & kRefIndexMask), "l"(P.nodes));
+#if RTB_NODE_LOAD_HINT
+                const float4 q0 = ldg4_keep(rec, l2_keep), q1 = ldg4_keep(rec + 1, l2_keep), q2 = ldg4_keep(rec + 2, l2_keep), q3 = ldg4_keep(rec + 3, l2_keep);
+#else
                 const float4 q0 = ldg4(rec), q1 = ldg4(rec + 1), q2 = ldg4(rec + 2), q3 = ldg4(rec + 3);
+#endif
                 const int lref = __float_as_int(q3.x), rref = __float_as_int(q3.y);
                 const float S1 = q3.z, S2 = q3.w;  // left child's max / right child's min on the split axis (Trixel.h:353-376)
                 const int axis = (lref >> kRefAxisShift) & 3;
@@ -256,9 +333,10 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                         const bool go_first = !culled(f_eff);
                         const bool go_second = visit_second & !culled(s_eff);
                         if (go_second) {
-                            if (sp > 0) { stk_ref[sp - 1] = top_ref; stk_tmin[sp - 1] = top_tmin; stk_tmax[sp - 1] = top_tmax; }
+                            if (sp > 0) RTB_STACK_STORE(sp - 1, top_ref, top_tmin, top_tmax);
                             top_ref = left_first ? rref : lref; top_tmin = s_eff; top_tmax = left_first ? rtmax : ltmax;
                             sp++;
+                            if (COUNT) ray_depth = max(ray_depth, sp);
                         }
                         cur = left_first ? lref : rref; cur_tmin = f_eff; cur_tmax = left_first ? ltmax : rtmax;
                         want_pop = !go_first;
@@ -272,9 +350,10 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                     const bool go_first = ((first < 0) | f_in) & !culled(f_tmin);
                     const bool go_second = visit_second & ((second < 0) | s_in) & !culled(s_tmin);
                     if (go_second) {
-                        if (sp > 0) { stk_ref[sp - 1] = top_ref; stk_tmin[sp - 1] = top_tmin; stk_tmax[sp - 1] = top_tmax; }
+                        if (sp > 0) RTB_STACK_STORE(sp - 1, top_ref, top_tmin, top_tmax);
                         top_ref = second; top_tmin = s_tmin; top_tmax = s_tmax;
                         sp++;
+                        if (COUNT) ray_depth = max(ray_depth, sp);
                     }
                     cur = first; cur_tmin = f_tmin; cur_tmax = f_tmax;
                     want_pop = !go_first;
@@ -286,16 +365,28 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                     descend((ex & 1) != 0, (ex & 2) != 0, (ex & 4) != 0, (ex & 8) != 0);
                 }
             }
+#if !RTB_LOOP_REDUX
             m_trav = __ballot_sync(0xffffffffu, state == kStateTraverse);
+#endif
         }
+#if RTB_LOOP_REDUX
+        const unsigned m_trav = __ballot_sync(0xffffffffu, state == kStateTraverse);
+#endif
 
         // ================= retire: Phong + store for finished rays ===================================
         if (state == kStateDone) {
             uint32_t color = P.background;
             if (id >= 0) {
-                color = phong(P, P.frames + (long long)kFrameStride * frame, r, best, id, cmx, cmy, cmz);
+                if (INLINE) {
+                    color = phong(P, P.frame0[0], P.frame0[1], P.frame0[2], P.frame0[4], P.frame0[5], P.frame0[6], P.frame0[8], P.frame0[9], P.frame0[10],
+                                  r, best, id, cmx, cmy, cmz);
+                } else {
+                    const float* __restrict__ M = P.frames + (long long)kFrameStride * frame;
+                    color = phong(P, M[0], M[1], M[2], M[4], M[5], M[6], M[8], M[9], M[10], r, best, id, cmx, cmy, cmz);
+                }
                 if (COUNT) c_hits++;
             }
+            if (COUNT) { c_depth += (unsigned long long)ray_depth; c_depth_max = max(c_depth_max, ray_depth); ray_depth = 0; }
             const long long o = (long long)frame * P.frame_stride + pix;
             // frames are write-once streams: keep them from displacing the scene in L2
             if (P.out_bgra) RTB_PIXEL_STORE(P.out_bgra + o, color);
@@ -310,7 +401,7 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
         if (!exhausted && u_next >= (1 << u_shift) && !(PUSH && blocked)) {
             for (;;) {
                 unsigned long long uid = 0;
-                if (lane == 0) uid = atomicAdd(P.work_counter, 1ull);
+                if (lane == 0) uid = atomicAdd(P.work_counter, 1ull) - P.work_base;
                 uid = __shfl_sync(0xffffffffu, uid, 0);
                 if ((long long)uid >= P.total_items) { exhausted = true; break; }
                 // which segment of the launch (unit size), which frame, which tile, which block of the tile
@@ -332,21 +423,28 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                 u_base = (rem % units_per_tile) << u_shift;
                 u_x0 = (tile % P.tiles_x) * kTile;
                 u_y0 = (tile / P.tiles_x) * kTile;
-                const float* __restrict__ F = P.frames + (long long)kFrameStride * u_frame;
-                u_rx0 = __float_as_int(__ldg(F + 12)); u_ry0 = __float_as_int(__ldg(F + 13));
-                u_rx1 = __float_as_int(__ldg(F + 14)); u_ry1 = __float_as_int(__ldg(F + 15));
-                const int xoff = (int)compact_even_bits((uint32_t)u_base), yoff = (int)compact_even_bits((uint32_t)u_base >> 1);
+                if (INLINE) {
+                    u_rx0 = __float_as_int(P.frame0[12]); u_ry0 = __float_as_int(P.frame0[13]);
+                    u_rx1 = __float_as_int(P.frame0[14]); u_ry1 = __float_as_int(P.frame0[15]);
+                } else {
+                    const float* __restrict__ F = P.frames + (long long)kFrameStride * u_frame;
+                    u_rx0 = __float_as_int(__ldg(F + 12)); u_ry0 = __float_as_int(__ldg(F + 13));
+                    u_rx1 = __float_as_int(__ldg(F + 14)); u_ry1 = __float_as_int(__ldg(F + 15));
+                }
+                int xoff, yoff;
+                tile_xy((uint32_t)u_base, xoff, yoff);
                 if (!COUNT) {
                     // ---- a unit that lies entirely outside the frame's root-box rectangle is background: the warp
                     // writes it with 16-byte stores at its final place and goes for the next unit -----------------
-                    const int wshift = (u_shift + 1) >> 1;  // a unit is a (1 << wshift) x (unit_pixels >> wshift) pixel block
+                    const int wshift = unit_wshift(u_shift);  // a unit is a (1 << wshift) x (unit_pixels >> wshift) pixel block
                     const int bx = u_x0 + xoff, by = u_y0 + yoff;
                     if (bx > u_rx1 || bx + (1 << wshift) - 1 < u_rx0 || by > u_ry1 || by + (unit_pixels >> wshift) - 1 < u_ry0) {
                         if (PUSH && P.push_skip_background) continue;  // the frame's owner has pre-filled it: nothing to send
-                        uint32_t* __restrict__ dc = PUSH ? P.push_bgra : P.out_bgra;
-                        int32_t* __restrict__ di = PUSH ? P.push_ids : P.out_ids;
+                        const int owner = PUSH ? u_frame % P.push_owners : 0;
+                        uint32_t* __restrict__ dc = PUSH ? P.push_bgra[owner] : P.out_bgra;
+                        int32_t* __restrict__ di = PUSH ? P.push_ids[owner] : P.out_ids;
                         const bool row_major = PUSH || !P.tile_major;
-                        const long long fbase = (long long)u_frame * (PUSH ? (long long)P.W * P.H : P.frame_stride);
+                        const long long fbase = PUSH ? (long long)(u_frame / P.push_owners) * P.W * P.H : (long long)u_frame * P.frame_stride;
                         const bool vec = !row_major || (P.W & 3) == 0;
                         for (int i = (int)lane; i < (unit_pixels >> 2); i += 32) {
                             const int row = i >> (wshift - 2), col = (i - (row << (wshift - 2))) << 2;
@@ -385,8 +483,9 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
             bool settled = false;  // PUSH: this lane took a pixel that needs no ray (outside the image, or background)
             if (((m_empty >> lane) & 1u) && slot < avail) {
                 settled = true;
-                const uint32_t K = (uint32_t)(u_base + u_next + slot);  // Morton ordinal inside the 32x32 tile
-                const int lx = (int)compact_even_bits(K), ly = (int)compact_even_bits(K >> 1);
+                const uint32_t K = (uint32_t)(u_base + u_next + slot);  // ordinal inside the 32x32 tile
+                int lx, ly;
+                tile_xy(K, lx, ly);
                 const int px = u_x0 + lx, py = u_y0 + ly;
                 if (px < P.W && py < P.H) {
                     const int opix = P.tile_major ? (u_slot * kTile + ly) * kTile + lx : py * P.W + px;
@@ -403,6 +502,7 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                         settled = false;
                         my_pslot = u_pslot;
                         const float* __restrict__ M = P.frames + (long long)kFrameStride * frame;
+                        auto mword = [&](int k) -> float { return INLINE ? P.frame0[k] : __ldg(M + k); };
                         // ---- primary ray, Camera.cu:103-104 (row 0 = bottom) --------------------------
                         const float fxp = (float)px, fyp = (float)py;
                         cmx = __fadd_rn(__fadd_rn(P.n_mod[0], __fmul_rn(P.u_mod[0], fxp)), __fmul_rn(P.v_mod[0], fyp));
@@ -410,9 +510,9 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                         cmz = __fadd_rn(__fadd_rn(P.n_mod[2], __fmul_rn(P.u_mod[2], fxp)), __fmul_rn(P.v_mod[2], fyp));
                         normalize21(cmx, cmy, cmz);
                         // ---- into object space, Trixel.cu:60-66 (sign dance kept for -0 fidelity) ------
-                        const float m0 = __ldg(M + 0), m1 = __ldg(M + 1), m2 = __ldg(M + 2), m3 = __ldg(M + 3);
-                        const float m4 = __ldg(M + 4), m5 = __ldg(M + 5), m6 = __ldg(M + 6), m7 = __ldg(M + 7);
-                        const float m8 = __ldg(M + 8), m9 = __ldg(M + 9), m10 = __ldg(M + 10), m11 = __ldg(M + 11);
+                        const float m0 = mword(0), m1 = mword(1), m2 = mword(2), m3 = mword(3);
+                        const float m4 = mword(4), m5 = mword(5), m6 = mword(6), m7 = mword(7);
+                        const float m8 = mword(8), m9 = mword(9), m10 = mword(10), m11 = mword(11);
                         r.ox = m3; r.oy = m7; r.oz = m11;
                         r.dx = __fmul_rn(-1.0f, __fadd_rn(__fadd_rn(__fmul_rn(m0, -cmx), __fmul_rn(m1, -cmy)), __fmul_rn(m2, -cmz)));
                         r.dy = __fmul_rn(-1.0f, __fadd_rn(__fadd_rn(__fmul_rn(m4, -cmx), __fmul_rn(m5, -cmy)), __fmul_rn(m6, -cmz)));
@@ -463,23 +563,26 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                 m_flush &= m_flush - 1u;
                 const int dshift = d.z >> 8, unit_pixels = 1 << dshift;
                 d.z &= 0xff;
-                const int wshift = (dshift + 1) >> 1;  // a unit is a (1 << wshift) x (unit_pixels >> wshift) block of its tile
+                const int wshift = unit_wshift(dshift);  // a unit is a (1 << wshift) x (unit_pixels >> wshift) block of its tile
                 const int tile = P.tile_first + d.y * P.tile_stride;
                 const int bx = (tile % P.tiles_x) * kTile + d.z, by = (tile / P.tiles_x) * kTile + d.w;
                 const long long lbase = (long long)d.x * P.frame_stride + ((long long)d.y * kTile + d.w) * kTile + d.z;
-                const long long rbase = (long long)d.x * P.W * P.H;
+                const int owner = d.x % P.push_owners;
+                uint32_t* const pc = P.push_bgra[owner];
+                int32_t* const pi = P.push_ids[owner];
+                const long long rbase = (long long)(d.x / P.push_owners) * P.W * P.H;
                 for (int i = (int)lane; i < (unit_pixels >> 2); i += 32) {
                     const int row = i >> (wshift - 2), col = (i - (row << (wshift - 2))) << 2;
                     const int px = bx + col, py = by + row;
                     if (py >= P.H || px >= P.W) continue;
                     const long long lo = lbase + row * kTile + col, ro = rbase + (long long)py * P.W + px;
                     if (((P.W & 3) == 0)) {  // whole 16-byte segments (px is a multiple of 4, so px + 3 < W as well)
-                        if (P.push_bgra) *reinterpret_cast<uint4*>(P.push_bgra + ro) = __ldcg(reinterpret_cast<const uint4*>(P.out_bgra + lo));
-                        if (P.push_ids) *reinterpret_cast<int4*>(P.push_ids + ro) = __ldcg(reinterpret_cast<const int4*>(P.out_ids + lo));
+                        if (pc) *reinterpret_cast<uint4*>(pc + ro) = __ldcg(reinterpret_cast<const uint4*>(P.out_bgra + lo));
+                        if (pi) *reinterpret_cast<int4*>(pi + ro) = __ldcg(reinterpret_cast<const int4*>(P.out_ids + lo));
                     } else {
                         for (int k = 0; k < 4 && px + k < P.W; k++) {
-                            if (P.push_bgra) P.push_bgra[ro + k] = __ldcg(P.out_bgra + lo + k);
-                            if (P.push_ids) P.push_ids[ro + k] = __ldcg(P.out_ids + lo + k);
+                            if (pc) pc[ro + k] = __ldcg(P.out_bgra + lo + k);
+                            if (pi) pi[ro + k] = __ldcg(P.out_ids + lo + k);
                         }
                     }
                 }
@@ -496,10 +599,13 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
             c_boxes += __shfl_down_sync(0xffffffffu, c_boxes, s);
             c_tris += __shfl_down_sync(0xffffffffu, c_tris, s);
             c_hits += __shfl_down_sync(0xffffffffu, c_hits, s);
+            c_depth += __shfl_down_sync(0xffffffffu, c_depth, s);
+            c_depth_max = max(c_depth_max, __shfl_down_sync(0xffffffffu, c_depth_max, s));
         }
         if (lane == 0) {
             atomicAdd(P.counters + 0, c_rays); atomicAdd(P.counters + 1, c_nodes); atomicAdd(P.counters + 2, c_boxes);
             atomicAdd(P.counters + 3, c_tris); atomicAdd(P.counters + 4, c_hits);
+            atomicAdd(P.counters + 5, c_depth); atomicMax(P.counters + 6, (unsigned long long)c_depth_max);
         }
     }
 }

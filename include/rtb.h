@@ -64,6 +64,14 @@ const char* rtb_version(void);
  * thread.  Replaces the hard-coded cudaSetDevice(0) of Trixel.cu:213,247,269, Camera.cu:73,115,166. */
 int rtb_device_count(void);
 int rtb_set_device(int device);
+/* Scheduling knobs of the render kernel, process-wide (development / tuning; the defaults are the measured best and are
+ * also read once from the environment as RTB_<NAME IN CAPITALS>): "unit_shift" log2 pixels per work unit (5..10, 0 = from
+ * the launch size), "t_active" (refill when no more lanes than this still traverse), "t_leaf" (leaf step when at least
+ * this many lanes wait at a leaf), "tail5" / "tail6" (trailing frames of a launch handed out in 32- / 64-pixel units,
+ * -1 = automatic), "reserve_sms" (SMs left free beside the persistent kernel), "l2_window" (persisting L2 window:
+ * 0 off, 1 node records, 2 nodes + triangles; applied at the next rtb_camera_add_object), "no_rect" (1: no root-box
+ * rectangle, every pixel is traced). */
+int rtb_set_knob(const char* name, int value);
 
 /* ---- mesh input -------------------------------------------------------------------------- */
 
@@ -146,6 +154,9 @@ const int32_t* rtb_camera_host_ids(const rtb_camera* cam);
  * [0] rays, [1] interior nodes entered (64-byte record fetches), [2] nodes popped in the reference's
  * sense (root + every child the parent scheduled), [3] triangle tests, [4] hits */
 int rtb_camera_counters(rtb_camera* cam, uint64_t out5[5], int reset);
+/* the same plus [5] sum over the traced rays of their deepest traversal stack (entries, counting the one kept in
+ * registers), [6] the deepest stack any ray reached, [7] reserved: sizes the shared-memory part of the stack */
+int rtb_camera_counters_ex(rtb_camera* cam, uint64_t out8[8], int reset);
 void rtb_camera_destroy(rtb_camera* cam);
 
 /* ---- object + transform ------------------------------------------------------------------ */
@@ -168,7 +179,9 @@ void rtb_object_destroy(rtb_object* obj);
  * (Object.cpp:10, Trixel.h:474, Trixel.cu:210).  One fused launch: ray generation, traversal,
  * Moller-Trumbore, Phong and background into the camera's device frame; follow with
  * rtb_camera_color_pixels(PHONG) to obtain it on the host, exactly like the reference's frame loop
- * (WinMain.cpp:212-213). */
+ * (WinMain.cpp:212-213).  The call returns as soon as the kernel is queued (the reference's cudaDeviceSynchronize at
+ * Trixel.cu:234 cannot be observed before color_pixels delivers the frame); rtb_camera_color_pixels is the one
+ * synchronisation of a frame, and launch errors surface there at the latest. */
 int rtb_object_render(rtb_object* obj, rtb_camera* cam, uint32_t flags);
 /* = rtb_object_render + rtb_camera_color_pixels(PHONG) with one synchronisation; the frame and the
  * id buffer are then readable through rtb_camera_host_color / rtb_camera_host_ids. */
@@ -176,8 +189,9 @@ int rtb_render_frame(rtb_object* obj, rtb_camera* cam, uint32_t flags);
 
 /* Batched animation sweep (WinMain.cpp:174-239 with a key held down): for frame k = 0..num_frames-1
  * apply `steps_per_frame` transforms ops[k*steps_per_frame ...] (each 5 floats: select, x, y, z, w;
- * select 0 = no-op) and render.  All frames go through ONE persistent launch; finished frames
- * stream to the host while later ones render.  bgra_out / ids_out are caller buffers of
+ * select 0 = no-op) and render.  The frames are rendered in chunks of about 16 MB of output per buffer, one persistent
+ * launch per chunk; a finished chunk streams to the host while the next one renders (two chunks in flight).  The call
+ * returns when every frame is in the caller's buffers.  bgra_out / ids_out are caller buffers of
  * num_frames*W*H elements (pageable or pinned; either may be NULL) -- the only interface here that
  * writes into caller memory.  The object's transform state advances as if the calls had been made
  * one by one; the camera's single-frame buffers (rtb_camera_host_color / _ids) are left untouched. */
@@ -189,7 +203,11 @@ int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32
  * image tiles t with t % tile_stride == tile_first (tiles are 32x32 pixels, row-major over the
  * image; stride 1 = whole frame).  Output is written at its final row-major position in
  * d_bgra/d_ids (num_frames*W*H elements each, device pointers; either may be NULL).  `stream` is a
- * cudaStream_t (NULL = the library's own stream; pass cudaStreamLegacy for the default stream).  Asynchronous with respect to the host. */
+ * cudaStream_t (NULL = the library's own stream; pass cudaStreamLegacy for the default stream).  Asynchronous with
+ * respect to the host: the call queues an upload of the frame records (none for a single frame: its record travels in
+ * the kernel parameters) and the launch, and returns; it may wait a few microseconds for the PREVIOUS call's upload on
+ * this object, never for a kernel.  Launches of one object are ordered on the device in call order whatever streams
+ * they are issued on (they share the object's frame records and work counter); different objects render concurrently. */
 int rtb_render_frames_device_async(rtb_object* obj, rtb_camera* cam, int32_t num_frames, const float* m12,
                                    int32_t tile_first, int32_t tile_stride, uint32_t flags, uint32_t* d_bgra,
                                    int32_t* d_ids, void* stream);
@@ -214,6 +232,14 @@ int rtb_compose_tiles_device_async(rtb_camera* cam, int32_t num_frames, int32_t 
 int rtb_render_frames_push_async(rtb_object* obj, rtb_camera* cam, int32_t num_frames, const float* m12,
                                  int32_t tile_first, int32_t tile_stride, uint32_t flags, uint32_t* d_frame_bgra,
                                  int32_t* d_frame_ids, void* stream);
+/* The same with STRIPED frame ownership: frame f of the launch is frame f / owners of owner f % owners, whose final-frame
+ * buffers are d_frame_bgra[f % owners] / d_frame_ids[f % owners] (each holding ceil(num_frames / owners) * W*H elements;
+ * either array may be NULL).  With one owner per rank every GPU takes in 1/N of the pushed pixels instead of one GPU
+ * taking all of them (that GPU's NVLink ingest bounded the single-owner exchange at N = 8), and every rank ends up
+ * holding -- and delivering -- 1/N of the finished frames.  owners <= 8. */
+int rtb_render_frames_push_striped_async(rtb_object* obj, rtb_camera* cam, int32_t num_frames, const float* m12,
+                                         int32_t tile_first, int32_t tile_stride, uint32_t flags, int32_t owners,
+                                         uint32_t* const* d_frame_bgra, int32_t* const* d_frame_ids, void* stream);
 /* set_cam_cuda (Camera.cu:12-18, the SET_COLOR_TAG fill) for `num_frames` device frames at once: background colour into
  * d_frame_bgra, -1 into d_frame_ids (either may be NULL).  With RTB_RENDER_PUSH_PREFILLED the owner of the final frames
  * runs this before the ranks push, and work units that contain nothing but background never cross NVLink. */
@@ -234,6 +260,12 @@ int rtb_peer_read(void* host_dst, const void* d_ptr, size_t bytes);
 /* host-side transform recurrence only (no GPU): advance `obj` by one op and return its matrix;
  * lets callers precompute the m12 array for rtb_render_frames_device_async. */
 int rtb_object_transform_host(rtb_object* obj, const float xyzw[4], uint8_t transform_select, float m12_out[12]);
+
+/* The same recurrence with no object and no GPU: start from the state Camera::add_object gives a new object for a camera
+ * at cam_pos (Camera.cpp:131-134), apply `count` ops (5 floats each: select, x, y, z, w; select 0 = no-op) one by one and
+ * write the matrix after each into m12_out (12 floats per op).  What a caller uses to precompute the matrices of a sweep,
+ * and what the tests pin against the reference's Object::transform over the whole 600-step orbit. */
+int rtb_transform_sequence_host(const float cam_pos[3], int32_t count, const float* ops5, float* m12_out);
 
 /* Device self-test of the exactness arguments the kernel relies on: `count` pseudo-random
  * operand sets (random bit patterns, near-ties, tiny values, NaN).  out4[0] = early-exit Newton rsqrt != literal 21

@@ -14,10 +14,15 @@
 #include "rtb.h"
 
 namespace {
-std::unordered_map<Trixel*, rtb_mesh*> g_mesh;
+struct MeshEntry { rtb_mesh* mesh = nullptr; bool tree_built = false; };
+std::unordered_map<Trixel*, MeshEntry> g_mesh;
 std::unordered_map<Camera*, rtb_camera*> g_cam;
 std::unordered_map<Object*, rtb_object*> g_obj;
-std::unordered_map<Object*, Camera*> g_cam_of;
+// Object::render hands the seam the object's OWN quaternion (Object.cpp:10-12 -> Trixel.h:474-476 -> Trixel.cu:210), which
+// Camera::add_object created just before it called init_camera_voxel_device_memory (Camera.cpp:134,139): the quaternion's
+// address identifies the object to draw.  WinMain registers two objects and renders / transforms the first
+// (WinMain.cpp:152-156,186-189,212).
+std::unordered_map<Quaternion*, rtb_object*> g_obj_of_quat;
 
 cudaError_t report(int rc, const char* who) {  // the reference prints and carries on (vector.cuh:15-18); its callers ignore the value
     if (rc) printf("%s failed: %s\n", who, rtb_last_error());
@@ -45,7 +50,8 @@ extern "C" cudaError_t init_trixels_device_memory(Trixel* t) {  // Trixel.cu:266
     cudaMemcpy(rad.data(), t->h_mem.d_color.rad, sizeof(Color::radiance) * (size_t)t->num_trixels, cudaMemcpyDeviceToHost);
     rtb_mesh* m = nullptr;
     const int rc = rtb_mesh_create(t->h_points_init_data, t->num_trixels, &rad[0].r, nullptr, &m);
-    g_mesh[t] = m;
+    g_mesh[t].mesh = m;
+    g_mesh[t].tree_built = false;
     return report(rc, "init_trixels_device_memory");
 }
 
@@ -67,15 +73,17 @@ extern "C" cudaError_t init_camera_trixel_device_memory(Trixel*, Camera*) { retu
 
 extern "C" cudaError_t init_camera_voxel_device_memory(Trixel* t, Camera* c) {  // Camera.cu:163, via Camera::add_object (Camera.cpp:139,208)
     Object* o = c->object_list[c->num_objects - 1];                              // the object being added (Camera.cpp:118-130)
-    rtb_mesh* m = g_mesh[t];
+    MeshEntry& e = g_mesh[t];
     // Trixel::create_kd has built the reference's host tree by now; the identical tree is rebuilt on the GPU in
-    // milliseconds (a maintainer may instead turn create_kd itself into rtb_mesh_build_tree and skip the host build)
-    int rc = rtb_mesh_build_tree(m);
+    // milliseconds, once per Trixel however many objects instance it (a maintainer may instead turn create_kd itself
+    // into rtb_mesh_build_tree and skip the host build)
+    int rc = e.tree_built ? 0 : rtb_mesh_build_tree(e.mesh);
+    e.tree_built = e.tree_built || rc == 0;
     rtb_object* h = nullptr;
-    if (!rc) rc = rtb_object_create(m, &h);
-    if (!rc) rc = rtb_camera_add_object(g_cam[c], h);
+    if (!rc) rc = rtb_object_create(e.mesh, &h);
+    if (!rc) rc = rtb_camera_add_object(g_cam[c], h);  // objects of one mesh share the camera-side arrays inside librtb
     g_obj[o] = h;
-    g_cam_of[o] = c;
+    g_obj_of_quat[o->quat] = h;                        // assigned at Camera.cpp:134, five lines before this call
     return report(rc, "init_camera_voxel_device_memory");
 }
 
@@ -84,8 +92,14 @@ extern "C" cudaError_t transform_camera_voxel_device_memory(Object* o, VEC4<T_fp
     return report(rtb_object_transform(g_obj[o], v, select), "transform_camera_voxel_device_memory");
 }
 
-cudaError_t intersect_trixels_device(Trixel*, Camera* c, Quaternion*, u32) {  // Trixel.cu:210 (C++ linkage, Trixel.h:13)
-    return report(rtb_object_render(g_obj[c->object_list[c->num_objects - 1]], g_cam[c], RTB_RENDER_DEFAULT), "intersect_trixels_device");
+cudaError_t intersect_trixels_device(Trixel*, Camera* c, Quaternion* q, u32) {  // Trixel.cu:210 (C++ linkage, Trixel.h:13)
+    // the reference renders with the matrix of the quaternion it is handed (Trixel.cu:222 `q->d_rot_m`): that names the object
+    const auto it = g_obj_of_quat.find(q);
+    if (it == g_obj_of_quat.end()) {
+        printf("intersect_trixels_device failed: the quaternion does not belong to an object added to a camera\n");
+        return (cudaError_t)RTB_ERR_STATE;
+    }
+    return report(rtb_object_render(it->second, g_cam[c], RTB_RENDER_DEFAULT), "intersect_trixels_device");
 }
 
 extern "C" cudaError_t color_camera_device(Camera* c, u8 tag) {  // Camera.cu:70

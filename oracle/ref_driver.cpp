@@ -36,11 +36,13 @@ namespace {
 struct RefScene {
     Camera* cam = nullptr;
     Trixel* trixels = nullptr;
-    Object* obj = nullptr;
+    Object* obj = nullptr;   // WinMain's obj1: the one it transforms and renders (WinMain.cpp:188-208,212)
+    Object* obj2 = nullptr;  // WinMain's obj2 (WinMain.cpp:153,156): registered, never drawn (:214 is commented out)
     Input* input = nullptr;
     T_fp* points = nullptr;
     T_uint ntri = 0;
 };
+int g_winmain_objects = 1;  // ref_set_objects: 2 = register two objects over the mesh like WinMain.cpp:152-156
 float fmin3(float a, float b, float c) { return min(a, min(b, c)); }
 float fmax3(float a, float b, float c) { return max(a, max(b, c)); }
 }  // namespace
@@ -87,11 +89,17 @@ void* ref_open(const char* ply_path, int mode, const float* points9, long ntri_i
     s->trixels = new Trixel(ntri, s->points, &colors);
     s->trixels->set_sorted_voxels(leafs, ntri);
     s->trixels->create_kd();
-    s->obj = new Object(s->trixels);
-    s->cam->add_object(s->obj);
+    s->obj = new Object(s->trixels);               // WinMain.cpp:152
+    if (g_winmain_objects >= 2) s->obj2 = new Object(s->trixels);  // :153
+    s->cam->add_object(s->obj);                    // :155
+    if (s->obj2) s->cam->add_object(s->obj2);      // :156
     s->input = new Input();
     return s;
 }
+
+// 1 (default): one object, the smallest scene; 2: the literal WinMain.cpp:152-156 sequence -- two objects over one
+// mesh, both added to the camera, the first one transformed and rendered.  Applies to scenes opened afterwards.
+void ref_set_objects(int n) { g_winmain_objects = n; }
 
 long ref_num_tris(void* h) { return (long)((RefScene*)h)->ntri; }
 long ref_num_nodes(void* h) { return (long)((RefScene*)h)->trixels->num_voxels; }

@@ -58,6 +58,7 @@ def lib(impl="emu"):
         L.ref_render_nocopy.argtypes = [C.c_void_p]
         L.ref_threads.restype = C.c_int
         L.ref_set_threads.argtypes = [C.c_int]
+        L.ref_set_objects.argtypes = [C.c_int]
         _libs[impl] = L
     return _libs[impl]
 
@@ -65,8 +66,11 @@ def lib(impl="emu"):
 class RefScene:
     """The reference app's scene: one camera, one mesh, one object (WinMain.cpp:69-156)."""
 
-    def __init__(self, W, H, cam14, rgb=(0.1, 0.55, 0.2), ply_path=None, mode=0, points9=None, impl="emu"):
+    def __init__(self, W, H, cam14, rgb=(0.1, 0.55, 0.2), ply_path=None, mode=0, points9=None, impl="emu", objects=1):
+        """objects=2 replays WinMain.cpp:152-156 literally: two objects over the mesh, both registered with the camera,
+        the first one transformed and rendered."""
         L = self.L = lib(impl)
+        L.ref_set_objects(objects)
         self.W, self.H = W, H
         cam = np.zeros(14, np.float32)
         cam[:len(cam14)] = np.asarray(cam14, np.float32)

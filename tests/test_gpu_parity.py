@@ -333,13 +333,12 @@ def test_against_reference_cuda_kernels_on_this_gpu(gpu, impl, case):
 
 
 @pytest.mark.parametrize("W,H,unit_shift", [(300, 170, None), (97, 61, None), (256, 144, 5), (640, 360, 9), (320, 180, 10)])
-def test_push_variant_composes_the_same_frames(gpu, orc, W, H, unit_shift, monkeypatch):
+def test_push_variant_composes_the_same_frames(gpu, orc, W, H, unit_shift):
     """The fused render + exchange kernel (rtb_render_frames_push_async): G emulated ranks push their finished work
     units straight into one final frame buffer; the result must be the 1-GPU frames bit for bit (vector path for
     W % 4 == 0, scalar path for ragged rows, every unit shape)."""
     import torch
-    if unit_shift is not None:
-        monkeypatch.setenv("RTB_UNIT_SHIFT", str(unit_shift))
+    gpu.set_knob("unit_shift", unit_shift or 0)
     pts = gpu.geodesic_mesh(20)
     p = Pair(gpu, orc, pts, W, H)
     mats = [p.obj.matrix()]
@@ -376,6 +375,7 @@ def test_push_variant_composes_the_same_frames(gpu, orc, W, H, unit_shift, monke
         assert np.array_equal(got_i, ref_ids.cpu().numpy()), "prefilled ids, G=%d" % G
         assert np.array_equal(got_c, ref_col.cpu().numpy()), "prefilled colours, G=%d" % G
         buf_c.close(); buf_i.close()
+    gpu.set_knob("unit_shift", 0)
     p.close()
 
 
@@ -661,3 +661,174 @@ def test_reference_host_classes_over_librtb(gpu, orc, case):
         if case == "bunny":
             assert orc.fnv1a64(ids) == g["bunny_960x540"]["frames"][k]["id_hash"]   # recorded from the reference's own kernels
     ref.close()
+
+
+def test_reference_winmain_two_object_sequence_over_librtb(gpu, orc):
+    """The reference's REAL start-up sequence (WinMain.cpp:152-156: obj1 and obj2 over one Trixel, both added to the
+    camera; :188, :212: obj1 is the one transformed and rendered) through the reference's own host classes over
+    integration/rtb_seam.cpp + librtb.so, against the reference's own CUDA kernels (contraction off) running the same
+    sequence on this GPU, and against the oracle.  The seam must draw the object whose quaternion Object::render hands
+    it (Object.cpp:10-12, Trixel.cu:210-224) -- with the last-registered object instead, the R key stops moving the picture."""
+    from oracle import refemu
+    if not refemu.available("seam") or not refemu.available("cuda_nofmad"):
+        pytest.skip("oracle/_ref/libref_seam.so / libref_cuda_nofmad.so not built (needs /root/reference at build time)")
+    path = mesh_path("rabbit_70k.ply")
+    cases = [("ico24", gpu.geodesic_mesh(24), None, 320, 180)]
+    if path is not None:
+        cases.append(("bunny", None, path, 960, 540))
+    for name, pts, ply, W, H in cases:
+        seam = refemu.RefScene(W, H, cam12(W, H), ply_path=ply, mode=1, points9=pts, impl="seam", objects=2)
+        ref = refemu.RefScene(W, H, cam12(W, H), ply_path=ply, mode=1, points9=pts, impl="cuda_nofmad", objects=2)
+        oracle = orc.Scene(seam.points(), W, H, cam12(W, H))
+        changed = 0
+        prev = None
+        for k in range(6):
+            if k:
+                q = gpu.R_KEY_QUAT if k < 5 else gpu.T_KEY_QUAT
+                sel = gpu.ROTATE_TRI_PY if k < 5 else gpu.ROTATE_TRI_NY
+                for sc in (seam, ref):
+                    sc.transform(sel, *q)
+                oracle.transform(sel, *q)
+            assert np.array_equal(seam.matrix().view(np.uint32), ref.matrix().view(np.uint32)), (name, k)
+            ids, bgra = seam.render()
+            rids, rbgra = ref.render()
+            oids, obgra = oracle.render()
+            assert np.array_equal(ids, rids), "%s frame %d: %d hit ids differ from the reference's kernels" % (name, k, int((ids != rids).sum()))
+            assert np.array_equal(ids, oids), "%s frame %d vs oracle" % (name, k)
+            assert channel_diff(bgra, rbgra).max(initial=0) <= COLOUR_TOL and np.array_equal(bgra, obgra)
+            if prev is not None:
+                changed += int((ids != prev).sum())
+            prev = ids
+        assert changed > 1000, "%s: the frames do not move (%d pixels changed over 5 transforms)" % (name, changed)
+        oracle.close()
+    refemu.lib("seam").ref_set_objects(1)
+    refemu.lib("cuda_nofmad").ref_set_objects(1)
+
+
+def test_objects_of_one_mesh_share_camera_arrays_and_move_independently(gpu, orc):
+    """Two objects over one mesh on one camera (WinMain.cpp:152-156): one copy of the camera-side arrays, two transforms."""
+    pts = gpu.geodesic_mesh(12)
+    mesh = gpu.Trixel(pts); mesh.create_kd()
+    W, H = 256, 144
+    cam = gpu.Camera(W, H, **cam_kwargs(W, H))
+    a, b = gpu.Object(mesh), gpu.Object(mesh)
+    cam.add_object(a); cam.add_object(b)
+    a.transform(gpu.R_KEY_QUAT, gpu.ROTATE_TRI_PY)
+    ra, rb = orc.Scene(pts, W, H, cam12(W, H)), orc.Scene(pts, W, H, cam12(W, H))
+    ra.transform(gpu.ROTATE_TRI_PY, *gpu.R_KEY_QUAT)
+    for obj, ref in ((a, ra), (b, rb), (a, ra)):
+        ids, bgra = obj.render_frame(cam)
+        oids, obgra = ref.render()
+        assert np.array_equal(ids.astype(np.int64), oids) and np.array_equal(bgra, obgra)
+    # destroying one of them leaves the other (and the shared arrays) intact
+    a.close()
+    ids, bgra = b.render_frame(cam)
+    oids, obgra = rb.render()
+    assert np.array_equal(ids.astype(np.int64), oids) and np.array_equal(bgra, obgra)
+    b.close(); cam.close(); mesh.close(); ra.close(); rb.close()
+
+
+def test_handle_lifetimes_in_any_order(gpu):
+    """Destroy order must not matter (the reference never frees anything; this library does): camera before its objects,
+    an object moved from one camera to another, a camera whose objects are gone."""
+    pts = gpu.geodesic_mesh(4)
+    mesh = gpu.Trixel(pts); mesh.create_kd()
+    c1 = gpu.Camera(64, 48, **cam_kwargs(64, 48)); c2 = gpu.Camera(96, 64, **cam_kwargs(96, 64))
+    a, b = gpu.Object(mesh), gpu.Object(mesh)
+    c1.add_object(a); c1.add_object(b)
+    ids_b, _ = b.render_frame(c1)
+    c1.close()                                  # both objects lose their camera ...
+    with pytest.raises(gpu.RtbError):
+        a.render(c2)                            # ... and say so
+    a.close()                                   # (used to read the freed camera)
+    c3 = gpu.Camera(64, 48, **cam_kwargs(64, 48))
+    c3.add_object(b)                            # b lives on: same frame on an identical camera
+    ids_b3, _ = b.render_frame(c3)
+    assert np.array_equal(ids_b, ids_b3)
+    c2.add_object(b)                            # moved from c3 to c2 ...
+    with pytest.raises(gpu.RtbError):
+        b.render(c3)                            # ... c3 no longer knows it
+    ids_c2, _ = b.render_frame(c2)
+    assert ids_c2.size == 96 * 64 and (ids_c2 >= 0).any()
+    b.close()
+    c3.close(); c2.close(); mesh.close()
+
+
+def test_launches_of_one_object_on_two_streams_keep_their_frames(gpu, orc):
+    """rtb_render_frames_device_async on stream A, then on stream B with other matrices, no host wait in between: the
+    launches share the object's frame records and work counter and must still both render their own frames."""
+    import torch
+    pts = gpu.geodesic_mesh(40)
+    W, H, F = 320, 180, 12
+    p = Pair(gpu, orc, pts, W, H)
+    mats = np.stack([p.obj.matrix()] + [p.obj.transform_host(gpu.R_KEY_QUAT, gpu.ROTATE_TRI_PY) for _ in range(2 * F - 1)])
+    sA, sB = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = [(torch.zeros(F * W * H, dtype=torch.int32, device="cuda"), torch.zeros(F * W * H, dtype=torch.int32, device="cuda")) for _ in range(2)]
+    want = []
+    for half in range(2):
+        c = torch.empty(F * W * H, dtype=torch.int32, device="cuda"); i = torch.empty(F * W * H, dtype=torch.int32, device="cuda")
+        p.obj.render_frames_device_async(p.cam, mats[half * F:(half + 1) * F], c.data_ptr(), i.data_ptr(), sA.cuda_stream)
+        torch.cuda.synchronize()
+        want.append((c.cpu().numpy(), i.cpu().numpy()))
+    for rep in range(3):
+        for half, st in ((0, sA), (1, sB)):
+            p.obj.render_frames_device_async(p.cam, mats[half * F:(half + 1) * F], outs[half][0].data_ptr(), outs[half][1].data_ptr(), st.cuda_stream)
+        # a single-frame launch (record in the kernel parameters) rides behind them on a third stream
+        one_c = torch.zeros(W * H, dtype=torch.int32, device="cuda"); one_i = torch.zeros(W * H, dtype=torch.int32, device="cuda")
+        p.obj.render_frames_device_async(p.cam, mats[3], one_c.data_ptr(), one_i.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        for half in range(2):
+            assert np.array_equal(outs[half][0].cpu().numpy(), want[half][0]) and np.array_equal(outs[half][1].cpu().numpy(), want[half][1]), (rep, half)
+        assert np.array_equal(one_i.cpu().numpy(), want[0][1][3 * W * H:4 * W * H])
+    p.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Depth of the long sweeps (BASELINE.json configs[2..3]): late frames of the drifting, never renormalised quaternion.
+# ---------------------------------------------------------------------------------------------------
+def _orbit_matrices(gpu, W, H, steps):
+    ops = np.zeros((steps, 5), np.float32)
+    ops[:, 0] = gpu.ROTATE_TRI_PY
+    ops[:, 1:] = gpu.R_KEY_QUAT
+    return gpu.transform_sequence((0.0, 0.1, -1.0), ops)
+
+
+def test_dragon_standin_late_orbit_frames_against_oracle(gpu, orc):
+    """C3 frames 299 and 599 (and every 50th frame of the 600-frame sweep as id hashes) against the oracle."""
+    pts = gpu.geodesic_mesh(209)
+    W, H = 960, 540
+    p = Pair(gpu, orc, pts, W, H)
+    mats = _orbit_matrices(gpu, W, H, 599)            # mats[k-1] = matrix of frame k
+    frames = list(range(49, 600, 50))                 # 49, 99, ..., 599
+    ops = gpu.orbit_ops(600)
+    ids_s, col_s = p.obj.render_sweep(p.cam, ops)     # the whole orbit through the batched API
+    for f in frames:
+        oids, obgra = p.ref.render(m12=mats[f - 1])
+        assert np.array_equal(ids_s[f].astype(np.int64), oids), "frame %d: %d ids differ" % (f, int((ids_s[f] != oids).sum()))
+        if f in (299, 599):
+            assert np.array_equal(col_s[f], obgra), "frame %d colours" % f
+        assert 25000 < (oids >= 0).sum() < 40000
+    assert np.array_equal(p.obj.matrix().view(np.uint32), mats[598].view(np.uint32))
+    p.close()
+
+
+def test_buddha_standin_4k_late_frame_and_dense_frame_against_oracle(gpu, orc):
+    """C4: frame 359 of the 4K orbit, and a 4K frame at ~64 % coverage (the close-up), against the oracle."""
+    pts = gpu.geodesic_mesh(233)
+    W, H = 3840, 2160
+    p = Pair(gpu, orc, pts, W, H)
+    mats = _orbit_matrices(gpu, W, H, 359)
+    s = None
+    import torch
+    d_col = torch.empty(W * H, dtype=torch.int32, device="cuda"); d_ids = torch.empty(W * H, dtype=torch.int32, device="cuda")
+    p.obj.render_frames_device_async(p.cam, mats[358], d_col.data_ptr(), d_ids.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    oids, obgra = p.ref.render(m12=mats[358])
+    assert np.array_equal(d_ids.cpu().numpy().astype(np.int64), oids)
+    assert np.array_equal(d_col.cpu().numpy().view(np.uint32), obgra)
+    n = p.cam.basis()[0:3]
+    for _ in range(140):
+        p.transform(gpu.TRANSLATE_Z, (float(n[0]), float(n[1]), float(n[2]), 0.005))
+    ids, _, _, _ = p.check()
+    assert (ids >= 0).mean() > 0.6
+    p.close()

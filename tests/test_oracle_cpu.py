@@ -172,6 +172,67 @@ def test_oracle_equals_reference_build_when_present(orc, rtb):
         assert np.array_equal(rids, ids) and np.array_equal(rbgra, bgra)
 
 
+def test_reference_two_object_sequence_equals_one_object(orc, rtb):
+    """WinMain.cpp:152-156 registers TWO objects over the mesh and transforms / renders the first (:188, :212).  In the
+    reference's own kernels that sequence draws exactly what a single object draws (the second add_object overwrites
+    the camera-side arrays with identical ones, Camera.cpp:156,206): the oracle scene is the one-object scene."""
+    from oracle import refemu
+    if not refemu.available():
+        pytest.skip("oracle/_ref/libref_emu.so not built (no /root/reference here)")
+    pts = rtb.geodesic_mesh(8)
+    W, H = 160, 90
+    two = refemu.RefScene(W, H, cam12(W, H), points9=pts, objects=2)
+    s = orc.Scene(pts, W, H, cam12(W, H))
+    moved = 0
+    for k in range(5):
+        if k:
+            two.transform(10, 0.0, 0.09950371902099893, 0.0, 0.9950371902099893)
+            s.transform(10, 0.0, 0.09950371902099893, 0.0, 0.9950371902099893)
+        ids2, bgra2 = two.render()
+        ids, bgra = s.render()
+        assert np.array_equal(ids2, ids) and np.array_equal(bgra2, bgra), "frame %d" % k
+        if k:
+            moved += int((ids != prev).sum())
+        prev = ids
+    assert moved > 0  # the R key really moves the picture
+    refemu.RefScene(W, H, cam12(W, H), points9=pts[:4], objects=1)  # (leaves the driver in its one-object default)
+
+
+def test_600_step_orbit_recurrence_matches_reference(orc, rtb):
+    """BASELINE.json configs[2]: 600 R-key steps.  The quaternion is never renormalised (vector.cpp:38-65), so the matrix
+    drifts; the product's host recurrence (rtb::Transform, the matrices every sweep frame is rendered with), the C
+    restatement and -- where built -- the reference's own Object::transform (Camera.cu:288-329) must agree bit for bit
+    on every one of the 600 steps, and through a block of translations afterwards."""
+    from oracle import refemu
+    pts = rtb.geodesic_mesh(2)
+    W, H = 32, 18
+    ref = refemu.RefScene(W, H, cam12(W, H), points9=pts) if refemu.available() else None
+    x = orc.Xform([0.0, 0.1, -1.0])
+    mesh = rtb.Trixel(pts, require_device=False)
+    q = (0.0, 0.09950371902099893, 0.0, 0.9950371902099893)
+    from cpp_cuda_raytracer_dev_b200 import lib as L
+    import ctypes as C
+    # the product's recurrence without a GPU: rtb_transform_sequence_host (host only)
+    ops = np.zeros((640, 5), np.float32)
+    ops[:600] = (10,) + q
+    ops[600:620] = (32, 0.0, 0.0, 1.0, 0.005)
+    ops[620:640] = (11, 0.0, -0.09950371902099893, 0.0, 0.9950371902099893)
+    got = np.empty((640, 12), np.float32)
+    pos = np.array([0.0, 0.1, -1.0], np.float32)
+    assert L.rtb_transform_sequence_host(pos.ctypes.data, 640, ops.ctypes.data, got.ctypes.data) == 0
+    for k in range(640):
+        op = ops[k]
+        x.apply(int(op[0]), float(op[1]), float(op[2]), float(op[3]), float(op[4]))
+        assert np.array_equal(x.matrix().view(np.uint32), got[k].view(np.uint32)), "step %d (oracle vs product)" % k
+        if ref is not None:
+            ref.transform(int(op[0]), float(op[1]), float(op[2]), float(op[3]), float(op[4]))
+            assert np.array_equal(ref.matrix().view(np.uint32), got[k].view(np.uint32)), "step %d (reference vs product)" % k
+    # the drift is real: after 600 steps the rotation part is off orthonormality by several float epsilons (measured 5.7e-7)
+    R = got[599].reshape(3, 4)[:, :3].astype(np.float64)
+    assert np.abs(R @ R.T - np.eye(3)).max() > 2.0 ** -22
+    mesh.close()
+
+
 def test_arithmetic_edge_cases_match_reference_golden(orc):
     """Rays with exactly zero direction components (1/0, 0*inf, 0/0 in the slab test), zero-thickness boxes, coincident
     and degenerate triangles, quarter-turn rotations, the camera plane sliding through box planes: the restatement

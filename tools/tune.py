@@ -37,8 +37,19 @@ for arg in sys.argv[1:]:
 if not grid:
     grid = {"RTB_T_ACTIVE": ["12", "16", "20", "24"], "RTB_T_LEAF": ["4", "8", "12"]}
 keys = list(grid)
+# what the traversal stack looks like on these views (untimed counter pass)
+for name in ("default", "closeup"):
+    cam.counters(reset=True)
+    obj.render_frames_device_async(cam, views[name][:8], col.data_ptr(), ids.data_ptr(), st.cuda_stream, flags=rtb.RENDER_COUNTERS)
+    torch.cuda.synchronize()
+    c = cam.counters(reset=True)
+    print("%s: per ray nodes %.2f tris %.2f hits %.3f  deepest stack: mean %.2f max %d" % (
+        name, c["nodes"] / c["rays"], c["tris"] / c["rays"], c["hits"] / c["rays"], c["stack_depth_sum"] / c["rays"], c["stack_depth_max"]))
+print("lib:", rtb.LIB_PATH)
 print("%-36s %18s %18s" % ("setting", "default mean/min ms", "closeup mean/min ms"))
 for combo in itertools.product(*[grid[k] for k in keys]):
-    for k, v in zip(keys, combo): os.environ[k] = v
+    for k, v in zip(keys, combo): rtb.set_knob(k[4:].lower(), int(v))
+    if any(k.startswith("RTB_L2_") for k in keys):
+        cam.add_object(obj)  # the L2 window is chosen when an object is added
     a = measure(views["default"]); b = measure(views["closeup"])
     print("%-36s %8.3f /%8.3f %8.3f /%8.3f" % (" ".join("%s=%s" % (k[4:], v) for k, v in zip(keys, combo)), a[0], a[1], b[0], b[1]), flush=True)
