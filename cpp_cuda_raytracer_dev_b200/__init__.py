@@ -34,7 +34,8 @@ EXPORTS = [
     "rtb_mesh_get_tree", "rtb_mesh_save_tree", "rtb_mesh_load_tree", "rtb_write_frame", "rtb_mesh_build_seconds", "rtb_mesh_destroy", "rtb_camera_create", "rtb_camera_get_basis",
     "rtb_camera_add_object", "rtb_camera_color_pixels", "rtb_camera_host_color", "rtb_camera_host_ids",
     "rtb_camera_counters", "rtb_camera_counters_ex", "rtb_camera_destroy", "rtb_object_create", "rtb_object_transform", "rtb_object_get_matrix",
-    "rtb_object_set_matrix", "rtb_object_destroy", "rtb_object_render", "rtb_render_frame", "rtb_render_sweep",
+    "rtb_object_set_matrix", "rtb_object_destroy", "rtb_object_render", "rtb_render_frame", "rtb_camera_set_lights", "rtb_camera_set_shadows", "rtb_camera_set_sample_rate", "rtb_camera_object_id_base",
+    "rtb_camera_render_scene", "rtb_camera_render_scene_device_async", "rtb_render_sweep",
     "rtb_render_frames_device_async", "rtb_render_frames_push_async", "rtb_render_frames_push_striped_async", "rtb_fill_frames_device_async", "rtb_peer_alloc", "rtb_peer_free", "rtb_peer_export", "rtb_peer_open", "rtb_peer_close", "rtb_peer_read", "rtb_object_transform_host", "rtb_transform_sequence_host", "rtb_device_props", "rtb_launch_count", "rtb_tile_major_elements", "rtb_compose_tiles_device_async", "rtb_selftest_exact", "rtb_measure_l2_read_bandwidth",
 ]
 
@@ -94,6 +95,13 @@ def _load():
     L.rtb_object_destroy.restype = None
     L.rtb_object_render.argtypes = [vp, vp, C.c_uint32]
     L.rtb_render_frame.argtypes = [vp, vp, C.c_uint32]
+    L.rtb_camera_set_lights.argtypes = [vp, C.c_int32, vp]
+    L.rtb_camera_set_shadows.argtypes = [vp, C.c_int32]
+    L.rtb_camera_set_sample_rate.argtypes = [vp, C.c_int32]
+    L.rtb_camera_object_id_base.argtypes = [vp, vp]
+    L.rtb_camera_object_id_base.restype = C.c_int64
+    L.rtb_camera_render_scene.argtypes = [vp, C.c_uint32]
+    L.rtb_camera_render_scene_device_async.argtypes = [vp, C.c_uint32, vp, vp, vp]
     L.rtb_render_sweep.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, C.c_uint32, vp, vp]
     L.rtb_render_frames_device_async.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_uint32, vp, vp, vp]
     L.rtb_device_props.argtypes = [vp]
@@ -289,6 +297,36 @@ class Camera:
         arr = (C.c_void_p * len(part_ptrs))(*part_ptrs)
         _check(lib.rtb_compose_tiles_device_async(self.h, num_frames, len(part_ptrs), arr, out_ptr, stream_ptr or None),
                "rtb_compose_tiles_device_async")
+
+    # ---- scene extension (include/rtb.h: lights, shadows, sample_rate, several objects) ----
+    def set_lights(self, xyz):
+        a = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        _check(lib.rtb_camera_set_lights(self.h, a.shape[0], a.ctypes.data), "rtb_camera_set_lights")
+
+    def set_shadows(self, enable):
+        _check(lib.rtb_camera_set_shadows(self.h, int(bool(enable))), "rtb_camera_set_shadows")
+
+    def set_sample_rate(self, n):
+        _check(lib.rtb_camera_set_sample_rate(self.h, int(n)), "rtb_camera_set_sample_rate")
+
+    def object_id_base(self, obj):
+        return int(lib.rtb_camera_object_id_base(self.h, obj.h))
+
+    def render_scene(self, flags=RENDER_DEFAULT):
+        """Camera::render(): every object added to this camera -> the camera's device frame (then color_pixels)."""
+        _check(lib.rtb_camera_render_scene(self.h, flags), "rtb_camera_render_scene")
+
+    def render_scene_frame(self, flags=RENDER_DEFAULT):
+        """render_scene + color_pixels(PHONG); returns copies of (ids int32, colour uint32)."""
+        self.render_scene(flags)
+        self.color_pixels(PHONG_COLOR_TAG)
+        return self.h_ids().copy(), self.h_color().copy()
+
+    def render_scene_device_async(self, d_bgra_ptr, d_ids_ptr, stream_ptr=None, flags=RENDER_DEFAULT):
+        if stream_ptr == 0:
+            stream_ptr = 1  # cudaStreamLegacy
+        _check(lib.rtb_camera_render_scene_device_async(self.h, flags, d_bgra_ptr or None, d_ids_ptr or None, stream_ptr or None),
+               "rtb_camera_render_scene_device_async")
 
     def counters(self, reset=True):
         out = np.zeros(8, np.uint64)

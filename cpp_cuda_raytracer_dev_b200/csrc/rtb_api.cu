@@ -14,10 +14,16 @@
 #include "rtb_host.hpp"
 #include "rtb_kernels.cuh"
 #include "rtb_render.cuh"
+#include "rtb_scene.cuh"
 
 namespace {
 
 std::atomic<uint64_t> g_launches{0};
+#ifdef RTB_WARP_LOG
+constexpr size_t kCounterWords = 16 + 8 * 8192;  // development builds: 8 words per warp behind the counters (rtb_camera_warp_log)
+#else
+constexpr size_t kCounterWords = 8;
+#endif
 thread_local std::string g_error;
 thread_local int g_device = 0;
 
@@ -101,6 +107,11 @@ struct rtb_camera {
     std::vector<rtb_object*> objects;   // every object currently added to this camera (Camera::object_list)
     int sm_count = 0;
     int blocks_per_sm[16] = {0};  // occupancy of the render kernel variants, asked once
+    // scene extension (rtb_camera_render_scene): the light list, the shadow test and sample_rate the reference leaves dormant
+    int num_lights = 1;
+    float lights[rtb::kMaxSceneLights][3] = {{2.0f, 2.0f, 2.0f}};  // Camera.cu:32
+    bool shadows = false;
+    int sample_rate = 0;          // Camera::render_properites::sample_rate (Camera.h:46, Camera.cpp:71)
     bool frame_rendered = false;  // the device frame holds a render (background + shaded hits of every pixel)
     bool frame_on_host = false;   // ... and h_bgra / h_ids hold that very frame already
 };
@@ -142,6 +153,7 @@ struct Knobs {
     int reserve_sms = 0;  // SMs left free beside the persistent kernel
     int l2_window = 1;    // persisting L2 window: 0 off, 1 node records, 2 nodes + triangles (takes effect at add_object)
     int no_rect = 0;      // 1: frame records carry the whole frame as the root-box rectangle
+    int l2_carve_mb = 0;  // persisting L2 carve-out in MB, 0 = the size of the window
 };
 Knobs& knobs() {
     static Knobs k = [] {
@@ -149,7 +161,7 @@ Knobs& knobs() {
         v.unit_shift = env_int("RTB_UNIT_SHIFT", v.unit_shift); v.t_active = env_int("RTB_T_ACTIVE", v.t_active);
         v.t_leaf = env_int("RTB_T_LEAF", v.t_leaf); v.tail5 = env_int("RTB_TAIL5", v.tail5); v.tail6 = env_int("RTB_TAIL6", v.tail6);
         v.reserve_sms = env_int("RTB_RESERVE_SMS", v.reserve_sms); v.l2_window = env_int("RTB_L2_WINDOW", v.l2_window);
-        v.no_rect = env_int("RTB_NO_RECT", v.no_rect);
+        v.no_rect = env_int("RTB_NO_RECT", v.no_rect); v.l2_carve_mb = env_int("RTB_L2_CARVE_MB", v.l2_carve_mb);
         return v;
     }();
     return k;
@@ -445,6 +457,7 @@ int rtb_set_knob(const char* name, int value) {
     else if (n == "reserve_sms") k.reserve_sms = value;
     else if (n == "l2_window") k.l2_window = value;
     else if (n == "no_rect") k.no_rect = value;
+    else if (n == "l2_carve_mb") k.l2_carve_mb = value;
     else return fail(RTB_ERR_ARG, "set_knob: unknown knob " + n);
     return RTB_OK;
 }
@@ -604,8 +617,8 @@ int rtb_camera_create(int32_t r_w, int32_t r_h, float f_w, float f_h, float fcle
     if (e == cudaSuccess) e = cudaMalloc(&c->d_ids, sizeof(int32_t) * (size_t)c->pixels);
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_bgra, sizeof(uint32_t) * (size_t)c->pixels);
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_ids, sizeof(int32_t) * (size_t)c->pixels);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 8);
-    if (e == cudaSuccess) e = cudaMemset(c->d_counters, 0, sizeof(unsigned long long) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_counters, sizeof(unsigned long long) * kCounterWords);
+    if (e == cudaSuccess) e = cudaMemset(c->d_counters, 0, sizeof(unsigned long long) * kCounterWords);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     for (int k = 0; k < 2 && e == cudaSuccess; k++) {
@@ -637,10 +650,15 @@ int rtb_camera_get_basis(const rtb_camera* cam, float out18[18]) {
 }
 
 namespace {
-// L2 residency (the 800k-triangle dragon fits the B200's L2).  The persisting window is
-// attached to every render launch (launch_render).  Measured on the dragon stand-in (873 620 triangles, 600-frame
-// launches): a window over nodes + triangles (98 MB against a 79 MB carve-out, hit ratio 0.81) changes nothing
-// (12.95 ms vs 12.89 ms without), a window over the node records alone (56 MB, hit ratio 1) gives 11.9 ms.
+// L2 residency (the 800k-triangle dragon fits the B200's L2).  A persisting access-policy window
+// over the NODE records is attached to every render launch (launch_render), and the device's persisting carve-out is set
+// to exactly their size.  Measured on the dragon stand-in (873 620 triangles: 56 MB of nodes + 42 MB of triangles,
+// 600-frame launches, 126 MB L2 of which at most 79 MB may persist):
+//     no window                                            12.89 ms
+//     nodes + triangles, carve-out 79 MB, hit ratio 0.81   12.95 ms   (round 1)
+//     nodes only,        carve-out 79 MB                   12.94 ms   (the carve-out starves triangles, stack and frames)
+//     nodes only,        carve-out 56 MB = the window      11.90 ms
+// Knob l2_window: 0 off, 1 node records (default), 2 nodes + triangles; l2_carve_mb > 0 forces the carve-out size.
 void choose_l2_window(const rtb_camera* cam, SceneArrays* sc) {
     sc->l2_window_bytes = 0;
     const int mode = knobs().l2_window;
@@ -649,13 +667,13 @@ void choose_l2_window(const rtb_camera* cam, SceneArrays* sc) {
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cam->device);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, cam->device);
     if (max_persist > 0 && max_window > 0) {
-        const size_t span = mode == 2 ? sc->scene_bytes : sc->node_bytes;
-        size_t limit = 0;
-        cudaDeviceGetLimit(&limit, cudaLimitPersistingL2CacheSize);
-        if (limit >= (size_t)max_persist || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess) {
+        const size_t span = std::min<size_t>(mode == 2 ? sc->scene_bytes : sc->node_bytes, (size_t)max_window);
+        size_t carve = std::min<size_t>(span, (size_t)max_persist);
+        if (knobs().l2_carve_mb > 0) carve = std::min<size_t>((size_t)knobs().l2_carve_mb << 20, (size_t)max_persist);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
             sc->l2_window_base = sc->d_scene;
-            sc->l2_window_bytes = std::min<size_t>(span, (size_t)max_window);
-            sc->l2_hit_ratio = (float)std::min(1.0, (double)max_persist / (double)sc->l2_window_bytes);
+            sc->l2_window_bytes = span;
+            sc->l2_hit_ratio = (float)std::min(1.0, (double)carve / (double)span);
         }
     }
     cudaGetLastError();
@@ -833,6 +851,16 @@ static int read_counters(rtb_camera* cam, uint64_t* out, int count, int reset) {
     if (reset) RTB_CUDA(cudaMemset(cam->d_counters, 0, sizeof h));
     return RTB_OK;
 }
+#ifdef RTB_WARP_LOG
+// development builds only: the per-warp log of the last launch (8 words per warp, see rtb_render.cuh)
+int rtb_camera_warp_log(rtb_camera* cam, uint64_t* out, int warps) {
+    if (!cam || !out || warps < 1 || warps > 8192) return fail(RTB_ERR_ARG, "warp_log: bad argument");
+    RTB_CUDA(cudaSetDevice(cam->device));
+    RTB_CUDA(cudaDeviceSynchronize());
+    RTB_CUDA(cudaMemcpy(out, cam->d_counters + 16, sizeof(unsigned long long) * 8 * (size_t)warps, cudaMemcpyDeviceToHost));
+    return RTB_OK;
+}
+#endif
 int rtb_camera_counters(rtb_camera* cam, uint64_t out5[5], int reset) { return read_counters(cam, out5, 5, reset); }
 int rtb_camera_counters_ex(rtb_camera* cam, uint64_t out8[8], int reset) { return read_counters(cam, out8, 8, reset); }
 
@@ -951,6 +979,88 @@ int rtb_object_render(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
     // Camera::color_pixels brings it to the host, which is where this library synchronises -- once per frame.
     return render_current(obj, cam, flags);
 }
+
+// ---- scene extension: SURVEY.md section 8(f) items 3-4 (csrc/rtb_scene.cuh) ------------------------------
+int rtb_camera_set_lights(rtb_camera* cam, int32_t num_lights, const float* xyz3) {
+    if (!cam || num_lights < 1 || num_lights > rtb::kMaxSceneLights || !xyz3) return fail(RTB_ERR_ARG, "set_lights: 1..8 lights");
+    cam->num_lights = num_lights;
+    std::memcpy(cam->lights, xyz3, sizeof(float) * 3 * (size_t)num_lights);
+    return RTB_OK;
+}
+int rtb_camera_set_shadows(rtb_camera* cam, int32_t enable) {
+    if (!cam) return fail(RTB_ERR_ARG, "set_shadows: null camera");
+    cam->shadows = enable != 0;
+    return RTB_OK;
+}
+int rtb_camera_set_sample_rate(rtb_camera* cam, int32_t n) {
+    if (!cam || n < 0 || n > 16) return fail(RTB_ERR_ARG, "set_sample_rate: 0..16");
+    cam->sample_rate = n;
+    return RTB_OK;
+}
+int64_t rtb_camera_object_id_base(const rtb_camera* cam, const rtb_object* obj) {
+    if (!cam || !obj) return -1;
+    int64_t base = 0;
+    for (const rtb_object* o : cam->objects) {
+        if (o == obj) return base;
+        base += o->scene->num_tri;
+    }
+    return -1;
+}
+
+int rtb_camera_render_scene_device_async(rtb_camera* cam, uint32_t flags, uint32_t* d_bgra, int32_t* d_ids, void* stream) {
+    if (!cam || !cam->d_bgra) return fail(RTB_ERR_CUDA, "render_scene: camera has no device memory");
+    if (cam->objects.empty()) return fail(RTB_ERR_STATE, "render_scene: no object was added to this camera (rtb_camera_add_object)");
+    if ((int)cam->objects.size() > rtb::kMaxSceneObjects) return fail(RTB_ERR_ARG, "render_scene: at most 8 objects per camera");
+    if (flags & ~(uint32_t)RTB_RENDER_NO_CULL) return fail(RTB_ERR_ARG, "render_scene: only RTB_RENDER_NO_CULL is understood here");
+    RTB_CUDA(cudaSetDevice(cam->device));
+    using namespace rtb;
+    SceneParams P;
+    std::memset(&P, 0, sizeof P);
+    const CameraBasis& b = cam->basis;
+    P.W = b.W; P.H = b.H;
+    for (int k = 0; k < 3; k++) { P.n_mod[k] = b.n_mod[k]; P.u_mod[k] = b.u_mod[k]; P.v_mod[k] = b.v_mod[k]; }
+    P.draw_distance = b.draw_distance;
+    P.background = ((uint32_t)b.background[3] << 24) | ((uint32_t)b.background[0] << 16) | ((uint32_t)b.background[1] << 8) | b.background[2];
+    P.num_objects = (int)cam->objects.size();
+    int64_t base = 0;
+    for (int k = 0; k < P.num_objects; k++) {
+        const rtb_object* o = cam->objects[(size_t)k];
+        const SceneArrays* sc = o->scene;
+        SceneObject& O = P.obj[k];
+        O.nodes = sc->d_nodes; O.tris = sc->d_tris; O.rad = sc->d_rad;
+        for (int c = 0; c < 3; c++) O.uniform_rad[c] = sc->uniform_rgb[c];
+        for (int c = 0; c < 6; c++) O.root_box[c] = sc->root_box[c];
+        O.root_ref = sc->root_ref;
+        if (base + sc->num_tri > 0x7fffffff) return fail(RTB_ERR_ARG, "render_scene: more than 2^31 triangles in the scene");
+        O.id_base = (int)base;
+        base += sc->num_tri;
+        o->xf.matrix(O.m);
+    }
+    P.num_lights = cam->num_lights;
+    std::memcpy(P.lights, cam->lights, sizeof P.lights);
+    P.shadows = cam->shadows ? 1 : 0;
+    P.samples = cam->sample_rate >= 2 ? cam->sample_rate : 1;
+    P.cull = (flags & RTB_RENDER_NO_CULL) ? 0 : 1;
+    P.cull_rel = 1e-5f;
+    const bool own = !d_bgra && !d_ids;
+    P.out_bgra = own ? cam->d_bgra : d_bgra;
+    P.out_ids = own ? cam->d_ids : d_ids;
+    cudaStream_t s = stream ? (cudaStream_t)stream : cam->stream;
+    // the objects' own launches (rtb_object_render ...) may still be writing the camera's frame on other streams
+    for (rtb_object* o : cam->objects) { const int rc = order_after_previous(o, s); if (rc) return rc; }
+    const dim3 grid((unsigned)((b.W + 15) / 16), (unsigned)((b.H + 7) / 8));
+    render_scene_kernel<<<grid, kBlockThreads, 0, s>>>(P);
+    g_launches++;
+    RTB_CUDA(cudaGetLastError());
+    for (rtb_object* o : cam->objects) {  // later launches of these objects are ordered behind this one
+        RTB_CUDA(cudaEventRecord(o->ev_launch, s));
+        o->launch_pending = true;
+        o->last_stream = s;
+    }
+    if (own) { cam->frame_rendered = true; cam->frame_on_host = false; }
+    return RTB_OK;
+}
+int rtb_camera_render_scene(rtb_camera* cam, uint32_t flags) { return rtb_camera_render_scene_device_async(cam, flags, nullptr, nullptr, nullptr); }
 
 int rtb_render_frame(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
     const int rc = rtb_object_render(obj, cam, flags);

@@ -106,6 +106,13 @@ public:
     }
     ~Camera() { rtb_camera_destroy(handle); }
     int add_object(Object* o) { return rtb_camera_add_object(handle, o->handle); }  // Camera.cpp:118
+    // Camera::render() (Camera.cpp:160-163, a stub in the reference): every object of object_list in one frame, with the
+    // light list, shadow test and sample_rate the reference leaves dormant (include/rtb.h, scene extension)
+    int render() { return rtb_camera_render_scene(handle, RTB_RENDER_DEFAULT); }
+    struct render_properites { int sample_rate = 0; } r_prop;                          // Camera.h:44-48
+    int set_sample_rate(int n) { r_prop.sample_rate = n; return rtb_camera_set_sample_rate(handle, n); }
+    int set_lights(int n, const float* xyz3) { return rtb_camera_set_lights(handle, n, xyz3); }
+    int set_shadows(bool on) { return rtb_camera_set_shadows(handle, on ? 1 : 0); }
     int color_pixels(u8 tag) {                                                       // Camera.cpp:229
         const int rc = rtb_camera_color_pixels(handle, tag);
         refresh();

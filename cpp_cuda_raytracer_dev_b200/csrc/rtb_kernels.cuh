@@ -279,12 +279,6 @@ __global__ void l2_read_kernel(const uint4* __restrict__ buf, long long n16, int
 // ---------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
-// the same read-only 16-byte load carrying an L2 eviction policy made by createpolicy (evict_last: scene records)
-__device__ __forceinline__ float4 ldg4_keep(const float4* p, unsigned long long policy) {
-    float4 v;
-    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy));
-    return v;
-}
 
 // Moller-Trumbore, Trixel.cu:98-145.  Returns true and updates best/id on acceptance.
 __device__ __forceinline__ bool moller_trumbore(const Ray& r, const float4* __restrict__ tris, int tri, float& best, int& id) {

@@ -166,19 +166,6 @@ __global__ void selftest_exact_kernel(uint64_t seed, long long count, unsigned l
 #ifndef RTB_MIN_BLOCKS
 #define RTB_MIN_BLOCKS 8
 #endif
-// RTB_STACK_PACKED 1: a stack entry is one 16-byte local-memory word (ref, tmin, tmax, -): one LDL.128 / STL.128 per pop /
-// push instead of three 4-byte accesses to three arrays.
-#ifndef RTB_STACK_PACKED
-#define RTB_STACK_PACKED 0
-#endif
-// RTB_LOOP_REDUX 1: the three ballots + popcounts that steer a traversal iteration become one warp-wide integer sum
-#ifndef RTB_LOOP_REDUX
-#define RTB_LOOP_REDUX 0
-#endif
-// RTB_NODE_LOAD_HINT 1: node records are loaded with an L2 evict_last policy (createpolicy), frames are written evict_first
-#ifndef RTB_NODE_LOAD_HINT
-#define RTB_NODE_LOAD_HINT 0
-#endif
 #ifndef RTB_MIN_BLOCKS_PUSH
 #define RTB_MIN_BLOCKS_PUSH 7  // the push variant carries more warp state: 72 registers spill nothing
 #endif
@@ -188,6 +175,11 @@ template <bool CULL, bool COUNT, bool PUSH, bool INLINE = false>
 __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RTB_MIN_BLOCKS) render_stream_kernel(const RenderParams P) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanemask_lt = (1u << lane) - 1u;
+#ifdef RTB_WARP_LOG  // development builds only (tools/warp_log.py): what every warp did and when, in nanoseconds
+    unsigned long long wl_t0, wl_first_work = 0, wl_exhausted = 0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(wl_t0));
+    unsigned wl_units = 0, wl_bg_units = 0, wl_iters = 0, wl_rays = 0;
+#endif
     __shared__ int s_owed[PUSH ? kBlockThreads / 32 : 1][PUSH ? kPushSlots : 1];   // pixels of an open unit not yet written
     __shared__ int4 s_unit[PUSH ? kBlockThreads / 32 : 1][PUSH ? kPushSlots : 1];  // frame, tile slot, x and y offset inside the tile
     const int wib = threadIdx.x >> 5;
@@ -200,27 +192,11 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
     // Traversal stack: the top entry lives in registers (top_*), deeper entries in local memory.
     // A pop hands out the register copy at once and re-loads the new top in the background, so the
     // memory latency of the stack is off the dependent chain.
-#if RTB_STACK_PACKED
-    float4 stk[kStackDepth];
-#else
     int stk_ref[kStackDepth];
     float stk_tmin[kStackDepth], stk_tmax[kStackDepth];
-#endif
     int top_ref = 0;
     float top_tmin = 0.0f, top_tmax = 0.0f;
-    // entry i of this thread's stack (0 = oldest), below the register-cached top
-#if RTB_STACK_PACKED
-#define RTB_STACK_LOAD(i, ref, tmin, tmax) do { const float4 e_ = stk[i]; ref = __float_as_int(e_.x); tmin = e_.y; tmax = e_.z; } while (0)
-#define RTB_STACK_STORE(i, ref, tmin, tmax) stk[i] = make_float4(__int_as_float(ref), tmin, tmax, 0.0f)
-#else
-#define RTB_STACK_LOAD(i, ref, tmin, tmax) do { ref = stk_ref[i]; tmin = stk_tmin[i]; tmax = stk_tmax[i]; } while (0)
-#define RTB_STACK_STORE(i, ref, tmin, tmax) do { stk_ref[i] = ref; stk_tmin[i] = tmin; stk_tmax[i] = tmax; } while (0)
-#endif
 
-#if RTB_NODE_LOAD_HINT
-    unsigned long long l2_keep;
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(l2_keep));
-#endif
     // ---- per-lane ray state ---------------------------------------------------------------------
     Ray r;
     r.dx = r.dy = r.dz = r.ix = r.iy = r.iz = r.fx = r.fy = r.fz = r.ox = r.oy = r.oz = 0.0f;
@@ -245,20 +221,15 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
     auto culled = [&](float tmin) -> bool { return CULL && (tmin > __fmaf_rn(P.cull_rel, fabsf(tmin), cull_base)); };
 
     for (;;) {
-#if RTB_LOOP_REDUX
-        int n_trav = __reduce_add_sync(0xffffffffu, state == kStateTraverse ? 1 : 0);
-#else
         unsigned m_trav = __ballot_sync(0xffffffffu, state == kStateTraverse);
-#endif
 
         // ================= traversal: steps until enough lanes have run dry ==========================
         // (while pixels remain, fall out to retire + refill as soon as no more than t_active lanes are
         // still traversing; once the work is exhausted, drain)
         const int keep_active = (exhausted | (PUSH && blocked)) ? 0 : P.t_active;
-#if RTB_LOOP_REDUX
-        while (n_trav > keep_active) {
-#else
         while (__popc(m_trav) > keep_active) {
+#ifdef RTB_WARP_LOG
+            wl_iters++;
 #endif
             // ---- lanes that finished a node or leaf take the stack top ------------------------------
             if (want_pop) {
@@ -266,23 +237,14 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                 else {
                     if (!culled(top_tmin)) { cur = top_ref; cur_tmin = top_tmin; cur_tmax = top_tmax; want_pop = false; }
                     sp--;
-                    if (sp > 0) RTB_STACK_LOAD(sp - 1, top_ref, top_tmin, top_tmax);
+                    if (sp > 0) { top_ref = stk_ref[sp - 1]; top_tmin = stk_tmin[sp - 1]; top_tmax = stk_tmax[sp - 1]; }
                 }
             }
             const bool ready = (state == kStateTraverse) & !want_pop;
             const bool at_leaf = ready & (cur < 0);
-#if RTB_LOOP_REDUX
-            // one warp-wide sum carries the three lane counts that steer the iteration: rays in flight (after the pops
-            // above, the only place a ray can finish), lanes waiting at a leaf, lanes ready for an interior step
-            const int votes = __reduce_add_sync(0xffffffffu, (state == kStateTraverse ? 1 : 0) | (at_leaf ? 0x100 : 0) | ((ready & !at_leaf) ? 0x10000 : 0));
-            n_trav = votes & 0xff;
-            const int n_leaf = (votes >> 8) & 0xff, n_int = votes >> 16;
-            if (n_leaf != 0 && (n_leaf >= P.t_leaf || n_int == 0)) {
-#else
             const unsigned m_ready = __ballot_sync(0xffffffffu, ready);
             const unsigned m_leaf = __ballot_sync(0xffffffffu, at_leaf);
             if (m_leaf != 0u && (__popc(m_leaf) >= P.t_leaf || m_leaf == m_ready)) {
-#endif
                 // ---- leaf step: always intersected when popped (Trixel.cu:98) -----------------------
                 if (at_leaf) {
                     if (COUNT) c_tris++;
@@ -294,11 +256,7 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                 if (COUNT) c_nodes++;
                 const float4* rec;  // P.nodes + 64 bytes * record index, as one IMAD.WIDE
                 asm("mad.wide.u32 %0, %1, 64, %2;" : "=l"(rec) : "r"((unsigned)cur & kRefIndexMask), "l"(P.nodes));
-#if RTB_NODE_LOAD_HINT
-                const float4 q0 = ldg4_keep(rec, l2_keep), q1 = ldg4_keep(rec + 1, l2_keep), q2 = ldg4_keep(rec + 2, l2_keep), q3 = ldg4_keep(rec + 3, l2_keep);
-#else
                 const float4 q0 = ldg4(rec), q1 = ldg4(rec + 1), q2 = ldg4(rec + 2), q3 = ldg4(rec + 3);
-#endif
                 const int lref = __float_as_int(q3.x), rref = __float_as_int(q3.y);
                 const float S1 = q3.z, S2 = q3.w;  // left child's max / right child's min on the split axis (Trixel.h:353-376)
                 const int axis = (lref >> kRefAxisShift) & 3;
@@ -333,7 +291,7 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                         const bool go_first = !culled(f_eff);
                         const bool go_second = visit_second & !culled(s_eff);
                         if (go_second) {
-                            if (sp > 0) RTB_STACK_STORE(sp - 1, top_ref, top_tmin, top_tmax);
+                            if (sp > 0) { stk_ref[sp - 1] = top_ref; stk_tmin[sp - 1] = top_tmin; stk_tmax[sp - 1] = top_tmax; }
                             top_ref = left_first ? rref : lref; top_tmin = s_eff; top_tmax = left_first ? rtmax : ltmax;
                             sp++;
                             if (COUNT) ray_depth = max(ray_depth, sp);
@@ -350,7 +308,7 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                     const bool go_first = ((first < 0) | f_in) & !culled(f_tmin);
                     const bool go_second = visit_second & ((second < 0) | s_in) & !culled(s_tmin);
                     if (go_second) {
-                        if (sp > 0) RTB_STACK_STORE(sp - 1, top_ref, top_tmin, top_tmax);
+                        if (sp > 0) { stk_ref[sp - 1] = top_ref; stk_tmin[sp - 1] = top_tmin; stk_tmax[sp - 1] = top_tmax; }
                         top_ref = second; top_tmin = s_tmin; top_tmax = s_tmax;
                         sp++;
                         if (COUNT) ray_depth = max(ray_depth, sp);
@@ -365,13 +323,8 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                     descend((ex & 1) != 0, (ex & 2) != 0, (ex & 4) != 0, (ex & 8) != 0);
                 }
             }
-#if !RTB_LOOP_REDUX
             m_trav = __ballot_sync(0xffffffffu, state == kStateTraverse);
-#endif
         }
-#if RTB_LOOP_REDUX
-        const unsigned m_trav = __ballot_sync(0xffffffffu, state == kStateTraverse);
-#endif
 
         // ================= retire: Phong + store for finished rays ===================================
         if (state == kStateDone) {
@@ -403,7 +356,16 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                 unsigned long long uid = 0;
                 if (lane == 0) uid = atomicAdd(P.work_counter, 1ull) - P.work_base;
                 uid = __shfl_sync(0xffffffffu, uid, 0);
-                if ((long long)uid >= P.total_items) { exhausted = true; break; }
+                if ((long long)uid >= P.total_items) {
+                    exhausted = true;
+#ifdef RTB_WARP_LOG
+                    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(wl_exhausted));
+#endif
+                    break;
+                }
+#ifdef RTB_WARP_LOG
+                wl_units++;
+#endif
                 // which segment of the launch (unit size), which frame, which tile, which block of the tile
                 long long item = (long long)uid;
                 int frame0 = 0;
@@ -439,6 +401,9 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                     const int wshift = unit_wshift(u_shift);  // a unit is a (1 << wshift) x (unit_pixels >> wshift) pixel block
                     const int bx = u_x0 + xoff, by = u_y0 + yoff;
                     if (bx > u_rx1 || bx + (1 << wshift) - 1 < u_rx0 || by > u_ry1 || by + (unit_pixels >> wshift) - 1 < u_ry0) {
+#ifdef RTB_WARP_LOG
+                        wl_bg_units++;
+#endif
                         if (PUSH && P.push_skip_background) continue;  // the frame's owner has pre-filled it: nothing to send
                         const int owner = PUSH ? u_frame % P.push_owners : 0;
                         uint32_t* __restrict__ dc = PUSH ? P.push_bgra[owner] : P.out_bgra;
@@ -465,6 +430,9 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                     }
                 }
                 u_next = 0;
+#ifdef RTB_WARP_LOG
+                if (wl_first_work == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(wl_first_work));
+#endif
                 if (PUSH) {
                     u_pslot = __ffs(~open_mask) - 1;
                     open_mask |= 1u << u_pslot;
@@ -524,6 +492,9 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                         sp = 0;
                         want_pop = false;
                         if (COUNT) c_rays++;
+#ifdef RTB_WARP_LOG
+                        wl_rays++;
+#endif
                         if (CULL) {
                             const float bx = fmaxf(fabsf(P.root_box[0]), fabsf(P.root_box[3]));
                             const float by = fmaxf(fabsf(P.root_box[1]), fabsf(P.root_box[4]));
@@ -591,6 +562,20 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
         }
         if (exhausted && m_trav == 0u) break;  // nothing in flight, nothing left to fetch
     }
+#ifdef RTB_WARP_LOG
+    {
+        unsigned long long wl_t1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(wl_t1));
+        wl_rays = __reduce_add_sync(0xffffffffu, wl_rays);
+        if (lane == 0 && P.counters) {  // log lives behind the counters: 8 words per warp from counters[16]
+            unsigned long long* L = P.counters + 16 + 8ull * ((unsigned long long)blockIdx.x * (kBlockThreads / 32) + wib);
+            unsigned smid;
+            asm("mov.u32 %0, %smid;" : "=r"(smid));
+            L[0] = wl_t0; L[1] = wl_t1; L[2] = wl_first_work; L[3] = wl_exhausted;
+            L[4] = ((unsigned long long)wl_units << 32) | wl_bg_units; L[5] = ((unsigned long long)wl_iters << 32) | wl_rays; L[6] = smid; L[7] = 0;
+        }
+    }
+#endif
 
     if (COUNT) {
         for (int s = 16; s > 0; s >>= 1) {

@@ -2,6 +2,7 @@
 //
 //   rtb_render --mesh FILE|geodesic:NU [--mode 0|1|2|-1] [--res WxH] [--frames N] [--zoom K]
 //              [--rotate X,Y,Z,W] [--out PREFIX] [--png] [--cam px,py,pz,lx,ly,lz,ux,uy,uz] [--sweep]
+//              [--objects N] [--shadows] [--samples n] [--light x,y,z]...   (scene extension: Camera::render())
 //
 // Same call sequence as the reference app: Camera(...) -> read_ply -> colour table -> Trixel ->
 // set_sorted_voxels -> create_kd -> Object -> add_object -> per frame { [transform]; render;
@@ -24,7 +25,9 @@ static double now_s() { return std::chrono::duration<double>(std::chrono::steady
 int main(int argc, char** argv) {
     std::string mesh = "geodesic:64", out;
     int mode = 0, W = 960, H = 540, frames = 1, zoom = 0;
-    bool sweep = false, png = false;
+    bool sweep = false, png = false, shadows = false;
+    int objects = 1, samples = 0;
+    std::vector<float> lights;
     float quat[4] = {0.0f, 0.09950371902099893f, 0.0f, 0.9950371902099893f};  // WinMain.cpp:187 (R key)
     float cam[9] = {0.0f, 0.10f, -1.0f, 0.0f, 0.10f, 0.0f, 0.0f, 1.0f, 0.0f};  // WinMain.cpp:71-73
     for (int i = 1; i < argc; i++) {
@@ -38,6 +41,10 @@ int main(int argc, char** argv) {
         else if (a == "--out") out = next();
         else if (a == "--sweep") sweep = true;
         else if (a == "--png") png = true;
+        else if (a == "--shadows") shadows = true;
+        else if (a == "--objects") objects = std::atoi(next());
+        else if (a == "--samples") samples = std::atoi(next());
+        else if (a == "--light") { float l[3] = {2, 2, 2}; std::sscanf(next(), "%f,%f,%f", &l[0], &l[1], &l[2]); lights.insert(lights.end(), l, l + 3); }
         else if (a == "--rotate") std::sscanf(next(), "%f,%f,%f,%f", &quat[0], &quat[1], &quat[2], &quat[3]);
         else if (a == "--cam") std::sscanf(next(), "%f,%f,%f,%f,%f,%f,%f,%f,%f", &cam[0], &cam[1], &cam[2], &cam[3], &cam[4], &cam[5], &cam[6], &cam[7], &cam[8]);
         else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
@@ -71,7 +78,26 @@ int main(int argc, char** argv) {
     Object* obj1 = new Object(trixel_list);
     if (main_cam->add_object(obj1) != 0) { std::fprintf(stderr, "add_object: %s\n", rtb_last_error()); return 1; }
 
+    // scene extension: WinMain.cpp:153,156 registers a second object over the same Trixel (its render is commented out, :214);
+    // here every further object is slid sideways by the Q key's translation (WinMain.cpp:198-201) so that it can be seen
+    const bool scene_mode = objects > 1 || shadows || samples > 1 || !lights.empty();
+    std::vector<Object*> more;
     Input input;
+    for (int k = 1; k < objects; k++) {
+        Object* o = new Object(trixel_list);
+        if (main_cam->add_object(o) != 0) { std::fprintf(stderr, "add_object: %s\n", rtb_last_error()); return 1; }
+        for (int step = 0; step < 12 * k; step++) {
+            input.set_quat(main_cam->o_prop.u.x, main_cam->o_prop.u.y, main_cam->o_prop.u.z, (k & 1) ? 0.012f : -0.012f);
+            o->transform(&input, TRANSLATE_X);
+        }
+        more.push_back(o);
+    }
+    if (scene_mode) {
+        if (!lights.empty() && main_cam->set_lights((int)(lights.size() / 3), lights.data()) != 0) { std::fprintf(stderr, "lights: %s\n", rtb_last_error()); return 1; }
+        main_cam->set_shadows(shadows);
+        main_cam->set_sample_rate(samples);
+        if (sweep) { std::fprintf(stderr, "--sweep renders one object with the reference's shading; drop it for --objects/--shadows/--samples/--light\n"); return 2; }
+    }
     for (int k = 0; k < zoom; k++) {  // W key, WinMain.cpp:190-193
         input.set_quat(main_cam->o_prop.n.x, main_cam->o_prop.n.y, main_cam->o_prop.n.z, 0.005f);
         obj1->transform(&input, TRANSLATE_Z);
@@ -104,7 +130,8 @@ int main(int argc, char** argv) {
                 input.set_quat(quat[0], quat[1], quat[2], quat[3]);
                 obj1->transform(&input, ROTATE_TRI_PY);
             }
-            obj1->render(main_cam);                   // WinMain.cpp:212
+            if (scene_mode) main_cam->render();       // Camera::render(): all objects, lights, shadows, samples
+            else obj1->render(main_cam);              // WinMain.cpp:212
             main_cam->color_pixels(PHONG_COLOR_TAG);  // WinMain.cpp:213
             present(f, main_cam->h_color.c, main_cam->h_color.id);
             main_cam->color_pixels(SET_COLOR_TAG);    // WinMain.cpp:237
@@ -112,6 +139,7 @@ int main(int argc, char** argv) {
         const double dt = now_s() - t0;
         std::printf("Resolution: %d x %d\nFPS: %f (frame loop of %d frames incl. PPM output)\n", W, H, frames / dt, frames);
     }
+    for (Object* o : more) delete o;
     delete obj1; delete trixel_list; delete main_cam;
     rtb_free(points_for_trixels);
     return 0;

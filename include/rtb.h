@@ -69,8 +69,8 @@ int rtb_set_device(int device);
  * the launch size), "t_active" (refill when no more lanes than this still traverse), "t_leaf" (leaf step when at least
  * this many lanes wait at a leaf), "tail5" / "tail6" (trailing frames of a launch handed out in 32- / 64-pixel units,
  * -1 = automatic), "reserve_sms" (SMs left free beside the persistent kernel), "l2_window" (persisting L2 window:
- * 0 off, 1 node records, 2 nodes + triangles; applied at the next rtb_camera_add_object), "no_rect" (1: no root-box
- * rectangle, every pixel is traced). */
+ * 0 off, 1 node records, 2 nodes + triangles; applied at the next rtb_camera_add_object), "l2_carve_mb" (persisting
+ * carve-out in MB, 0 = the size of the window), "no_rect" (1: no root-box rectangle, every pixel is traced). */
 int rtb_set_knob(const char* name, int value);
 
 /* ---- mesh input -------------------------------------------------------------------------- */
@@ -186,6 +186,32 @@ int rtb_object_render(rtb_object* obj, rtb_camera* cam, uint32_t flags);
 /* = rtb_object_render + rtb_camera_color_pixels(PHONG) with one synchronisation; the frame and the
  * id buffer are then readable through rtb_camera_host_color / rtb_camera_host_ids. */
 int rtb_render_frame(rtb_object* obj, rtb_camera* cam, uint32_t flags);
+
+/* ---- scene extension: what the reference leaves dormant around its hot path ----------
+ * The reference draws ONE object with ONE light and ONE ray per pixel.  Its code carries the stubs of more: the light loop
+ * and the shadow test of color_cam_cuda, commented out (Camera.cu:28-34, 54); Camera::render_properites::sample_rate
+ * (Camera.h:46, Camera.cpp:71), never read; a second object, created and registered but never rendered
+ * (WinMain.cpp:153,156,214-215; Camera::object_list, Camera.cpp:118-130).  There is no reference behaviour to be
+ * identical to, so DESIGN.md section 11 defines it -- the smallest completion of those stubs that leaves the default
+ * output untouched -- oracle/rtb_oracle.c (orc_render_scene) restates the definition on the CPU, and the kernel
+ * (csrc/rtb_scene.cuh) is held to it bit for bit.  With one object, the default light, no shadows and sample_rate <= 1,
+ * rtb_camera_render_scene produces exactly the frame of rtb_object_render.
+ *   lights      : 1..8 point lights, default one at (2,2,2) (Camera.cu:32); radiance is summed over them in order
+ *   shadows     : a light counts only if the segment from the hit point to it hits no other triangle of the object that
+ *                 was hit (the commented call names one triangle list: objects do not shadow one another)
+ *   sample_rate : n >= 2 casts n x n rays per pixel on a regular sub-pixel grid; the pixel is the per-channel integer
+ *                 mean of the shaded samples, its hit id that of sample (n/2, n/2)
+ *   objects     : every object added to the camera, in the order of rtb_camera_add_object; the closest hit wins, the
+ *                 first added object wins ties; hit id = rtb_camera_object_id_base(object) + triangle id.  At most 8. */
+int rtb_camera_set_lights(rtb_camera* cam, int32_t num_lights, const float* xyz3);
+int rtb_camera_set_shadows(rtb_camera* cam, int32_t enable);
+int rtb_camera_set_sample_rate(rtb_camera* cam, int32_t n);
+int64_t rtb_camera_object_id_base(const rtb_camera* cam, const rtb_object* obj);
+/* Camera::render() (Camera.cpp:160-163, a stub in the reference): all objects of the camera, each with its current
+ * transform, into the camera's device frame; follow with rtb_camera_color_pixels(PHONG).  flags: RTB_RENDER_NO_CULL. */
+int rtb_camera_render_scene(rtb_camera* cam, uint32_t flags);
+/* the same into caller-owned device buffers (W*H elements each, either may be NULL) on a caller stream */
+int rtb_camera_render_scene_device_async(rtb_camera* cam, uint32_t flags, uint32_t* d_bgra, int32_t* d_ids, void* stream);
 
 /* Batched animation sweep (WinMain.cpp:174-239 with a key held down): for frame k = 0..num_frames-1
  * apply `steps_per_frame` transforms ops[k*steps_per_frame ...] (each 5 floats: select, x, y, z, w;

@@ -56,6 +56,7 @@ def lib():
         L.orc_scene_destroy.argtypes = [vp]
         L.orc_render.argtypes = [vp, vp, ci, ci, vp, vp, vp]
         L.orc_render_bruteforce.argtypes = [vp, vp, ci, ci, vp, vp]
+        L.orc_render_scene.argtypes = [ci, vp, vp, vp, ci, vp, ci, ci, ci, ci, vp, vp]
         L.orc_fnv1a64.restype = C.c_uint64
         L.orc_fnv1a64.argtypes = [vp, C.c_size_t]
         L.orc_threads.restype = ci
@@ -164,6 +165,27 @@ class Scene:
         if self.h:
             lib().orc_scene_destroy(self.h)
             self.h = None
+
+
+DEFAULT_LIGHT = ((2.0, 2.0, 2.0),)  # Camera.cu:32
+
+
+def render_scene(scenes, mats=None, lights=DEFAULT_LIGHT, shadows=False, sample_rate=0, rows=None):
+    """The extension of SURVEY.md section 8(f) items 3-4 as defined in rtb_oracle.c (orc_render_scene): all `scenes`
+    (Scene objects made for the SAME camera, in registration order) in one frame, closest hit wins, first registered wins
+    ties; a light list, optional shadow rays, sample_rate^2 rays per pixel.  Returns (ids int64 with per-object id bases
+    added, colours uint32).  With one scene, the default light, no shadows and sample_rate <= 1 it is Scene.render()."""
+    s0 = scenes[0]
+    m = np.ascontiguousarray([sc.matrix() for sc in scenes] if mats is None else mats, np.float32).reshape(len(scenes), 12)
+    base = np.cumsum([0] + [sc.n for sc in scenes[:-1]]).astype(np.int64)
+    hs = (C.c_void_p * len(scenes))(*[sc.h for sc in scenes])
+    L3 = np.ascontiguousarray(lights, np.float32).reshape(-1, 3)
+    y0, y1 = (0, s0.H) if rows is None else rows
+    ids = np.full(s0.W * s0.H, -1, np.int64)
+    bgra = np.zeros(s0.W * s0.H, np.uint32)
+    lib().orc_render_scene(len(scenes), hs, m.ctypes.data, base.ctypes.data, L3.shape[0], L3.ctypes.data, int(bool(shadows)), int(sample_rate),
+                           y0, y1, ids.ctypes.data, bgra.ctypes.data)
+    return ids, bgra
 
     def __del__(self):
         try:

@@ -684,6 +684,215 @@ void orc_render_bruteforce(const orc_scene* s, const float* m12, int y0, int y1,
     }
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* EXTENSIONS -- SURVEY.md section 8(f) items 3 and 4: what the reference leaves dormant        */
+/* ------------------------------------------------------------------------------------------ */
+/* The reference draws ONE object with ONE light and ONE ray per pixel; its code carries the stubs of more:
+ *   - the light loop and the shadow test of color_cam_cuda, commented out (Camera.cu:28-34, 54):
+ *         for each light { sd = light - pnt; in_shadow = (-1 != device_moller_trumbore(..., sd, ...)); if (!in_shadow) phong }
+ *   - Camera::render_properites::sample_rate (Camera.h:46), never read;
+ *   - a second object, created and registered but never rendered (WinMain.cpp:153,156,214-215), for which
+ *     Camera::add_object keeps an object_list (Camera.cpp:118-130).
+ * There is no reference BEHAVIOUR to be identical to, so this section DEFINES it, as the smallest
+ * completion of those stubs that leaves today's output untouched: with one object, one light at (2,2,2), shadows off and
+ * sample_rate <= 1, orc_render_scene() is orc_render() bit for bit (tests/test_oracle_cpu.py).  "parity unpinned" applies
+ * to everything beyond that default: the GPU path is compared with THIS definition only.
+ *
+ *   objects     : every object of the camera's list is traversed in registration order with the running closest distance
+ *                 carried over; the strict `w < best` of Trixel.cu:127 then makes the closest hit win and the first
+ *                 registered object win ties.  Hit id = id_base[object] + triangle (id_base = triangles of the objects
+ *                 registered before it).  Shading uses the winning object's matrix and colours.
+ *   lights      : point_rad += phong(light) for each light in order (the commented loop), then the max-channel normalise.
+ *   shadows     : a light contributes only if the segment from the hit point to it is free: a ray from the hit point
+ *                 X = w*d - od (object space of the object that was hit) with the UNNORMALISED direction sd = light - pnt
+ *                 (the very vector the commented call passes) hits no triangle OF THAT OBJECT other than the hit triangle
+ *                 at a parameter 1e-4 < t < 1 (Moller-Trumbore with the u/v tests of Trixel.cu:127).  Objects do not
+ *                 shadow one another (the commented call names one triangle list).  All lights shadowed: radiance 0,
+ *                 0/0 in the normalise, pixel black (NaN -> 0).
+ *   sample_rate : n >= 2 casts n x n rays per pixel through (ix + (a + .5)/n - .5, iy + (b + .5)/n - .5); the pixel is the
+ *                 per-channel integer mean (floor) of the n*n shaded samples (background included); the hit id is that of
+ *                 sample (n/2, n/2), the one nearest the pixel centre. */
+
+/* Trixel.cu:41-172 for one object with the closest distance carried in/out: *best is updated and *h overwritten only when
+ * this object has a closer hit (h->id >= 0 afterwards says so; the caller resets h->id = -1 before). */
+static void trace_object(const orc_scene* s, const float* m12, const float* rmd, float* best, orc_hit* h, uint64_t* cnt) {
+    s32 stack[128];
+    int front = 0;
+    stack[0] = 0;
+    float odx = m12[3], ody = m12[7], odz = m12[11];
+    float rx = -1 * (m12[0] * -rmd[0] + m12[1] * -rmd[1] + m12[2] * -rmd[2]);
+    float ry = -1 * (m12[4] * -rmd[0] + m12[5] * -rmd[1] + m12[6] * -rmd[2]);
+    float rz = -1 * (m12[8] * -rmd[0] + m12[9] * -rmd[1] + m12[10] * -rmd[2]);
+    while (front >= 0) {
+        s32 c = stack[front--];
+        cnt[0]++;
+        const float* B = s->Bo + 6 * (size_t)c;
+        float t0x = rx > 0 ? B[0] * (1 / rx) : B[3] * (1 / rx);
+        float t1x = rx > 0 ? B[3] * (1 / rx) : B[0] * (1 / rx);
+        float t0y = ry > 0 ? B[1] * (1 / ry) : B[4] * (1 / ry);
+        float t1y = ry > 0 ? B[4] * (1 / ry) : B[1] * (1 / ry);
+        float t0z = rz > 0 ? B[2] * (1 / rz) : B[5] * (1 / rz);
+        float t1z = rz > 0 ? B[5] * (1 / rz) : B[2] * (1 / rz);
+        const u8* fl = s->flags + 3 * (size_t)c;
+        float dir = ((rx * fl[0]) + (ry * fl[1]) + (rz * fl[2]));
+        float ds = ((odx * fl[0]) + (ody * fl[1]) + (odz * fl[2]));
+        float maxt0 = fmax(t0z + odz / rz, fmax(t0x + odx / rx, t0y + ody / ry));
+        float mint1 = fmin(t1z + odz / rz, fmin(t1x + odx / rx, t1y + ody / ry));
+        if (s->is_leaf[c]) {
+            cnt[1]++;
+            mt_test(s, s->tri[c], m12, rx, ry, rz, odx, ody, odz, best, h);
+            continue;
+        }
+        if (mint1 >= maxt0 - DEV_EPS && maxt0 > -DEV_EPS) {
+            maxt0 *= dir; mint1 *= dir;
+            float s1 = s->S1[c] + DEV_EPS + ds;
+            float s2 = s->S2[c] + ds;
+            if (maxt0 < s2 + DEV_EPS) {
+                if (mint1 > s2 - DEV_EPS) stack[++front] = (s32)s->right[c];
+                stack[++front] = (s32)s->left[c];
+            } else {
+                if (mint1 < s1 || maxt0 < s1) stack[++front] = (s32)s->left[c];
+                stack[++front] = (s32)s->right[c];
+            }
+        }
+    }
+}
+
+/* Is the segment o' + t*d, 1e-4 < t < 1, blocked by a triangle of `s` other than `skip`?  The ray is handed over the way
+ * the primary ray is (Trixel.cu:60-66,112): `o` = MINUS its origin in camera-relative object coordinates, so that
+ * T = d_t - o and the slab offsets o/d are formed exactly as in the primary traversal.  A node is entered iff the segment
+ * overlaps its box: tmax >= tmin, tmax >= 0, tmin <= 1 (plain float comparisons, false for NaN); leaves are tested when
+ * reached.  Any-hit: the answer does not depend on the visit order. */
+#define SHADOW_T_MIN 1e-4f
+static int segment_blocked(const orc_scene* s, s64 skip, const float* o, const float* d) {
+    s32 stack[128];
+    int front = 0;
+    stack[0] = 0;
+    const float rx = d[0], ry = d[1], rz = d[2], odx = o[0], ody = o[1], odz = o[2];
+    while (front >= 0) {
+        s32 c = stack[front--];
+        if (s->is_leaf[c]) {
+            const s64 t = s->tri[c];
+            if (t == skip) continue;
+            const float* e1 = s->e1 + 3 * t; const float* e2 = s->e2 + 3 * t; const float* dt = s->dt + 3 * t;
+            float px, py, pz, qx, qy, qz;
+            cross3(&px, &py, &pz, rx, ry, rz, e2[0], e2[1], e2[2]);
+            float f = dot3(px, py, pz, e1[0], e1[1], e1[2]);
+            if (f < MT_EPS && f > -MT_EPS) continue;
+            float pe1 = 1.0 / f;
+            float u = pe1 * dot3(px, py, pz, dt[0] - odx, dt[1] - ody, dt[2] - odz);
+            cross3(&qx, &qy, &qz, dt[0] - odx, dt[1] - ody, dt[2] - odz, e1[0], e1[1], e1[2]);
+            float v = pe1 * dot3(rx, ry, rz, qx, qy, qz);
+            float w = pe1 * dot3(e2[0], e2[1], e2[2], qx, qy, qz);
+            if (!((u < MT_EPS) || (v < MT_EPS) || ((u + v) > 1 + MT_EPS) || (w < MT_EPS)) && w > SHADOW_T_MIN && w < 1.0f) return 1;
+            continue;
+        }
+        for (int side = 0; side < 2; side++) {
+            const s32 k = (s32)(side ? s->right[c] : s->left[c]);
+            if (!s->is_leaf[k]) {
+                const float* B = s->Bo + 6 * (size_t)k;
+                float t0x = rx > 0 ? B[0] * (1 / rx) : B[3] * (1 / rx);
+                float t1x = rx > 0 ? B[3] * (1 / rx) : B[0] * (1 / rx);
+                float t0y = ry > 0 ? B[1] * (1 / ry) : B[4] * (1 / ry);
+                float t1y = ry > 0 ? B[4] * (1 / ry) : B[1] * (1 / ry);
+                float t0z = rz > 0 ? B[2] * (1 / rz) : B[5] * (1 / rz);
+                float t1z = rz > 0 ? B[5] * (1 / rz) : B[2] * (1 / rz);
+                float tmin = fmax(t0z + odz / rz, fmax(t0x + odx / rx, t0y + ody / ry));
+                float tmax = fmin(t1z + odz / rz, fmin(t1x + odx / rx, t1y + ody / ry));
+                if (!(tmax >= tmin && tmax >= 0.0f && tmin <= 1.0f)) continue;
+            }
+            stack[++front] = k;
+        }
+    }
+    return 0;
+}
+
+/* color_cam_cuda with the light loop and the shadow test restored (Camera.cu:27-61).  d = object-space direction of the
+ * primary ray, od = the object's translation column (what Trixel.cu:134-136 built pnt from). */
+static inline u32 shade_lights(const orc_scene* s, const orc_hit* h, const float* rmd, const float* d, const float* od, int nlights,
+                               const float* lights3, int shadows) {
+    float pr = 0.0f, pg = 0.0f, pb = 0.0f;
+    for (int l = 0; l < nlights; l++) {
+        float sdx = lights3[3 * l] - h->pnt[0], sdy = lights3[3 * l + 1] - h->pnt[1], sdz = lights3[3 * l + 2] - h->pnt[2];
+        if (shadows) {
+            /* minus the hit point X = w*d - od, i.e. od - w*d */
+            const float o[3] = {od[0] - h->dist * d[0], od[1] - h->dist * d[1], od[2] - h->dist * d[2]};
+            const float sd[3] = {sdx, sdy, sdz};
+            if (segment_blocked(s, h->id, o, sd)) continue;
+        }
+        device_normalize(&sdx, &sdy, &sdz);
+        float dot_r_n = dot3(sdx, sdy, sdz, h->norm[0], h->norm[0], h->norm[2]);
+        float rx = (sdx - (2 * dot_r_n * h->norm[0])) * rmd[0];
+        float ry = (sdy - (2 * dot_r_n * h->norm[1])) * rmd[1];
+        float rz = (sdz - (2 * dot_r_n * h->norm[2])) * rmd[2];
+        float dif = .6 * fabsf(dot_r_n);
+        float spc = powf(fabsf((rx + ry + rz)), 5) * .3;
+        pr += (h->rad[0] * dif) + (1 * spc);
+        pg += (h->rad[1] * dif) + (1 * spc);
+        pb += (h->rad[2] * dif) + (1 * spc);
+    }
+    float mx = fmaxf(fmaxf(pr, pg), pb);
+    float cr = (pr / mx) * 255, cg = (pg / mx) * 255, cb = (pb / mx) * 255;
+    u32 r8 = cr == cr ? (u32)(u8)(int)cr : 0, g8 = cg == cg ? (u32)(u8)(int)cg : 0, b8 = cb == cb ? (u32)(u8)(int)cb : 0;
+    return (r8 << 16) | (g8 << 8) | b8;
+}
+
+/* One frame of a scene of `nobj` objects (scenes[k] = the camera-side arrays of object k's mesh, all made for the same
+ * camera; m12s + 12*k = its matrix; id_base[k] added to its triangle ids) with `nlights` lights, optional shadows and
+ * sample_rate^2 rays per pixel, over pixel rows [y0,y1). */
+void orc_render_scene(int nobj, const orc_scene* const* scenes, const float* m12s, const s64* id_base, int nlights, const float* lights3,
+                      int shadows, int sample_rate, int y0, int y1, s64* ids, u32* bgra) {
+    const orc_scene* s0 = scenes[0];
+    const int n = sample_rate >= 2 ? sample_rate : 1;
+    const u32 bg = ((u32)s0->bg[3] << 24) | ((u32)s0->bg[0] << 16) | ((u32)s0->bg[1] << 8) | (u32)s0->bg[2];
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int y = y0; y < y1; y++) {
+        uint64_t cnt[3] = {0, 0, 0};
+        for (int x = 0; x < s0->W; x++) {
+            const s64 i = (s64)y * s0->W + x;
+            u32 sum_r = 0, sum_g = 0, sum_b = 0;
+            s64 centre_id = -1;
+            for (int b = 0; b < n; b++) {
+                for (int a = 0; a < n; a++) {
+                    float rmd[3];
+                    if (n == 1) {
+                        primary_ray(s0->n_mod, s0->u_mod, s0->v_mod, s0->W, i, rmd);
+                    } else {
+                        const float fx = (float)x + (((float)a + 0.5f) / (float)n - 0.5f), fy = (float)y + (((float)b + 0.5f) / (float)n - 0.5f);
+                        rmd[0] = s0->n_mod[0] + s0->u_mod[0] * fx + s0->v_mod[0] * fy;
+                        rmd[1] = s0->n_mod[1] + s0->u_mod[1] * fx + s0->v_mod[1] * fy;
+                        rmd[2] = s0->n_mod[2] + s0->u_mod[2] * fx + s0->v_mod[2] * fy;
+                        device_normalize(&rmd[0], &rmd[1], &rmd[2]);
+                    }
+                    float best = s0->draw_distance;
+                    orc_hit hit;
+                    int hit_obj = -1;
+                    hit.id = -1;
+                    for (int k = 0; k < nobj; k++) {
+                        orc_hit hk;
+                        hk.id = -1;
+                        trace_object(scenes[k], m12s + 12 * k, rmd, &best, &hk, cnt);
+                        if (hk.id >= 0) { hit = hk; hit_obj = k; }
+                    }
+                    u32 c = bg;
+                    if (hit_obj >= 0) {
+                        const float* m = m12s + 12 * hit_obj;
+                        const float d[3] = {-1 * (m[0] * -rmd[0] + m[1] * -rmd[1] + m[2] * -rmd[2]), -1 * (m[4] * -rmd[0] + m[5] * -rmd[1] + m[6] * -rmd[2]),
+                                            -1 * (m[8] * -rmd[0] + m[9] * -rmd[1] + m[10] * -rmd[2])};
+                        const float od[3] = {m[3], m[7], m[11]};
+                        c = shade_lights(scenes[hit_obj], &hit, rmd, d, od, nlights, lights3, shadows);
+                    }
+                    sum_r += (c >> 16) & 0xff; sum_g += (c >> 8) & 0xff; sum_b += c & 0xff;
+                    if (a == n / 2 && b == n / 2) centre_id = hit_obj >= 0 ? id_base[hit_obj] + hit.id : -1;
+                }
+            }
+            if (ids) ids[i] = centre_id;
+            if (bgra) bgra[i] = n == 1 ? ((sum_r << 16) | (sum_g << 8) | sum_b) | (bg & 0xff000000u)
+                                       : ((sum_r / (u32)(n * n)) << 16) | ((sum_g / (u32)(n * n)) << 8) | (sum_b / (u32)(n * n)) | (bg & 0xff000000u);
+        }
+    }
+}
+
 /* 64-bit FNV-1a over raw bytes (golden fixtures store these) */
 uint64_t orc_fnv1a64(const void* data, size_t nbytes) {
     const u8* p = (const u8*)data;

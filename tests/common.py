@@ -92,3 +92,45 @@ def edge_script():
 def golden_edge():
     with open(os.path.join(GOLDEN_DIR, "golden_edge.json")) as f:
         return json.load(f)
+
+
+# ---- scene extension cases (shared by the golden generator, the CPU oracle test and the GPU test) ----------------------------
+R_KEY = (10, 0.0, 0.09950371902099893, 0.0, 0.9950371902099893)
+
+
+def scene_cases():
+    """name -> dict(W, H, objects=[(nu, [ops...])...], lights, shadows, sample_rate).  An object is a stand-in icosphere of
+    20*nu^2 triangles moved by a list of (select, x, y, z, w) ops."""
+    side = [(31, 1.0, 0.0, 0.0, 0.012)] * 10   # TRANSLATE_X: slides the second object sideways (overlapping silhouettes)
+    near = [(32, 0.0, 0.0, 1.0, 0.01)] * 6     # TRANSLATE_Z: and towards the camera
+    lights3 = [(2.0, 2.0, 2.0), (-2.0, 1.0, -2.0), (0.0, 3.0, -1.0)]
+    front = [(-1.5, 1.0, -2.0)]                # a light on the camera's side: the visible surface is mostly lit
+    return {
+        "shadows_backlit": dict(W=200, H=120, objects=[(12, [R_KEY])], lights=[(2.0, 2.0, 2.0)], shadows=True, sample_rate=0),
+        "shadows_frontlit": dict(W=200, H=120, objects=[(12, [R_KEY])], lights=front, shadows=True, sample_rate=0),
+        "three_lights": dict(W=200, H=120, objects=[(12, [R_KEY])], lights=lights3, shadows=False, sample_rate=0),
+        "three_lights_shadows": dict(W=200, H=120, objects=[(12, [R_KEY] * 2)], lights=lights3, shadows=True, sample_rate=0),
+        "samples2": dict(W=160, H=90, objects=[(10, [])], lights=[(2.0, 2.0, 2.0)], shadows=False, sample_rate=2),
+        "samples3_shadows": dict(W=97, H=61, objects=[(10, [R_KEY])], lights=front, shadows=True, sample_rate=3),
+        "two_objects": dict(W=240, H=136, objects=[(12, [R_KEY]), (9, side)], lights=[(2.0, 2.0, 2.0)], shadows=False, sample_rate=0),
+        "two_objects_ties": dict(W=160, H=90, objects=[(8, []), (8, [])], lights=[(2.0, 2.0, 2.0)], shadows=False, sample_rate=0),
+        "three_objects_everything": dict(W=192, H=108, objects=[(10, [R_KEY]), (7, side + near), (6, [(31, 1.0, 0.0, 0.0, -0.012)] * 9)],
+                                         lights=lights3, shadows=True, sample_rate=2),
+    }
+
+
+def build_scene_case(orc, mesh_fn, case):
+    """Oracle scenes of a case (one orc.Scene per object, transforms applied) and the keyword arguments of orc.render_scene."""
+    W, H = case["W"], case["H"]
+    scenes = []
+    for nu, ops in case["objects"]:
+        s = orc.Scene(mesh_fn(nu), W, H, cam12(W, H))
+        for op in ops:
+            s.transform(*op)
+        scenes.append(s)
+    return scenes, dict(lights=case["lights"], shadows=case["shadows"], sample_rate=case["sample_rate"])
+
+
+def golden_scene():
+    with open(os.path.join(GOLDEN_DIR, "golden_scene.json")) as f:
+        return json.load(f)

@@ -832,3 +832,170 @@ def test_buddha_standin_4k_late_frame_and_dense_frame_against_oracle(gpu, orc):
     ids, _, _, _ = p.check()
     assert (ids >= 0).mean() > 0.6
     p.close()
+
+
+@pytest.mark.parametrize("owners,G,F", [(1, 2, 3), (2, 2, 4), (3, 3, 7), (8, 8, 8), (4, 2, 5)])
+def test_striped_push_delivers_every_frame_to_its_owner(gpu, orc, owners, G, F):
+    """rtb_render_frames_push_striped_async: G emulated ranks push their tiles of F frames; frame f must arrive, whole and
+    bit-identical to the single-GPU frame, as frame f // owners of owner f % owners (ragged F: the last owners hold one
+    frame fewer)."""
+    import torch
+    pts = gpu.geodesic_mesh(20)
+    W, H = 320, 180
+    p = Pair(gpu, orc, pts, W, H)
+    mats = np.stack([p.obj.matrix()] + [p.obj.transform_host(gpu.R_KEY_QUAT, gpu.ROTATE_TRI_PY) for _ in range(F - 1)])
+    s = torch.cuda.current_stream().cuda_stream
+    ref_c = torch.zeros(F * W * H, dtype=torch.int32, device="cuda"); ref_i = torch.zeros(F * W * H, dtype=torch.int32, device="cuda")
+    p.obj.render_frames_device_async(p.cam, mats, ref_c.data_ptr(), ref_i.data_ptr(), s)
+    torch.cuda.synchronize()
+    want_c, want_i = ref_c.cpu().numpy().reshape(F, -1), ref_i.cpu().numpy().reshape(F, -1)
+    per_owner = (F + owners - 1) // owners
+    for prefilled in (False, True):
+        bufs_c = [gpu.PeerBuffer(4 * per_owner * W * H) for _ in range(owners)]
+        bufs_i = [gpu.PeerBuffer(4 * per_owner * W * H) for _ in range(owners)]
+        if prefilled:
+            for k in range(owners):
+                p.cam.fill_frames_device_async(per_owner, bufs_c[k].ptr, bufs_i[k].ptr, s)
+        for r in range(G):
+            p.obj.render_frames_push_striped_async(p.cam, mats, [b.ptr for b in bufs_c], [b.ptr for b in bufs_i], s, tile_first=r, tile_stride=G,
+                                                   flags=gpu.RENDER_PUSH_PREFILLED if prefilled else 0)
+        torch.cuda.synchronize()
+        for k in range(owners):
+            got_c = np.empty(per_owner * W * H, np.int32); got_i = np.empty(per_owner * W * H, np.int32)
+            gpu.memcpy_d2h(got_c, bufs_c[k].ptr); gpu.memcpy_d2h(got_i, bufs_i[k].ptr)
+            for j in range(per_owner):
+                f = j * owners + k
+                if f < F:
+                    assert np.array_equal(got_i.reshape(per_owner, -1)[j], want_i[f]), (prefilled, k, j)
+                    assert np.array_equal(got_c.reshape(per_owner, -1)[j], want_c[f]), (prefilled, k, j)
+        for b in bufs_c + bufs_i:
+            b.close()
+    p.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Scene extension (SURVEY.md section 8(f) items 3-4): lights, shadow rays, sample_rate, several objects per camera --
+# csrc/rtb_scene.cuh against its definition, oracle/rtb_oracle.c orc_render_scene, bit for bit (ids AND colours).
+# ---------------------------------------------------------------------------------------------------
+def _gpu_scene(gpu, case):
+    W, H = case["W"], case["H"]
+    cam = gpu.Camera(W, H, **cam_kwargs(W, H))
+    meshes, objs = [], []
+    for nu, ops in case["objects"]:
+        m = gpu.Trixel(gpu.geodesic_mesh(nu)); m.create_kd()
+        o = gpu.Object(m)
+        cam.add_object(o)
+        for op in ops:
+            o.transform(op[1:], op[0])
+        meshes.append(m); objs.append(o)
+    cam.set_lights(case["lights"]); cam.set_shadows(case["shadows"]); cam.set_sample_rate(case["sample_rate"])
+    return cam, meshes, objs
+
+
+def test_scene_extension_against_its_oracle(gpu, orc):
+    from common import build_scene_case, golden_scene, scene_cases
+    g = golden_scene()
+    for name, case in scene_cases().items():
+        scenes, kw = build_scene_case(orc, gpu.geodesic_mesh, case)
+        oids, obgra = orc.render_scene(scenes, **kw)
+        cam, meshes, objs = _gpu_scene(gpu, case)
+        for k, o in enumerate(objs):
+            assert np.array_equal(o.matrix().view(np.uint32), scenes[k].matrix().view(np.uint32)), name
+            assert cam.object_id_base(o) == sum(s.n for s in scenes[:k])
+        for flags in (0, gpu.RENDER_NO_CULL):
+            ids, bgra = cam.render_scene_frame(flags)
+            bad = int((ids.astype(np.int64) != oids).sum())
+            assert bad == 0, "%s: %d of %d hit ids differ (flags %d)" % (name, bad, ids.size, flags)
+            assert np.array_equal(bgra, obgra), "%s: %d colours differ (flags %d)" % (name, int((bgra != obgra).sum()), flags)
+        assert orc.fnv1a64(ids.astype(np.int64)) == g[name]["id_hash"] and orc.fnv1a64(bgra) == g[name]["colour_hash"], name
+        for o in objs:
+            o.close()
+        cam.close()
+        for m in meshes:
+            m.close()
+        for s in scenes:
+            s.close()
+
+
+def test_scene_extension_default_equals_the_hot_path(gpu, orc):
+    """One object, the default light, no shadows, one ray per pixel: rtb_camera_render_scene == rtb_object_render, on the
+    bunny (default view and close-up), on 3_walls (all ties) and with per-triangle colours."""
+    import torch
+    cases = [("ico", gpu.geodesic_mesh(24), {}, None, 320, 180, 0)]
+    if mesh_path("rabbit_70k.ply"):
+        cases.append(("bunny", gpu.read_ply(mesh_path("rabbit_70k.ply"), 1), {}, None, 960, 540, 150))
+    if mesh_path("3_walls.ply"):
+        cases.append(("walls", gpu.read_ply(mesh_path("3_walls.ply"), -1), WALLS_CAMERA, None, 640, 360, 0))
+    rng = np.random.default_rng(3)
+    pts8 = gpu.geodesic_mesh(8)
+    cases.append(("colours", pts8, {}, rng.uniform(0.05, 1.0, size=(len(pts8), 3)).astype(np.float32), 200, 120, 0))
+    for name, pts, camkw, cols, W, H, zoom in cases:
+        p = Pair(gpu, orc, pts, W, H, cam=camkw, colors=cols)
+        n = p.cam.basis()[0:3]
+        for k in range(3):
+            if k == 1:
+                p.transform(gpu.ROTATE_TRI_PY, gpu.R_KEY_QUAT)
+            if k == 2:
+                for _ in range(zoom):
+                    p.transform(gpu.TRANSLATE_Z, (float(n[0]), float(n[1]), float(n[2]), 0.005))
+            ids, bgra, oids, obgra = p.check()
+            ids2, bgra2 = p.cam.render_scene_frame()
+            assert np.array_equal(ids, ids2) and np.array_equal(bgra, bgra2), (name, k)
+        # device-resident variant on a caller stream
+        d_c = torch.zeros(W * H, dtype=torch.int32, device="cuda"); d_i = torch.zeros(W * H, dtype=torch.int32, device="cuda")
+        p.cam.render_scene_device_async(d_c.data_ptr(), d_i.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_i.cpu().numpy(), ids) and np.array_equal(d_c.cpu().numpy().view(np.uint32), bgra)
+        p.close()
+
+
+def test_scene_extension_misuse(gpu):
+    cam = gpu.Camera(64, 48, **cam_kwargs(64, 48))
+    with pytest.raises(gpu.RtbError):
+        cam.render_scene()                       # no object yet
+    with pytest.raises(gpu.RtbError):
+        cam.set_lights(np.zeros((9, 3)))         # more than 8 lights
+    with pytest.raises(gpu.RtbError):
+        cam.set_sample_rate(-1)
+    m = gpu.Trixel(gpu.geodesic_mesh(2)); m.create_kd()
+    objs = []
+    for k in range(9):
+        o = gpu.Object(m); cam.add_object(o); objs.append(o)
+    with pytest.raises(gpu.RtbError):
+        cam.render_scene()                       # more than 8 objects
+    objs.pop().close()
+    cam.render_scene()
+    cam.color_pixels(gpu.PHONG_COLOR_TAG)
+    assert (cam.h_ids() >= 0).any() and cam.h_ids().max() < len(gpu.geodesic_mesh(2))   # all ties: the first object wins everywhere
+    for o in objs:
+        o.close()
+    cam.close(); m.close()
+
+
+def test_headless_cpp_driver_scene_mode(gpu, orc, tmp_path):
+    """rtb_render --objects 2 --shadows --samples 2 --light ...: Camera::render() of the C++ mirror (rtb_framework.hpp)
+    through the scene extension; its files against the extension's oracle."""
+    import subprocess
+    from cpp_cuda_raytracer_dev_b200 import build as rtb_build
+    W, H = 240, 136
+    cmd = [rtb_build.DRIVER, "--mesh", "geodesic:16", "--res", "%dx%d" % (W, H), "--frames", "2", "--out", str(tmp_path / "s"),
+           "--objects", "2", "--shadows", "--samples", "2", "--light", "2,2,2", "--light", "-1.5,1,-2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    pts = gpu.geodesic_mesh(16)
+    a, b = orc.Scene(pts, W, H, cam12(W, H)), orc.Scene(pts, W, H, cam12(W, H))
+    u = a.basis[6:9]
+    for _ in range(12):
+        b.transform(31, float(u[0]), float(u[1]), float(u[2]), 0.012)
+    for f in range(2):
+        if f:
+            a.transform(gpu.ROTATE_TRI_PY, *gpu.R_KEY_QUAT)      # the driver's R key moves obj1 only (WinMain.cpp:188)
+        oids, obgra = orc.render_scene([a, b], lights=[(2, 2, 2), (-1.5, 1, -2)], shadows=True, sample_rate=2)
+        ids = np.fromfile(tmp_path / ("s_%04d.ids" % f), np.int32)
+        assert np.array_equal(ids.astype(np.int64), oids), "frame %d" % f
+        raw = (tmp_path / ("s_%04d.ppm" % f)).read_bytes()
+        head = ("P6\n%d %d\n255\n" % (W, H)).encode()
+        rgb = np.frombuffer(raw[len(head):], np.uint8).reshape(H, W, 3)[::-1].reshape(-1, 3).astype(np.uint32)
+        assert np.array_equal((rgb[:, 0] << 16) | (rgb[:, 1] << 8) | rgb[:, 2], obgra & 0x00ffffff)
+        assert (oids >= len(pts)).any() and (oids >= 0).sum() > 2000
+    a.close(); b.close()

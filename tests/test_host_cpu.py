@@ -293,3 +293,16 @@ def test_bench_reference_arm_contract(tmp_path):
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"] == "bunny_960x540"
+    assert line["product_library_loaded"] is False      # the reference arm must not touch librtb.so
+
+
+def test_reference_arm_standin_mesh_is_the_products_standin_mesh(rtb):
+    """oracle/standin.py (numpy; what `bench.py --impl reference` and the cpu_baseline leg render when the Stanford meshes
+    are absent) against rtb_mesh_geodesic (what our arm renders): the two arms must see the same triangles, bit for bit."""
+    from oracle import standin
+    for kw in (dict(nu=1), dict(nu=2), dict(nu=13), dict(nu=59), dict(nu=7, radius=0.09, center=(0.2, -0.1, 0.3), displacement=0.08, seed=77)):
+        a = rtb.geodesic_mesh(**kw)
+        b = standin.geodesic_mesh(**kw)
+        assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), kw
+    big_a, big_b = rtb.geodesic_mesh(209), standin.geodesic_mesh(209)     # the dragon-sized stand-in of the headline bench
+    assert np.array_equal(big_a.view(np.uint32), big_b.view(np.uint32))

@@ -255,3 +255,55 @@ def test_arithmetic_edge_cases_match_reference_golden(orc):
         want = g["grid_%dx%d" % (W, H)]
         assert orc.fnv1a64(ids) == want["id_hash"] and orc.fnv1a64(bgra) == want["colour_hash"]
         s.close()
+
+
+def test_scene_extension_default_is_the_reference_pinned_path(orc, rtb):
+    """orc_render_scene (lights, shadows, sample_rate, several objects -- defined here because the
+    reference leaves them dormant) must leave today's output untouched: one object, the light of Camera.cu:32, no shadows,
+    one ray per pixel == orc_render (pinned to the reference), on a moved object and on the all-ties scene."""
+    pts = rtb.geodesic_mesh(12)
+    W, H = 200, 120
+    s = orc.Scene(pts, W, H, cam12(W, H))
+    for k in range(3):
+        s.transform(10, 0.0, 0.09950371902099893, 0.0, 0.9950371902099893)
+        a, b = s.render(), orc.render_scene([s])
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        c = orc.render_scene([s], sample_rate=1)
+        assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1])
+    path = mesh_path("3_walls.ply")
+    if path is not None:
+        w = orc.Scene(orc.read_ply(path, -1), 320, 180, cam12(320, 180, **WALLS_CAMERA))
+        a, b = w.render(), orc.render_scene([w])
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and (a[0] >= 0).sum() > 1000
+        # two coincident copies of the scene: every hit is a tie between the objects, the first registered one wins
+        w2 = orc.Scene(orc.read_ply(path, -1), 320, 180, cam12(320, 180, **WALLS_CAMERA))
+        c = orc.render_scene([w, w2])
+        assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1])
+
+
+def test_scene_extension_matches_its_fixtures_and_makes_sense(orc):
+    """The extension's definition against the hashes recorded from it (tests/golden/make_golden_scene.py), plus properties
+    that do not depend on fixtures: shadows never change hit ids and only darken; a second, farther copy of an object
+    changes nothing; a nearer object hides the farther one exactly where it is hit."""
+    from common import build_scene_case, golden_scene, scene_cases
+    from oracle import standin
+    g = golden_scene()
+    for name, case in scene_cases().items():
+        scenes, kw = build_scene_case(orc, standin.geodesic_mesh, case)
+        ids, bgra = orc.render_scene(scenes, **kw)
+        want = g[name]
+        assert int((ids >= 0).sum()) == want["hits"] and orc.fnv1a64(ids) == want["id_hash"] and orc.fnv1a64(bgra) == want["colour_hash"], name
+        if kw["shadows"] and kw["sample_rate"] < 2:
+            ids0, bgra0 = orc.render_scene(scenes, lights=kw["lights"], shadows=False)
+            assert np.array_equal(ids, ids0), name
+            changed = bgra != bgra0
+            assert changed.any() and (ids[changed] >= 0).all(), name      # only hit pixels change
+        if len(scenes) == 2 and name == "two_objects":
+            a, _ = orc.render_scene(scenes[:1]); b, _ = orc.render_scene(scenes[1:])
+            both = (a >= 0) & (b >= 0)
+            assert both.any()
+            merged = np.where(ids >= scenes[0].n, ids - scenes[0].n, ids)
+            assert np.array_equal(merged[(a >= 0) & (b < 0)], a[(a >= 0) & (b < 0)]) and np.array_equal(merged[(b >= 0) & (a < 0)], b[(b >= 0) & (a < 0)])
+            assert ((ids >= 0) == ((a >= 0) | (b >= 0))).all()
+        for s in scenes:
+            s.close()

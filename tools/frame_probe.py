@@ -67,6 +67,21 @@ def full():
     obj.transform(rtb.R_KEY_QUAT, rtb.ROTATE_TRI_PY); obj.render(cam); cam.color_pixels(rtb.PHONG_COLOR_TAG)
 us = loop(full)
 print("full loop iteration                %8.1f us  = %.0f FPS" % (us, 1e6 / us))
+# SM clock while the loop runs (the GPU idles at 120 MHz; does a loop of 0.3 ms kernels + copies keep it at boost?)
+try:
+    import pynvml, threading
+    pynvml.nvmlInit(); hnd = pynvml.nvmlDeviceGetHandleByIndex(0)
+    samples, stop = [], [False]
+    def sample():
+        while not stop[0]:
+            samples.append(pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM)); time.sleep(0.002)
+    th = threading.Thread(target=sample); th.start()
+    N = 2000; us = loop(full); stop[0] = True; th.join()
+    print("  same loop, %d iterations: %.1f us; SM clock during it: median %d MHz, min %d, max %d (%d samples)" % (
+        N, us, int(np.median(samples)), min(samples), max(samples), len(samples)))
+    N = 400
+except Exception as exc:
+    print("  (no NVML: %s)" % exc)
 # copy-only: the frame's 8 bytes per pixel to pinned host memory
 hc = torch.empty(W * H, dtype=torch.int32).pin_memory(); hi = torch.empty(W * H, dtype=torch.int32).pin_memory()
 def copy_only():

@@ -9,3 +9,5 @@ for v in base morton redux packed both; do
 done
 echo "=== frame anatomy"
 timeout 600 python tools/frame_probe.py 2>&1 | tail -22
+echo "=== bench (no extras)"
+timeout 900 python bench.py --steps 5 --no-other-workloads > gpurun_out/r2b_bench.json 2> gpurun_out/r2b_bench.err; tail -c 3000 gpurun_out/r2b_bench.json; tail -5 gpurun_out/r2b_bench.err
