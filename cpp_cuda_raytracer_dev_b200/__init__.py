@@ -331,7 +331,7 @@ class Camera:
     def counters(self, reset=True):
         out = np.zeros(8, np.uint64)
         _check(lib.rtb_camera_counters_ex(self.h, out.ctypes.data, int(reset)), "rtb_camera_counters_ex")
-        return dict(zip(["rays", "nodes", "boxes", "tris", "hits", "stack_depth_sum", "stack_depth_max"], out.tolist()))
+        return dict(zip(["rays", "nodes", "boxes", "tris", "hits", "stack_depth_sum", "stack_depth_max", "ray_steps_max"], out.tolist()))
 
     def close(self):
         if self.h:

@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -36,6 +38,21 @@ int fail(rtb_status code, const std::string& what) {
         cudaError_t e_ = (expr);                                                                    \
         if (e_ != cudaSuccess) return fail(RTB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
     } while (0)
+
+// include/rtb.h promises that no entry point throws: the ones that grow host containers from caller- or file-controlled
+// sizes run their body through this guard.
+template <class F>
+int guarded(const char* who, F&& body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        return fail(RTB_ERR_NOMEM, std::string(who) + ": out of host memory");
+    } catch (const std::exception& e) {
+        return fail(RTB_ERR_ARG, std::string(who) + ": " + e.what());
+    } catch (...) {
+        return fail(RTB_ERR_ARG, std::string(who) + ": unexpected exception");
+    }
+}
 
 template <class T>
 void dfree(T*& p) {
@@ -122,6 +139,7 @@ struct rtb_object {
     int device = 0;
     rtb::Transform xf;
     bool xf_ready = false;
+    bool xf_overridden = false;  // rtb_object_set_matrix replaced the rows: the recurrence's quaternion / faces no longer describe them
     SceneArrays* scene = nullptr;
     // per-object launch scratch: frame records (matrices + pixel rectangles) of the frames in flight and the work
     // counter of the persistent kernel.  Launches of one object are ordered on the device through ev_launch, whatever
@@ -153,6 +171,7 @@ struct Knobs {
     int reserve_sms = 0;  // SMs left free beside the persistent kernel
     int l2_window = 1;    // persisting L2 window: 0 off, 1 node records, 2 nodes + triangles (takes effect at add_object)
     int no_rect = 0;      // 1: frame records carry the whole frame as the root-box rectangle
+    int frame_order = 1;  // multi-frame launches work through their frames sorted by viewing direction (order_frames)
     int l2_carve_mb = 0;  // persisting L2 carve-out in MB, 0 = the size of the window
 };
 Knobs& knobs() {
@@ -161,7 +180,7 @@ Knobs& knobs() {
         v.unit_shift = env_int("RTB_UNIT_SHIFT", v.unit_shift); v.t_active = env_int("RTB_T_ACTIVE", v.t_active);
         v.t_leaf = env_int("RTB_T_LEAF", v.t_leaf); v.tail5 = env_int("RTB_TAIL5", v.tail5); v.tail6 = env_int("RTB_TAIL6", v.tail6);
         v.reserve_sms = env_int("RTB_RESERVE_SMS", v.reserve_sms); v.l2_window = env_int("RTB_L2_WINDOW", v.l2_window);
-        v.no_rect = env_int("RTB_NO_RECT", v.no_rect); v.l2_carve_mb = env_int("RTB_L2_CARVE_MB", v.l2_carve_mb);
+        v.no_rect = env_int("RTB_NO_RECT", v.no_rect); v.frame_order = env_int("RTB_FRAME_ORDER", v.frame_order); v.l2_carve_mb = env_int("RTB_L2_CARVE_MB", v.l2_carve_mb);
         return v;
     }();
     return k;
@@ -204,8 +223,9 @@ int ensure_frames(rtb_object* o, int frames) {
     if (o->d_frames) cudaFree(o->d_frames);
     if (o->h_frames) cudaFreeHost(o->h_frames);
     o->d_frames = nullptr; o->h_frames = nullptr; o->frames_capacity = 0;
-    RTB_CUDA(cudaMalloc(&o->d_frames, sizeof(float) * rtb::kFrameStride * (size_t)cap));
-    RTB_CUDA(cudaMallocHost(&o->h_frames, sizeof(float) * rtb::kFrameStride * (size_t)cap));
+    // (one more word per frame: the processing order of a multi-frame launch follows the records, see order_frames)
+    RTB_CUDA(cudaMalloc(&o->d_frames, sizeof(float) * (rtb::kFrameStride + 1) * (size_t)cap));
+    RTB_CUDA(cudaMallocHost(&o->h_frames, sizeof(float) * (rtb::kFrameStride + 1) * (size_t)cap));
     o->frames_capacity = cap;
     return RTB_OK;
 }
@@ -217,8 +237,9 @@ int order_after_previous(rtb_object* o, cudaStream_t s) {
     return RTB_OK;
 }
 
-int upload_frames(rtb_object* o, int num_frames, cudaStream_t s) {
-    RTB_CUDA(cudaMemcpyAsync(o->d_frames, o->h_frames, sizeof(float) * rtb::kFrameStride * (size_t)num_frames, cudaMemcpyHostToDevice, s));
+int upload_frames(rtb_object* o, int num_frames, cudaStream_t s, bool with_order = false) {
+    RTB_CUDA(cudaMemcpyAsync(o->d_frames, o->h_frames, sizeof(float) * (rtb::kFrameStride + (with_order ? 1 : 0)) * (size_t)num_frames,
+                             cudaMemcpyHostToDevice, s));
     RTB_CUDA(cudaEventRecord(o->ev_upload, s));
     o->upload_pending = true;
     return RTB_OK;
@@ -272,11 +293,43 @@ void fill_frame_record(const SceneArrays* sc, const rtb_camera* c, const float m
     std::memcpy(rec + 12, rect, sizeof rect);
 }
 
+// Processing order of the frames of one launch.  The frames of a launch are independent, so the order in which the
+// persistent kernel works through them is free; what is in flight at any moment is about one frame's worth of work
+// units, and the node and triangle records a frame touches are re-used by the next one only if it shows the object from
+// nearly the same side.  An orbit in index order turns the object by the step angle from frame to frame and comes
+// back to a view only a revolution (31 frames, ~100 MB of records) later; sorted by viewing direction, neighbours in
+// the order differ by a fraction of a degree and find each other's records in L1/L2.  Key: direction of the camera
+// axis in object space (R^T n), as azimuth inside eight elevation bands walked in alternating direction.
+// Written behind the records in the pinned staging (h_frames + kFrameStride * num_frames); returns false (and
+// writes nothing) when the launch is too small to gain or the knob is off.
+bool order_frames(const rtb_object* o, const rtb_camera* c, int num_frames) {
+    if (!knobs().frame_order || num_frames < 4) return false;
+    const float* rec = o->h_frames;
+    int* order = reinterpret_cast<int*>(o->h_frames + rtb::kFrameStride * (size_t)num_frames);
+    const float* n = c->basis.n;
+    std::vector<std::pair<double, int>> key((size_t)num_frames);
+    const double kPi = 3.14159265358979323846;
+    for (int f = 0; f < num_frames; f++) {
+        const float* m = rec + rtb::kFrameStride * (size_t)f;
+        const double dx = (double)m[0] * n[0] + (double)m[4] * n[1] + (double)m[8] * n[2];
+        const double dy = (double)m[1] * n[0] + (double)m[5] * n[1] + (double)m[9] * n[2];
+        const double dz = (double)m[2] * n[0] + (double)m[6] * n[1] + (double)m[10] * n[2];
+        const double len = std::sqrt(dx * dx + dy * dy + dz * dz);
+        double az = 0.0, el = 0.0;
+        if (std::isfinite(len) && len > 0.0) { az = std::atan2(dz, dx); el = std::asin(std::max(-1.0, std::min(1.0, dy / len))); }
+        const int band = std::max(0, std::min(7, (int)((el + kPi / 2) / kPi * 8.0)));
+        key[(size_t)f] = {band * 8.0 + ((band & 1) ? -az : az), f};  // |az| <= pi < 4: bands never overlap
+    }
+    std::sort(key.begin(), key.end());
+    for (int f = 0; f < num_frames; f++) order[f] = key[(size_t)f].second;
+    return true;
+}
+
 // Launch the persistent render kernel over `num_frames` frame records: resident in device memory at `d_frames`, or --
 // single frame -- handed over as `inline_record` and carried in the kernel's parameters (no upload, d_frames == nullptr).
 int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, const float* inline_record, int num_frames, int tile_first,
                   int tile_stride, uint32_t flags, uint32_t* d_bgra, int32_t* d_ids, cudaStream_t stream, int push_owners = 0,
-                  uint32_t* const* push_bgra = nullptr, int32_t* const* push_ids = nullptr) {
+                  uint32_t* const* push_bgra = nullptr, int32_t* const* push_ids = nullptr, const int* d_frame_order = nullptr) {
     using namespace rtb;
     const SceneArrays* sc = o->scene;
     RenderParams P;
@@ -291,6 +344,7 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, const flo
     P.nodes = sc->d_nodes; P.tris = sc->d_tris; P.rad = sc->d_rad;
     for (int k = 0; k < 3; k++) P.uniform_rad[k] = sc->uniform_rgb[k];
     P.frames = d_frames;
+    P.frame_order = d_frame_order;
     if (inline_record) std::memcpy(P.frame0, inline_record, sizeof P.frame0);
     P.num_frames = num_frames;
     P.tiles_x = (b.W + kTile - 1) / kTile;
@@ -457,12 +511,14 @@ int rtb_set_knob(const char* name, int value) {
     else if (n == "reserve_sms") k.reserve_sms = value;
     else if (n == "l2_window") k.l2_window = value;
     else if (n == "no_rect") k.no_rect = value;
+    else if (n == "frame_order") k.frame_order = value;
     else if (n == "l2_carve_mb") k.l2_carve_mb = value;
     else return fail(RTB_ERR_ARG, "set_knob: unknown knob " + n);
     return RTB_OK;
 }
 
 int rtb_read_ply(const char* file_name, int mode, float** points9, uint32_t* num_tri) {
+    return guarded("read_ply", [&]() -> int {
     if (!file_name || !points9 || !num_tri) return fail(RTB_ERR_ARG, "read_ply: null argument");
     std::vector<float> pts;
     std::string err = rtb::load_ply(file_name, mode, pts);
@@ -473,18 +529,22 @@ int rtb_read_ply(const char* file_name, int mode, float** points9, uint32_t* num
     *points9 = out;
     *num_tri = (uint32_t)(pts.size() / 9);
     return RTB_OK;
+    });
 }
 void rtb_free(void* p) { std::free(p); }
 
 int rtb_write_ply(const char* file_name, const float* points9, uint32_t num_tri) {
+    return guarded("write_ply", [&]() -> int {
     if (!file_name || !points9) return fail(RTB_ERR_ARG, "write_ply: null argument");
     std::string err = rtb::save_ply(file_name, points9, num_tri);
     if (!err.empty()) return fail(RTB_ERR_IO, err);
     return RTB_OK;
+    });
 }
 
 int rtb_mesh_geodesic(int nu, float radius, const float center[3], float displacement, uint32_t seed, float** points9,
                       uint32_t* num_tri) {
+    return guarded("mesh_geodesic", [&]() -> int {
     if (nu < 1 || nu > 4000 || !center || !points9 || !num_tri) return fail(RTB_ERR_ARG, "mesh_geodesic: bad argument");
     std::vector<float> pts;
     rtb::make_geodesic(nu, radius, center, displacement, seed, pts);
@@ -494,17 +554,24 @@ int rtb_mesh_geodesic(int nu, float radius, const float center[3], float displac
     *points9 = out;
     *num_tri = (uint32_t)(pts.size() / 9);
     return RTB_OK;
+    });
 }
 
 // ---- mesh ----------------------------------------------------------------------------------------
 
 int rtb_mesh_create(const float* points9, int64_t num_tri, const float* rad3, const float uniform_rgb[3], rtb_mesh** out) {
     if (!points9 || num_tri <= 0 || num_tri > 0x1fffffff || !out) return fail(RTB_ERR_ARG, "mesh_create: bad argument");
-    rtb_mesh* m = new rtb_mesh();
+    rtb_mesh* m = nullptr;
+    try {
+        m = new rtb_mesh();
+        m->points.assign(points9, points9 + 9 * (size_t)num_tri);
+        if (rad3) m->rad.assign(rad3, rad3 + 3 * (size_t)num_tri);
+    } catch (const std::bad_alloc&) {
+        delete m;
+        return fail(RTB_ERR_NOMEM, "mesh_create: out of host memory");
+    }
     m->device = g_device;
     m->n = num_tri;
-    m->points.assign(points9, points9 + 9 * (size_t)num_tri);
-    if (rad3) m->rad.assign(rad3, rad3 + 3 * (size_t)num_tri);
     if (uniform_rgb) std::memcpy(m->uniform_rgb, uniform_rgb, 12);
     cudaError_t e = cudaSetDevice(m->device);
     if (e == cudaSuccess) e = cudaMalloc(&m->d_points, sizeof(float) * 9 * (size_t)num_tri);
@@ -521,6 +588,7 @@ int rtb_mesh_create(const float* points9, int64_t num_tri, const float* rad3, co
 }
 
 int rtb_mesh_build_tree_on(rtb_mesh* mesh, int where) {
+    return guarded("build_tree", [&]() -> int {
     if (!mesh) return fail(RTB_ERR_ARG, "build_tree: null mesh");
     if (where < 0 || where > 2) return fail(RTB_ERR_ARG, "build_tree: where must be 0 (auto), 1 (host) or 2 (device)");
     const bool device = where == 2 || (where == 0 && mesh->d_points != nullptr);
@@ -543,6 +611,7 @@ int rtb_mesh_build_tree_on(rtb_mesh* mesh, int where) {
     mesh->built_on_device = device;
     mesh->generation++;
     return RTB_OK;
+    });
 }
 int rtb_mesh_build_tree(rtb_mesh* mesh) { return rtb_mesh_build_tree_on(mesh, 0); }
 int64_t rtb_mesh_num_triangles(const rtb_mesh* mesh) { return mesh ? mesh->n : 0; }
@@ -550,6 +619,7 @@ int64_t rtb_mesh_num_nodes(const rtb_mesh* mesh) { return mesh ? 2 * mesh->n - 1
 
 int rtb_mesh_get_tree(const rtb_mesh* mesh_c, int32_t* left, int32_t* right, int32_t* tri, int32_t* cut_flag, float* bounds6,
                       float* s1, float* s2) {
+    return guarded("get_tree", [&]() -> int {
     rtb_mesh* mesh = const_cast<rtb_mesh*>(mesh_c);  // a device-built tree is downloaded on first use
     if (!mesh || !mesh->built) return fail(RTB_ERR_STATE, "get_tree: tree not built");
     const int rc = ensure_host_tree(mesh);
@@ -565,16 +635,20 @@ int rtb_mesh_get_tree(const rtb_mesh* mesh_c, int32_t* left, int32_t* right, int
     }
     if (bounds6) std::memcpy(bounds6, T.bounds.data(), sizeof(float) * 6 * (size_t)T.num_nodes);
     return RTB_OK;
+    });
 }
 int rtb_mesh_save_tree(const rtb_mesh* mesh_c, const char* file_name) {
+    return guarded("save_tree", [&]() -> int {
     rtb_mesh* mesh = const_cast<rtb_mesh*>(mesh_c);
     if (!mesh || !file_name || !mesh->built) return fail(RTB_ERR_STATE, "save_tree: tree not built");
     const int rc = ensure_host_tree(mesh);
     if (rc) return rc;
     const std::string err = rtb::save_tree(file_name, mesh->tree, mesh->points.data());
     return err.empty() ? RTB_OK : fail(RTB_ERR_IO, err);
+    });
 }
 int rtb_mesh_load_tree(rtb_mesh* mesh, const char* file_name) {
+    return guarded("load_tree", [&]() -> int {
     if (!mesh || !file_name) return fail(RTB_ERR_ARG, "load_tree: null argument");
     rtb::HostTree T;
     const std::string err = rtb::load_tree(file_name, mesh->points.data(), mesh->n, T);
@@ -585,11 +659,14 @@ int rtb_mesh_load_tree(rtb_mesh* mesh, const char* file_name) {
     mesh->generation++;
     mesh->seconds_sort = mesh->seconds_partition = 0.0;
     return RTB_OK;
+    });
 }
 int rtb_write_frame(const char* file_name, const uint32_t* bgra, int32_t width, int32_t height) {
+    return guarded("write_frame", [&]() -> int {
     if (!file_name || !bgra || width <= 0 || height <= 0) return fail(RTB_ERR_ARG, "write_frame: bad argument");
     const std::string err = rtb::save_frame(file_name, bgra, width, height);
     return err.empty() ? RTB_OK : fail(RTB_ERR_IO, err);
+    });
 }
 int rtb_mesh_build_seconds(const rtb_mesh* mesh, double out3[3]) {
     if (!mesh || !mesh->built || !out3) return fail(RTB_ERR_STATE, "build_seconds: tree not built");
@@ -775,6 +852,7 @@ int make_scene_arrays(rtb_camera* cam, rtb_mesh* m, SceneArrays** out) {
 }  // namespace
 
 int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj) {
+    return guarded("add_object", [&]() -> int {
     if (!cam || !obj) return fail(RTB_ERR_ARG, "add_object: null handle");
     rtb_mesh* m = obj->mesh;
     if (!m->built) return fail(RTB_ERR_STATE, "add_object: rtb_mesh_build_tree has not been called");
@@ -803,7 +881,9 @@ int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj) {
     // Camera.cpp:131-134: faces = -camera position, identity quaternion
     obj->xf.reset(cam->basis.pos);
     obj->xf_ready = true;
+    obj->xf_overridden = false;
     return RTB_OK;
+    });
 }
 
 int rtb_camera_color_pixels(rtb_camera* cam, uint8_t tag) {
@@ -900,6 +980,8 @@ int rtb_object_create(rtb_mesh* mesh, rtb_object** out) {
 int rtb_object_transform_host(rtb_object* obj, const float xyzw[4], uint8_t select, float m12_out[12]) {
     if (!obj || !xyzw) return fail(RTB_ERR_ARG, "transform: null argument");
     if (!obj->xf_ready) return fail(RTB_ERR_STATE, "transform: object was not added to a camera");
+    if (obj->xf_overridden)
+        return fail(RTB_ERR_STATE, "transform: the matrix was set with rtb_object_set_matrix; rtb_camera_add_object restarts the recurrence");
     if (!obj->xf.apply(select, xyzw[0], xyzw[1], xyzw[2], xyzw[3])) return fail(RTB_ERR_ARG, "transform: unknown selector");
     if (m12_out) obj->xf.matrix(m12_out);
     return RTB_OK;
@@ -929,6 +1011,7 @@ int rtb_object_get_matrix(const rtb_object* obj, float m12[12]) {
 int rtb_object_set_matrix(rtb_object* obj, const float m12[12]) {
     if (!obj || !m12 || !obj->xf_ready) return fail(RTB_ERR_STATE, "set_matrix: object was not added to a camera");
     obj->xf.set_matrix(m12);
+    obj->xf_overridden = true;
     return RTB_OK;
 }
 void rtb_object_destroy(rtb_object* obj) {
@@ -1082,10 +1165,12 @@ int rtb_render_frames_device_async(rtb_object* obj, rtb_camera* cam, int32_t num
     rc = ensure_frames(obj, num_frames);  // (waits for the previous upload from the pinned staging, never for a kernel)
     if (rc) return rc;
     for (int f = 0; f < num_frames; f++) fill_frame_record(obj->scene, cam, m12 + 12 * (size_t)f, obj->h_frames + rtb::kFrameStride * (size_t)f);
+    const bool ordered = order_frames(obj, cam, num_frames);
     rc = order_after_previous(obj, s);
-    if (!rc) rc = upload_frames(obj, num_frames, s);
+    if (!rc) rc = upload_frames(obj, num_frames, s, ordered);
     if (rc) return rc;
-    return launch_render(obj, cam, obj->d_frames, nullptr, num_frames, tile_first, tile_stride, flags, d_bgra, d_ids, s);
+    return launch_render(obj, cam, obj->d_frames, nullptr, num_frames, tile_first, tile_stride, flags, d_bgra, d_ids, s, 0, nullptr, nullptr,
+                         ordered ? reinterpret_cast<const int*>(obj->d_frames + rtb::kFrameStride * (size_t)num_frames) : nullptr);
 }
 
 int rtb_render_frames_push_async(rtb_object* obj, rtb_camera* cam, int32_t num_frames, const float* m12, int32_t tile_first,
@@ -1121,11 +1206,13 @@ int rtb_render_frames_push_striped_async(rtb_object* obj, rtb_camera* cam, int32
         cam->push_elements = need;
     }
     for (int f = 0; f < num_frames; f++) fill_frame_record(obj->scene, cam, m12 + 12 * (size_t)f, obj->h_frames + rtb::kFrameStride * (size_t)f);
+    const bool ordered = order_frames(obj, cam, num_frames);
     rc = order_after_previous(obj, s);
-    if (!rc) rc = upload_frames(obj, num_frames, s);
+    if (!rc) rc = upload_frames(obj, num_frames, s, ordered);
     if (rc) return rc;
     return launch_render(obj, cam, obj->d_frames, nullptr, num_frames, tile_first, tile_stride, flags, d_frame_bgra ? cam->push_bgra : nullptr,
-                         d_frame_ids ? cam->push_ids : nullptr, s, owners, d_frame_bgra, d_frame_ids);
+                         d_frame_ids ? cam->push_ids : nullptr, s, owners, d_frame_bgra, d_frame_ids,
+                         ordered ? reinterpret_cast<const int*>(obj->d_frames + rtb::kFrameStride * (size_t)num_frames) : nullptr);
 }
 
 int rtb_fill_frames_device_async(rtb_camera* cam, int32_t num_frames, uint32_t* d_frame_bgra, int32_t* d_frame_ids, void* stream) {
@@ -1198,6 +1285,8 @@ int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32
             const float* op = ops5 + 5 * ((size_t)f * steps_per_frame + s);
             const int select = (int)op[0];
             if (select == 0) continue;
+            if (obj->xf_overridden)
+                return fail(RTB_ERR_STATE, "render_sweep: the matrix was set with rtb_object_set_matrix; rtb_camera_add_object restarts the recurrence");
             if (!obj->xf.apply((uint8_t)select, op[1], op[2], op[3], op[4])) return fail(RTB_ERR_ARG, "render_sweep: unknown selector");
         }
         float m12[12];

@@ -170,6 +170,8 @@ std::string load_ply_conforming(const FileBytes& fb, std::vector<float>& points9
             e.name = w[1];
             e.count = std::atol(w[2].c_str());
             if (e.count < 0) return "read_ply: negative element count";
+            // every element occupies at least one byte of the body (ascii: its line break), whatever the format
+            if (e.count > (long)fb.data.size()) return "read_ply: element count exceeds the file size";
             elements.push_back(e);
         } else if (w[0] == "property") {
             if (elements.empty()) return "read_ply: property before any element";
@@ -311,6 +313,7 @@ std::string load_ply(const char* path, int mode, std::vector<float>& points9) {
     if (!header_done) return "read_ply: no end_header";
     if (num_vert <= 0 || num_face <= 0) return "read_ply: header has no vertex/face counts";
     if (binary) return "read_ply: binary PLY needs mode -1 (the reference reader only parses text)";
+    if (num_vert > (long)(end - p) || num_face > (long)(end - p)) return "read_ply: element count exceeds the file size";
     std::vector<float> verts((size_t)num_vert * 3);
     points9.reserve((size_t)num_face * 9);
     const int columns = mode == 1 ? 5 : mode == 2 ? 6 : 3;
@@ -442,15 +445,55 @@ std::string save_frame(const char* path, const uint32_t* bgra, int W, int H) {
     return "";
 }
 
-// Tree cache: the built tree of one mesh as a flat little-endian blob, tied to the mesh by a hash of its points.
-//   "RTBKD1\0\0" | u64 num_tri | u64 num_nodes | u64 fnv1a64(points9) | bounds[6N] f32 | left[N] i32 | tri[N] i32 |
-//   s1[N] f32 | s2[N] f32 | cut_flag[N] u8
+// Tree cache: the built tree of one mesh as a flat little-endian blob, tied to the mesh by a hash of its points and
+// protected by a hash of its own payload.
+//   "RTBKD2\0\0" | u64 num_tri | u64 num_nodes | u64 fnv1a64(points9) | u64 fnv1a64 chained over the six arrays |
+//   bounds[6N] f32 | left[N] i32 | tri[N] i32 | s1[N] f32 | s2[N] f32 | cut_flag[N] u8
+// ("RTBKD1" files, which lack the payload hash, are still read; both go through the same structural validation.)
+namespace {
+uint64_t tree_payload_hash(const HostTree& T) {
+    const size_t N = (size_t)T.num_nodes;
+    uint64_t h = fnv1a64(T.bounds.data(), 4 * 6 * N);
+    const struct { const void* p; size_t n; } parts[5] = {{T.left.data(), 4 * N}, {T.tri.data(), 4 * N}, {T.s1.data(), 4 * N}, {T.s2.data(), 4 * N},
+                                                           {T.cut_flag.data(), N}};
+    for (const auto& part : parts) {  // chain: hash of (previous hash, next array)
+        const uint64_t g = fnv1a64(part.p, part.n);
+        const uint64_t pair[2] = {h, g};
+        h = fnv1a64(pair, sizeof pair);
+    }
+    return h;
+}
+// Everything the render kernels rely on: children lie behind their parent (so one forward pass sees every node after
+// its parent), every node but the root has exactly ONE parent, leaves name a triangle of the mesh and every triangle is
+// named by exactly one leaf, and no node lies deeper than the traversal stack can hold (kMaxTreeDepth: the kernels'
+// stack has kStackDepth = 40 entries and a descent pushes at most one entry per level).
+constexpr int kMaxTreeDepth = 38;
+bool tree_structure_ok(const HostTree& T, int64_t num_tri) {
+    const size_t N = (size_t)T.num_nodes;
+    std::vector<uint8_t> depth(N, 0), parents(N, 0), tri_seen((size_t)num_tri, 0);
+    for (size_t i = 0; i < N; i++) {
+        if (i > 0 && parents[i] != 1) return false;  // unreachable, or reachable along two paths
+        const int32_t l = T.left[i];
+        if (l < 0) {
+            const int32_t t = T.tri[i];
+            if (t < 0 || t >= num_tri || tri_seen[(size_t)t]++) return false;
+            continue;
+        }
+        if ((size_t)l + 1 >= N || (size_t)l <= i || T.cut_flag[i] >= 6 || depth[i] >= kMaxTreeDepth) return false;
+        for (size_t c = (size_t)l; c <= (size_t)l + 1; c++) {
+            if (parents[c]++) return false;
+            depth[c] = (uint8_t)(depth[i] + 1);
+        }
+    }
+    return true;
+}
+}  // namespace
 std::string save_tree(const char* path, const HostTree& T, const float* points9) {
     FILE* f = std::fopen(path, "wb");
     if (!f) return std::string("save_tree: cannot open ") + path;
-    const uint64_t head[3] = {(uint64_t)T.num_tri, (uint64_t)T.num_nodes, fnv1a64(points9, sizeof(float) * 9 * (size_t)T.num_tri)};
+    const uint64_t head[4] = {(uint64_t)T.num_tri, (uint64_t)T.num_nodes, fnv1a64(points9, sizeof(float) * 9 * (size_t)T.num_tri), tree_payload_hash(T)};
     const size_t N = (size_t)T.num_nodes;
-    bool ok = std::fwrite("RTBKD1\0\0", 1, 8, f) == 8 && std::fwrite(head, 8, 3, f) == 3;
+    bool ok = std::fwrite("RTBKD2\0\0", 1, 8, f) == 8 && std::fwrite(head, 8, 4, f) == 4;
     ok = ok && std::fwrite(T.bounds.data(), 4, 6 * N, f) == 6 * N && std::fwrite(T.left.data(), 4, N, f) == N;
     ok = ok && std::fwrite(T.tri.data(), 4, N, f) == N && std::fwrite(T.s1.data(), 4, N, f) == N && std::fwrite(T.s2.data(), 4, N, f) == N;
     ok = ok && std::fwrite(T.cut_flag.data(), 1, N, f) == N;
@@ -461,9 +504,11 @@ std::string load_tree(const char* path, const float* points9, int64_t num_tri, H
     FILE* f = std::fopen(path, "rb");
     if (!f) return std::string("load_tree: cannot open ") + path;
     char magic[8];
-    uint64_t head[3];
+    uint64_t head[4] = {0, 0, 0, 0};
     std::string err;
-    if (std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, "RTBKD1\0\0", 8) != 0 || std::fread(head, 8, 3, f) != 3) err = "load_tree: not a tree file";
+    int version = 0;
+    if (std::fread(magic, 1, 8, f) == 8) version = std::memcmp(magic, "RTBKD2\0\0", 8) == 0 ? 2 : std::memcmp(magic, "RTBKD1\0\0", 8) == 0 ? 1 : 0;
+    if (version == 0 || std::fread(head, 8, (size_t)(version == 2 ? 4 : 3), f) != (size_t)(version == 2 ? 4 : 3)) err = "load_tree: not a tree file";
     else if ((int64_t)head[0] != num_tri || head[1] != 2 * head[0] - 1) err = "load_tree: the file holds a tree of a different triangle count";
     else if (head[2] != fnv1a64(points9, sizeof(float) * 9 * (size_t)num_tri)) err = "load_tree: the file belongs to a different mesh (point hash mismatch)";
     if (err.empty()) {
@@ -473,13 +518,9 @@ std::string load_tree(const char* path, const float* points9, int64_t num_tri, H
         bool ok = std::fread(T.bounds.data(), 4, 6 * N, f) == 6 * N && std::fread(T.left.data(), 4, N, f) == N;
         ok = ok && std::fread(T.tri.data(), 4, N, f) == N && std::fread(T.s1.data(), 4, N, f) == N && std::fread(T.s2.data(), 4, N, f) == N;
         ok = ok && std::fread(T.cut_flag.data(), 1, N, f) == N;
-        // structural sanity, so that a damaged file cannot send the traversal out of bounds
-        for (size_t i = 0; ok && i < N; i++) {
-            const int32_t l = T.left[i];
-            if (l < 0) ok = T.tri[i] >= 0 && T.tri[i] < num_tri;
-            else ok = (size_t)l + 1 < N && (size_t)l > i && T.cut_flag[i] < 6;
-        }
-        if (!ok) err = "load_tree: truncated or damaged file";
+        if (!ok) err = "load_tree: truncated file";
+        else if (version == 2 && head[3] != tree_payload_hash(T)) err = "load_tree: damaged file (payload hash mismatch)";
+        else if (!tree_structure_ok(T, num_tri)) err = "load_tree: damaged file (not a tree over this mesh, or deeper than the traversal stack)";
         T.seconds_sort = T.seconds_partition = 0.0;
     }
     std::fclose(f);

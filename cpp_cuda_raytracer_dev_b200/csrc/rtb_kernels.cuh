@@ -51,6 +51,8 @@ struct RenderParams {
     float uniform_rad[3];
     const float* __restrict__ frames;  // kFrameStride floats per frame: rows x,y,z = (i,j,k,w), then the pixel rectangle
                                        // x0,y0,x1,y1 (int bits, inclusive) outside which no ray can reach the root box
+    const int* __restrict__ frame_order;  // optional: the k-th frame PROCESSED is frame_order[k] (views sorted for cache reuse);
+                                          // null = in index order.  Output placement is by the frame's own index either way.
     float frame0[kFrameStride];        // render_stream_kernel<.., INLINE = true>: the record of a single-frame launch travels
                                        // with the kernel parameters (constant bank) instead of through device memory
     int num_frames;

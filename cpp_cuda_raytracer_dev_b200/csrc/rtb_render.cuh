@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
     bool blocked = false;      // warp-uniform: no free slot for the next unit -> drain in-flight rays first
     unsigned long long c_nodes = 0, c_boxes = 0, c_tris = 0, c_rays = 0, c_hits = 0, c_depth = 0;
     int ray_depth = 0, c_depth_max = 0;  // COUNT: deepest stack of the lane's current ray / of any ray of this lane
+    int ray_steps = 0, c_steps_max = 0;  // COUNT: interior + leaf steps of the lane's current ray / the longest ray of this lane
 
     // Traversal stack: the top entry lives in registers (top_*), deeper entries in local memory.
     // A pop hands out the register copy at once and re-loads the new top in the background, so the
@@ -247,13 +248,13 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
             if (m_leaf != 0u && (__popc(m_leaf) >= P.t_leaf || m_leaf == m_ready)) {
                 // ---- leaf step: always intersected when popped (Trixel.cu:98) -----------------------
                 if (at_leaf) {
-                    if (COUNT) c_tris++;
+                    if (COUNT) { c_tris++; ray_steps++; }
                     if (moller_trumbore(r, P.tris, (int)((unsigned)cur & kRefIndexMask), best, id)) set_cull_base();
                     want_pop = true;
                 }
             } else if (ready & !at_leaf) {
                 // ---- interior step: `cur` is a node whose own box test passed ------------------------
-                if (COUNT) c_nodes++;
+                if (COUNT) { c_nodes++; ray_steps++; }
                 const float4* rec;  // P.nodes + 64 bytes * record index, as one IMAD.WIDE
                 asm("mad.wide.u32 %0, %1, 64, %2;" : "=l"(rec) : "r"((unsigned)cur & kRefIndexMask), "l"(P.nodes));
                 const float4 q0 = ldg4(rec), q1 = ldg4(rec + 1), q2 = ldg4(rec + 2), q3 = ldg4(rec + 3);
@@ -339,7 +340,10 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                 }
                 if (COUNT) c_hits++;
             }
-            if (COUNT) { c_depth += (unsigned long long)ray_depth; c_depth_max = max(c_depth_max, ray_depth); ray_depth = 0; }
+            if (COUNT) {
+                c_depth += (unsigned long long)ray_depth; c_depth_max = max(c_depth_max, ray_depth); ray_depth = 0;
+                c_steps_max = max(c_steps_max, ray_steps); ray_steps = 0;
+            }
             const long long o = (long long)frame * P.frame_stride + pix;
             // frames are write-once streams: keep them from displacing the scene in L2
             if (P.out_bgra) RTB_PIXEL_STORE(P.out_bgra + o, color);
@@ -379,6 +383,7 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                 const long long per_frame = (long long)P.my_tiles * units_per_tile;
                 const int fseg = (int)(item / per_frame);
                 u_frame = frame0 + fseg;
+                if (!INLINE && P.frame_order) u_frame = __ldg(P.frame_order + u_frame);
                 const int rem = (int)(item - (long long)fseg * per_frame);
                 u_slot = rem / units_per_tile;
                 const int tile = P.tile_first + u_slot * P.tile_stride;
@@ -586,11 +591,13 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
             c_hits += __shfl_down_sync(0xffffffffu, c_hits, s);
             c_depth += __shfl_down_sync(0xffffffffu, c_depth, s);
             c_depth_max = max(c_depth_max, __shfl_down_sync(0xffffffffu, c_depth_max, s));
+            c_steps_max = max(c_steps_max, __shfl_down_sync(0xffffffffu, c_steps_max, s));
         }
         if (lane == 0) {
             atomicAdd(P.counters + 0, c_rays); atomicAdd(P.counters + 1, c_nodes); atomicAdd(P.counters + 2, c_boxes);
             atomicAdd(P.counters + 3, c_tris); atomicAdd(P.counters + 4, c_hits);
             atomicAdd(P.counters + 5, c_depth); atomicMax(P.counters + 6, (unsigned long long)c_depth_max);
+            atomicMax(P.counters + 7, (unsigned long long)c_steps_max);
         }
     }
 }

@@ -155,7 +155,8 @@ const int32_t* rtb_camera_host_ids(const rtb_camera* cam);
  * sense (root + every child the parent scheduled), [3] triangle tests, [4] hits */
 int rtb_camera_counters(rtb_camera* cam, uint64_t out5[5], int reset);
 /* the same plus [5] sum over the traced rays of their deepest traversal stack (entries, counting the one kept in
- * registers), [6] the deepest stack any ray reached, [7] reserved: sizes the shared-memory part of the stack */
+ * registers), [6] the deepest stack any ray reached, [7] the most steps (interior records + triangle tests) any single ray took:
+ * the length of the longest dependent chain of the launch */
 int rtb_camera_counters_ex(rtb_camera* cam, uint64_t out8[8], int reset);
 void rtb_camera_destroy(rtb_camera* cam);
 
@@ -170,6 +171,10 @@ int rtb_object_create(rtb_mesh* mesh, rtb_object** out);
 int rtb_object_transform(rtb_object* obj, const float xyzw[4], uint8_t transform_select);
 /* the object's 3x4 matrix: rows x,y,z of Quaternion::rot_m, each (i,j,k,w=translation) */
 int rtb_object_get_matrix(const rtb_object* obj, float m12[12]);
+/* Render-only override (no reference counterpart): the next renders use m12 as they would use the recurrence's
+ * matrix.  The quaternion and face bookkeeping of the recurrence (Quaternion::vec, Object::init_face / cur_face) are
+ * NOT derived from it, so rtb_object_transform / rtb_object_transform_host / rtb_render_sweep steps return
+ * RTB_ERR_STATE afterwards, until rtb_camera_add_object restarts the recurrence (Camera.cpp:131-134). */
 int rtb_object_set_matrix(rtb_object* obj, const float m12[12]);
 void rtb_object_destroy(rtb_object* obj);
 

@@ -999,3 +999,65 @@ def test_headless_cpp_driver_scene_mode(gpu, orc, tmp_path):
         assert np.array_equal((rgb[:, 0] << 16) | (rgb[:, 1] << 8) | rgb[:, 2], obgra & 0x00ffffff)
         assert (oids >= len(pts)).any() and (oids >= 0).sum() > 2000
     a.close(); b.close()
+
+
+def test_frame_order_does_not_change_frames(gpu, orc):
+    """Multi-frame launches work through their frames sorted by viewing direction (rtb_api.cu order_frames); the frames
+    themselves must not notice: same ids and colours with the knob off, in index order, and against the oracle."""
+    import torch
+    W, H, F = 192, 108, 40
+    pts = gpu.geodesic_mesh(12)
+    p = Pair(gpu, orc, pts, W, H)
+    mats = [p.obj.matrix()]
+    rng = np.random.RandomState(5)
+    for k in range(F - 1):  # an orbit that also tilts and zooms: views recur out of index order
+        sel, q = [(gpu.ROTATE_TRI_PY, gpu.R_KEY_QUAT), (gpu.ROTATE_TRI_PY, gpu.T_KEY_QUAT), (gpu.ROTATE_TRI_PY, (0.0998, 0.0, 0.0, 0.995))][rng.randint(3)]
+        mats.append(p.obj.transform_host(q, sel))
+        p.ref.transform(sel, *q)
+    mats = np.stack(mats)
+    out = {}
+    for knob in (1, 0):
+        gpu.set_knob("frame_order", knob)
+        col = torch.zeros(F * W * H, dtype=torch.int32, device="cuda"); ids = torch.zeros(F * W * H, dtype=torch.int32, device="cuda")
+        p.obj.render_frames_device_async(p.cam, mats, col.data_ptr(), ids.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        out[knob] = (col.cpu().numpy().reshape(F, -1), ids.cpu().numpy().reshape(F, -1))
+    gpu.set_knob("frame_order", 1)
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    for f in (0, 17, F - 1):
+        p.obj.set_matrix(mats[f])
+        ids1, bgra1 = p.obj.render_frame(p.cam)
+        assert np.array_equal(ids1, out[1][1][f]) and np.array_equal(bgra1.view(np.int32), out[1][0][f])
+    oids, obgra = p.ref.render()  # the oracle has followed the same steps: it stands at the last frame
+    assert np.array_equal(out[1][1][F - 1].astype(np.int64), oids)
+    assert channel_diff(out[1][0][F - 1].view(np.uint32), obgra).max(initial=0) <= COLOUR_TOL
+    p.close()
+
+
+def test_set_matrix_suspends_the_recurrence(gpu, orc):
+    """rtb_object_set_matrix is render-only state: the frame follows the matrix, transform calls and sweep
+    steps are refused with RTB_ERR_STATE until add_object restarts the recurrence."""
+    W, H = 160, 90
+    pts = gpu.geodesic_mesh(8)
+    p = Pair(gpu, orc, pts, W, H)
+    for _ in range(3):
+        p.transform(gpu.ROTATE_TRI_PY, gpu.R_KEY_QUAT)
+    m3 = p.obj.matrix()
+    ids3, bgra3, _, _ = p.check()
+    p.cam.add_object(p.obj)  # identity again
+    ids0, _ = p.obj.render_frame(p.cam)
+    assert not np.array_equal(ids0, ids3)
+    p.obj.set_matrix(m3)
+    ids, bgra = p.obj.render_frame(p.cam)
+    assert np.array_equal(ids, ids3) and np.array_equal(bgra, bgra3)
+    with pytest.raises(gpu.RtbError, match="set_matrix"):
+        p.obj.transform(gpu.R_KEY_QUAT, gpu.ROTATE_TRI_PY)
+    with pytest.raises(gpu.RtbError, match="set_matrix"):
+        p.obj.render_sweep(p.cam, gpu.orbit_ops(2))
+    p.cam.add_object(p.obj)
+    p.obj.transform(gpu.R_KEY_QUAT, gpu.ROTATE_TRI_PY)  # the recurrence runs again, from the identity
+    p.ref.close()
+    p.ref = orc.Scene(pts, W, H, cam12(W, H))
+    p.ref.transform(gpu.ROTATE_TRI_PY, *gpu.R_KEY_QUAT)
+    p.check()
+    p.close()

@@ -269,12 +269,80 @@ def test_tree_cache_round_trip(rtb, tmp_path):
         b.load_tree(str(tmp_path / "short.kd"))
     bad = bytearray(blob)
     N = 2 * len(pts) - 1
-    off = 32 + 4 * 6 * N  # first entry of left[]
+    assert blob[:8] == b"RTBKD2\0\0"
+    off = 40 + 4 * 6 * N  # first entry of left[] (header: magic, num_tri, num_nodes, point hash, payload hash)
     bad[off:off + 4] = (N + 5).to_bytes(4, "little")
     (tmp_path / "bad.kd").write_bytes(bytes(bad))
-    with pytest.raises(rtb.RtbError):
+    with pytest.raises(rtb.RtbError, match="payload hash"):
         b.load_tree(str(tmp_path / "bad.kd"))
     a.close(); b.close(); other.close()
+
+
+def _tree_file_v1(pts, left, tri, cut):
+    """A version-1 cache file (no payload hash) with the given structure: what a crafted file could hold."""
+    import struct
+    N = len(left)
+    h = 0xcbf29ce484222325
+    for byte in np.ascontiguousarray(pts, np.float32).tobytes():
+        h = ((h ^ byte) * 0x100000001b3) & 0xffffffffffffffff
+    return (b"RTBKD1\0\0" + struct.pack("<QQQ", len(pts), N, h) + np.zeros(6 * N, np.float32).tobytes() + np.asarray(left, np.int32).tobytes() +
+            np.asarray(tri, np.int32).tobytes() + np.zeros(2 * N, np.float32).tobytes() + np.asarray(cut, np.uint8).tobytes())
+
+
+def test_tree_cache_rejects_structures_the_kernels_cannot_walk(rtb, tmp_path):
+    """a structurally valid chain deeper than the traversal stack, a node with two parents and a triangle named by
+    two leaves must all be refused (the render kernels push without a bound check)."""
+    n = 48
+    pts = rtb.geodesic_mesh(2)[:n].copy()
+    m = rtb.Trixel(pts, require_device=False)
+    N = 2 * n - 1
+    # (1) a left-leaning chain: node 2k has children 2k+1 (leaf) and 2k+2 -> depth 47 > 38, otherwise a perfectly valid tree
+    left = [-1] * N; tri = [-1] * N
+    t = 0
+    for i in range(0, N - 1, 2):
+        left[i] = i + 1
+        tri[i + 1] = t; t += 1
+    tri[N - 1] = t
+    path = tmp_path / "deep.kd"
+    path.write_bytes(_tree_file_v1(pts, left, tri, [0] * N))
+    with pytest.raises(rtb.RtbError, match="deeper|damaged"):
+        m.load_tree(str(path))
+    # the same chain cut off at an allowed depth loads (the validator is not simply refusing version-1 files)
+    n2 = 20
+    pts2 = pts[:n2].copy(); m2 = rtb.Trixel(pts2, require_device=False); N2 = 2 * n2 - 1
+    left2 = [-1] * N2; tri2 = [-1] * N2; t = 0
+    for i in range(0, N2 - 1, 2):
+        left2[i] = i + 1; tri2[i + 1] = t; t += 1
+    tri2[N2 - 1] = t
+    ok = tmp_path / "ok.kd"
+    ok.write_bytes(_tree_file_v1(pts2, left2, tri2, [0] * N2))
+    m2.load_tree(str(ok))
+    # (2) two parents: node 0 and node 2 both name node 3 as their left child
+    two = list(left2); two[2] = 1
+    (tmp_path / "two.kd").write_bytes(_tree_file_v1(pts2, two, tri2, [0] * N2))
+    with pytest.raises(rtb.RtbError):
+        m2.load_tree(str(tmp_path / "two.kd"))
+    # (3) one triangle named by two leaves (and one by none)
+    dup = list(tri2); dup[N2 - 1] = 0
+    (tmp_path / "dup.kd").write_bytes(_tree_file_v1(pts2, left2, dup, [0] * N2))
+    with pytest.raises(rtb.RtbError):
+        m2.load_tree(str(tmp_path / "dup.kd"))
+    m.close(); m2.close()
+
+
+def test_set_matrix_is_render_only_state(rtb):
+    """rtb_object_set_matrix replaces the rows but not the recurrence's quaternion / faces; transform calls are
+    refused until add_object restarts the recurrence (no GPU: handles are created without device memory)."""
+    import ctypes
+    lib = rtb.lib
+    o = ctypes.c_void_p()
+    pts = rtb.geodesic_mesh(2)
+    m = rtb.Trixel(pts, require_device=False)
+    assert lib.rtb_object_create(m.h, ctypes.byref(o)) == 0
+    m12 = (ctypes.c_float * 12)(*range(12))
+    assert lib.rtb_object_set_matrix(o, m12) == 5  # RTB_ERR_STATE: not added to a camera
+    lib.rtb_object_destroy(o)
+    m.close()
 
 
 def test_bench_reference_arm_contract(tmp_path):

@@ -2,8 +2,9 @@
 
     python tools/profile_summary.py gpurun_out/x.ncu-rep profiles/x.txt ["command line that was profiled"]
     python tools/profile_summary.py --launches gpurun_out/launches.csv profiles/launches.txt
+    python tools/profile_summary.py --traffic profiles/x_traffic.json workload=gpurun_out/x.ncu-rep:frames_per_launch[:profiles/x.txt] ...
 """
-import csv, io, subprocess, sys
+import csv, io, json, subprocess, sys
 
 KEYS = ["Duration", "Elapsed Cycles", "SM Frequency", "SM Active Cycles", "Executed Ipc Active", "Issue Slots Busy", "Executed Instructions ",
         "Avg. Active Threads Per Warp", "Avg. Not Predicated Off Threads Per Warp", "Registers Per Thread", "Theoretical Occupancy", "Achieved Occupancy",
@@ -75,8 +76,44 @@ def report(rep, dst, cmdline):
         f.write(lines)
 
 
+def traffic(dst, specs):
+    """profiles/*_traffic.json: what bench.py's roofline reads -- DRAM bytes, executed warp instructions, issue-slot use and
+    L2 / L1 hit rates of ONE render launch per workload, straight from the raw page of its `ncu --set full` capture."""
+    out = {"_comment": "per workload: dram__bytes_read.sum + dram__bytes_write.sum, smsp__inst_executed.sum and friends of ONE "
+                       "render_stream_kernel launch (a whole bench step), from the ncu --set full captures named in `report` "
+                       "(tools/profile_summary.py --traffic). bench.py copies its workload's values into roofline.traffic / legs."}
+    for spec in specs:
+        workload, _, rest = spec.partition("=")
+        parts = rest.split(":")
+        rep, frames = parts[0], int(parts[1])
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+
+        def get(name, scale_units=True):
+            i = hdr.index(name)
+            v = float(vals[i].replace(",", ""))
+            u = units[i].lower()
+            if scale_units:
+                v *= {"kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12, "byte": 1.0}.get(u, 1.0)
+            return v
+        rd, wr = get("dram__bytes_read.sum"), get("dram__bytes_write.sum")
+        out[workload] = {"dram_read_mb": rd / 1e6, "dram_write_mb": wr / 1e6, "bytes": rd + wr, "frames_per_launch": frames,
+                         "inst_executed": get("smsp__inst_executed.sum", False),
+                         "issue_slots_busy_pct": get("sm__inst_issued.avg.pct_of_peak_sustained_active", False) if "sm__inst_issued.avg.pct_of_peak_sustained_active" in hdr else None,
+                         "threads_per_inst": get("smsp__thread_inst_executed_per_inst_executed.ratio", False),
+                         "l2_hit_pct": get("lts__t_sector_hit_rate.pct", False), "l1_hit_pct": get("l1tex__t_sector_hit_rate.pct", False),
+                         "duration_under_ncu_ms": get("gpu__time_duration.sum", False) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[hdr.index("gpu__time_duration.sum")].lower(), 1.0),
+                         "report": parts[2] if len(parts) > 2 else rep}
+    with open(dst, "w") as f:
+        json.dump(out, f, indent=1)
+        f.write("\n")
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "--launches":
+    if sys.argv[1] == "--traffic":
+        traffic(sys.argv[2], sys.argv[3:])
+    elif sys.argv[1] == "--launches":
         launches(sys.argv[2], sys.argv[3])
     else:
         report(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
