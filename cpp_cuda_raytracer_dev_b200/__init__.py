@@ -36,7 +36,7 @@ EXPORTS = [
     "rtb_camera_counters", "rtb_camera_counters_ex", "rtb_camera_destroy", "rtb_object_create", "rtb_object_transform", "rtb_object_get_matrix",
     "rtb_object_set_matrix", "rtb_object_destroy", "rtb_object_render", "rtb_render_frame", "rtb_camera_set_lights", "rtb_camera_set_shadows", "rtb_camera_set_sample_rate", "rtb_camera_object_id_base",
     "rtb_camera_render_scene", "rtb_camera_render_scene_device_async", "rtb_render_sweep",
-    "rtb_render_frames_device_async", "rtb_render_frames_push_async", "rtb_render_frames_push_striped_async", "rtb_fill_frames_device_async", "rtb_peer_alloc", "rtb_peer_free", "rtb_peer_export", "rtb_peer_open", "rtb_peer_close", "rtb_peer_read", "rtb_object_transform_host", "rtb_transform_sequence_host", "rtb_device_props", "rtb_launch_count", "rtb_tile_major_elements", "rtb_compose_tiles_device_async", "rtb_selftest_exact", "rtb_measure_l2_read_bandwidth",
+    "rtb_render_frames_device_async", "rtb_render_frames_push_async", "rtb_render_frames_push_striped_async", "rtb_fill_frames_device_async", "rtb_peer_alloc", "rtb_peer_free", "rtb_peer_export", "rtb_peer_open", "rtb_peer_close", "rtb_peer_read", "rtb_object_transform_host", "rtb_transform_sequence_host", "rtb_device_props", "rtb_launch_count", "rtb_tile_major_elements", "rtb_compose_tiles_device_async", "rtb_selftest_exact", "rtb_measure_l2_read_bandwidth", "rtb_measure_host_fill_bandwidth",
 ]
 
 
@@ -111,6 +111,7 @@ def _load():
     L.rtb_render_frames_push_striped_async.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_uint32, C.c_int32, vp, vp, vp]
     L.rtb_fill_frames_device_async.argtypes = [vp, C.c_int32, vp, vp, vp]
     L.rtb_measure_l2_read_bandwidth.argtypes = [C.c_size_t, C.c_int, C.POINTER(C.c_double)]
+    L.rtb_measure_host_fill_bandwidth.argtypes = [C.c_size_t, C.c_int, C.POINTER(C.c_double)]
     L.rtb_peer_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.rtb_peer_free.argtypes = [vp]
     L.rtb_peer_export.argtypes = [vp, vp]
@@ -438,6 +439,13 @@ def measure_l2_read_bandwidth(nbytes=32 << 20, iters=200):
     """GB/s of L1-bypassing 16-byte loads over an L2-resident buffer (the L2 leg of the roofline)."""
     out = C.c_double()
     _check(lib.rtb_measure_l2_read_bandwidth(nbytes, iters, C.byref(out)), "rtb_measure_l2_read_bandwidth")
+    return out.value
+
+
+def measure_host_fill_bandwidth(nbytes=512 << 20, threads=0):
+    """GB/s at which `threads` host threads (0 = all) fill pinned memory with streaming stores."""
+    out = C.c_double(0.0)
+    _check(lib.rtb_measure_host_fill_bandwidth(nbytes, threads, C.byref(out)), "rtb_measure_host_fill_bandwidth")
     return out.value
 
 

@@ -1,8 +1,10 @@
 // rtb_api.cu -- the C ABI declared in include/rtb.h: handles, device memory, launches.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -131,6 +133,12 @@ struct rtb_camera {
     int sample_rate = 0;          // Camera::render_properites::sample_rate (Camera.h:46, Camera.cpp:71)
     bool frame_rendered = false;  // the device frame holds a render (background + shaded hits of every pixel)
     bool frame_on_host = false;   // ... and h_bgra / h_ids hold that very frame already
+    // Single-frame path (rtb_object_render): the kernel stores the frame straight into h_bgra / h_ids (pinned, mapped),
+    // and only where it can differ from what they hold -- host_rect is the pixel rectangle outside which the host frame
+    // is known to be background / -1 (the root-box rectangle of the frame last stored there this way).
+    bool host_rect_valid = false;
+    int host_rect[4] = {0, 0, -1, -1};
+    bool device_frame_stale = false;  // the last frame went to the host only: d_bgra / d_ids hold an older one
 };
 
 struct rtb_object {
@@ -172,6 +180,13 @@ struct Knobs {
     int l2_window = 1;    // persisting L2 window: 0 off, 1 node records, 2 nodes + triangles (takes effect at add_object)
     int no_rect = 0;      // 1: frame records carry the whole frame as the root-box rectangle
     int frame_order = 1;  // multi-frame launches work through their frames sorted by viewing direction (order_frames)
+    int host_direct = 1;  // rtb_object_render stores its frame straight into the camera's host buffers (0: device frame + copy)
+    int sweep_direct = 1; // rtb_render_sweep into pinned caller buffers: host threads pre-fill the background, the kernel stores the rest
+    int host_fill_threads = 0;  // threads of that pre-fill, 0 = min(12, CPUs this process may run on)
+    int t_active_inline = 30;   // single-frame launches: t_active (a warp that sees the empty queue early shares its long rays early)
+    int steal_spin = 8;         // ... and how many iterations a draining warp runs between two looks for lanes to share with (power of two)
+    int inline_prefetch = 1;    // ... and whether it asks for both children's records ahead of the decision
+    int sweep_chunk_mb = 256;   // ... and the size of the chunks (MB of host frames) in which fill and render alternate
     int l2_carve_mb = 0;  // persisting L2 carve-out in MB, 0 = the size of the window
 };
 Knobs& knobs() {
@@ -180,10 +195,23 @@ Knobs& knobs() {
         v.unit_shift = env_int("RTB_UNIT_SHIFT", v.unit_shift); v.t_active = env_int("RTB_T_ACTIVE", v.t_active);
         v.t_leaf = env_int("RTB_T_LEAF", v.t_leaf); v.tail5 = env_int("RTB_TAIL5", v.tail5); v.tail6 = env_int("RTB_TAIL6", v.tail6);
         v.reserve_sms = env_int("RTB_RESERVE_SMS", v.reserve_sms); v.l2_window = env_int("RTB_L2_WINDOW", v.l2_window);
-        v.no_rect = env_int("RTB_NO_RECT", v.no_rect); v.frame_order = env_int("RTB_FRAME_ORDER", v.frame_order); v.l2_carve_mb = env_int("RTB_L2_CARVE_MB", v.l2_carve_mb);
+        v.no_rect = env_int("RTB_NO_RECT", v.no_rect); v.frame_order = env_int("RTB_FRAME_ORDER", v.frame_order);
+        v.host_direct = env_int("RTB_HOST_DIRECT", v.host_direct); v.sweep_direct = env_int("RTB_SWEEP_DIRECT", v.sweep_direct);
+        v.host_fill_threads = env_int("RTB_HOST_FILL_THREADS", v.host_fill_threads); v.sweep_chunk_mb = env_int("RTB_SWEEP_CHUNK_MB", v.sweep_chunk_mb);
+        v.t_active_inline = env_int("RTB_T_ACTIVE_INLINE", v.t_active_inline); v.steal_spin = env_int("RTB_STEAL_SPIN", v.steal_spin);
+        v.inline_prefetch = env_int("RTB_INLINE_PREFETCH", v.inline_prefetch); v.l2_carve_mb = env_int("RTB_L2_CARVE_MB", v.l2_carve_mb);
         return v;
     }();
     return k;
+}
+
+int host_fill_threads() {
+    int t = knobs().host_fill_threads;
+    if (t > 0) return t;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    t = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : 1;
+    return std::max(1, std::min(12, t));  // measured on the pool's hosts: 8 threads already reach the memory system's limit
 }
 
 int ensure_host_tree(rtb_mesh* m) {
@@ -329,7 +357,8 @@ bool order_frames(const rtb_object* o, const rtb_camera* c, int num_frames) {
 // single frame -- handed over as `inline_record` and carried in the kernel's parameters (no upload, d_frames == nullptr).
 int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, const float* inline_record, int num_frames, int tile_first,
                   int tile_stride, uint32_t flags, uint32_t* d_bgra, int32_t* d_ids, cudaStream_t stream, int push_owners = 0,
-                  uint32_t* const* push_bgra = nullptr, int32_t* const* push_ids = nullptr, const int* d_frame_order = nullptr) {
+                  uint32_t* const* push_bgra = nullptr, int32_t* const* push_ids = nullptr, const int* d_frame_order = nullptr,
+                  const int* push_prev_rect = nullptr) {
     using namespace rtb;
     const SceneArrays* sc = o->scene;
     RenderParams P;
@@ -359,6 +388,10 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, const flo
     P.push_owners = std::max(push_owners, 1);
     for (int k = 0; k < push_owners; k++) { P.push_bgra[k] = push_bgra ? push_bgra[k] : nullptr; P.push_ids[k] = push_ids ? push_ids[k] : nullptr; }
     P.push_skip_background = (push && (flags & RTB_RENDER_PUSH_PREFILLED)) ? 1 : 0;
+    if (push && push_prev_rect) {
+        P.push_skip_background = 2;
+        std::memcpy(P.push_prev_rect, push_prev_rect, sizeof P.push_prev_rect);
+    }
     P.tile_major = ((flags & RTB_RENDER_TILE_MAJOR) || push) ? 1 : 0;
     P.frame_stride = P.tile_major ? (long long)((tiles + tile_stride - 1) / tile_stride) * kTile * kTile : (long long)b.W * b.H;
     P.work_counter = o->d_work;
@@ -368,11 +401,12 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, const flo
     if (P.total_items == 0) return RTB_OK;
 
     const bool cull = !(flags & RTB_RENDER_NO_CULL), count = (flags & RTB_RENDER_COUNTERS) != 0;
-    const bool inl = inline_record != nullptr && !count && !push;
-    if (inline_record && !inl) return fail(RTB_ERR_ARG, "render: inline frame records are for plain single-frame launches");
+    const bool inl = inline_record != nullptr && !count;
+    if (inline_record && !inl) return fail(RTB_ERR_ARG, "render: inline frame records are for single-frame launches without counters");
     void (*kern)(const RenderParams);
     int variant;
-    if (push) { kern = cull ? render_stream_kernel<true, false, true> : render_stream_kernel<false, false, true>; variant = 4 + (cull ? 1 : 0); }
+    if (push && inl) { kern = cull ? render_stream_kernel<true, false, true, true> : render_stream_kernel<false, false, true, true>; variant = 8 + (cull ? 1 : 0); }
+    else if (push) { kern = cull ? render_stream_kernel<true, false, true> : render_stream_kernel<false, false, true>; variant = 4 + (cull ? 1 : 0); }
     else if (inl) { kern = cull ? render_stream_kernel<true, false, false, true> : render_stream_kernel<false, false, false, true>; variant = 6 + (cull ? 1 : 0); }
     else {
         kern = cull ? (count ? render_stream_kernel<true, true, false> : render_stream_kernel<true, false, false>)
@@ -392,7 +426,13 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, const flo
     while (shift > 5 && (pixels >> shift) < warps_total * 4) shift--;
     const Knobs& K = knobs();
     P.unit_shift = std::min(10, std::max(5, K.unit_shift > 0 ? K.unit_shift : shift));
-    P.t_active = std::min(31, std::max(0, K.t_active));
+    P.t_active = std::min(31, std::max(0, inl ? K.t_active_inline : K.t_active));
+    {
+        int spin = 1;
+        while (spin < K.steal_spin && spin < 64) spin <<= 1;
+        P.steal_mask = spin - 1;
+    }
+    P.prefetch = K.inline_prefetch ? 1 : 0;
     P.t_leaf = std::max(1, K.t_leaf);
     // Segments of decreasing unit size towards the end of the launch (see RenderParams::seg_*): a unit handed out late
     // is worked through by ONE warp while the queue is already empty, so late units must be small.  Measured on the
@@ -512,6 +552,13 @@ int rtb_set_knob(const char* name, int value) {
     else if (n == "l2_window") k.l2_window = value;
     else if (n == "no_rect") k.no_rect = value;
     else if (n == "frame_order") k.frame_order = value;
+    else if (n == "host_direct") k.host_direct = value;
+    else if (n == "sweep_direct") k.sweep_direct = value;
+    else if (n == "host_fill_threads") k.host_fill_threads = value;
+    else if (n == "sweep_chunk_mb") k.sweep_chunk_mb = value;
+    else if (n == "t_active_inline") k.t_active_inline = value;
+    else if (n == "steal_spin") k.steal_spin = value;
+    else if (n == "inline_prefetch") k.inline_prefetch = value;
     else if (n == "l2_carve_mb") k.l2_carve_mb = value;
     else return fail(RTB_ERR_ARG, "set_knob: unknown knob " + n);
     return RTB_OK;
@@ -909,6 +956,7 @@ int rtb_camera_color_pixels(rtb_camera* cam, uint8_t tag) {
         return fail(RTB_ERR_ARG, "color_pixels: unknown tag");
     }
     if (!cam->frame_on_host) {
+        cam->host_rect_valid = false;  // the host frame becomes a copy of the device frame: nothing is known about its background
         RTB_CUDA(cudaMemcpyAsync(cam->h_bgra, cam->d_bgra, sizeof(uint32_t) * (size_t)cam->pixels, cudaMemcpyDeviceToHost, cam->stream));
         RTB_CUDA(cudaMemcpyAsync(cam->h_ids, cam->d_ids, sizeof(int32_t) * (size_t)cam->pixels, cudaMemcpyDeviceToHost, cam->stream));
     }
@@ -1030,6 +1078,20 @@ void rtb_object_destroy(rtb_object* obj) {
 // ---- render --------------------------------------------------------------------------------------
 
 namespace {
+// the camera's tile-major staging of the push variants holds at least `need` elements per array
+int ensure_push_staging(rtb_camera* cam, size_t need) {
+    if (cam->push_elements >= need) return RTB_OK;
+    // the staging grows: kernels of any object of this camera that still stage into the old one must finish
+    for (rtb_object* other : cam->objects)
+        if (other->launch_pending) { RTB_CUDA(cudaEventSynchronize(other->ev_launch)); other->launch_pending = false; }
+    dfree(cam->push_bgra); dfree(cam->push_ids);
+    cam->push_elements = 0;
+    RTB_CUDA(cudaMalloc(&cam->push_bgra, 4 * need));
+    RTB_CUDA(cudaMalloc(&cam->push_ids, 4 * need));
+    cam->push_elements = need;
+    return RTB_OK;
+}
+
 // One frame of the object's current transform into the camera's device frame, no synchronisation: the record travels
 // in the kernel parameters, the work counter is never reset -- the launch is the only stream operation.
 int render_current(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
@@ -1044,12 +1106,32 @@ int render_current(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
         rc = order_after_previous(obj, cam->stream);
         if (!rc) rc = upload_frames(obj, 1, cam->stream);
         if (!rc) rc = launch_render(obj, cam, obj->d_frames, nullptr, 1, 0, 1, flags, cam->d_bgra, cam->d_ids, cam->stream);
+    } else if (knobs().host_direct) {
+        // Straight into the camera's host frame: the warps store their finished work units as row segments into the pinned,
+        // mapped buffers (the peer-push variant with the host as the owner), so the frame crosses PCIe while the rest of
+        // it is still being traced and no copy follows the kernel.  Work units that hold nothing but background are
+        // stored only where the host frame may hold something else: inside the rectangle of the frame stored before.
+        rc = ensure_push_staging(cam, (size_t)rtb_tile_major_elements(cam, 1));
+        if (rc) return rc;
+        int prev[4] = {0, 0, cam->basis.W - 1, cam->basis.H - 1};
+        if (cam->host_rect_valid) std::memcpy(prev, cam->host_rect, sizeof prev);
+        uint32_t* owner_bgra = cam->h_bgra;  // unified addressing: a pinned allocation has the same address on the device
+        int32_t* owner_ids = cam->h_ids;
+        rc = launch_render(obj, cam, nullptr, record, 1, 0, 1, flags, cam->push_bgra, cam->push_ids, cam->stream, 1, &owner_bgra, &owner_ids, nullptr, prev);
+        if (rc) { cam->host_rect_valid = false; return rc; }
+        std::memcpy(cam->host_rect, record + 12, sizeof cam->host_rect);
+        cam->host_rect_valid = true;
+        cam->frame_rendered = true;
+        cam->frame_on_host = true;  // once the stream has drained, which is what rtb_camera_color_pixels waits for
+        cam->device_frame_stale = true;
+        return RTB_OK;
     } else {
         rc = launch_render(obj, cam, nullptr, record, 1, 0, 1, flags, cam->d_bgra, cam->d_ids, cam->stream);
     }
     if (rc) return rc;
     cam->frame_rendered = true;
     cam->frame_on_host = false;
+    cam->device_frame_stale = false;
     return RTB_OK;
 }
 }  // namespace
@@ -1194,17 +1276,8 @@ int rtb_render_frames_push_striped_async(rtb_object* obj, rtb_camera* cam, int32
     cudaStream_t s = stream ? (cudaStream_t)stream : cam->stream;
     rc = ensure_frames(obj, num_frames);
     if (rc) return rc;
-    const size_t need = (size_t)num_frames * (size_t)rtb_tile_major_elements(cam, tile_stride);
-    if (cam->push_elements < need) {
-        // the tile staging grows: kernels of any object of this camera that still stage into the old one must finish
-        for (rtb_object* other : cam->objects)
-            if (other->launch_pending) { RTB_CUDA(cudaEventSynchronize(other->ev_launch)); other->launch_pending = false; }
-        dfree(cam->push_bgra); dfree(cam->push_ids);
-        cam->push_elements = 0;
-        RTB_CUDA(cudaMalloc(&cam->push_bgra, 4 * need));
-        RTB_CUDA(cudaMalloc(&cam->push_ids, 4 * need));
-        cam->push_elements = need;
-    }
+    rc = ensure_push_staging(cam, (size_t)num_frames * (size_t)rtb_tile_major_elements(cam, tile_stride));
+    if (rc) return rc;
     for (int f = 0; f < num_frames; f++) fill_frame_record(obj->scene, cam, m12 + 12 * (size_t)f, obj->h_frames + rtb::kFrameStride * (size_t)f);
     const bool ordered = order_frames(obj, cam, num_frames);
     rc = order_after_previous(obj, s);
@@ -1296,11 +1369,48 @@ int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32
     rc = upload_frames(obj, num_frames, cam->stream);
     if (rc) return rc;
 
-    // ring of two device chunks; chunk k+1 renders while chunk k streams to the host
     const size_t P = (size_t)cam->pixels;
-    // chunk = the frames rendered by one launch and copied out together.  Small enough that the first
-    // copy starts early (the sweep is PCIe-bound: 8 bytes per pixel leave the device), large enough to
-    // amortise launches: about 16 MB per buffer.
+    // caller buffers that are already pinned can be written by the device directly
+    auto pinned_device_pointer = [](const void* p) -> void* {
+        if (!p) return nullptr;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+    };
+    void* const dev_bgra = pinned_device_pointer(bgra_out);
+    void* const dev_ids = pinned_device_pointer(ids_out);
+    const bool direct_bgra = dev_bgra != nullptr, direct_ids = dev_ids != nullptr;
+
+    // ---- pinned caller buffers: no copy engine at all -------------------------------------------------------------------
+    // Most of a frame is background (94 % of the pixels of the default view), and background is a constant: the HOST writes
+    // it, with streaming stores on a few threads (measured ~190 GB/s on the pool's hosts, against the ~57 GB/s a device-to-host
+    // copy gets over PCIe), chunk by chunk, while the GPU traces the chunk before and stores only the work units that contain
+    // something else straight into the caller's buffers (the peer-push variant of the kernel with the host as the owner of
+    // the frames: 128-byte row stores over PCIe).  What crosses the bus is the picture, not the wallpaper.
+    if (knobs().sweep_direct && !(flags & RTB_RENDER_COUNTERS) && (bgra_out || ids_out) && (!bgra_out || direct_bgra) && (!ids_out || direct_ids)) {
+        const size_t frame_bytes = 4 * P * ((bgra_out ? 1u : 0u) + (ids_out ? 1u : 0u));
+        const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)num_frames, ((size_t)std::max(1, knobs().sweep_chunk_mb) << 20) / frame_bytes));
+        rc = ensure_push_staging(cam, (size_t)chunk * (size_t)rtb_tile_major_elements(cam, 1));
+        if (rc) return rc;
+        const rtb::CameraBasis& b = cam->basis;
+        const uint32_t bg = ((uint32_t)b.background[3] << 24) | ((uint32_t)b.background[0] << 16) | ((uint32_t)b.background[1] << 8) | b.background[2];
+        const int threads = host_fill_threads();
+        for (int f0 = 0; f0 < num_frames; f0 += chunk) {
+            const int nf = std::min(chunk, num_frames - f0);
+            if (bgra_out) rtb::fill_words(bgra_out + (size_t)f0 * P, (size_t)nf * P, bg, threads);
+            if (ids_out) rtb::fill_words(reinterpret_cast<uint32_t*>(ids_out) + (size_t)f0 * P, (size_t)nf * P, 0xffffffffu, threads);
+            uint32_t* owner_bgra = bgra_out ? static_cast<uint32_t*>(dev_bgra) + (size_t)f0 * P : nullptr;
+            int32_t* owner_ids = ids_out ? static_cast<int32_t*>(dev_ids) + (size_t)f0 * P : nullptr;
+            rc = launch_render(obj, cam, obj->d_frames + rtb::kFrameStride * (size_t)f0, nullptr, nf, 0, 1, flags | RTB_RENDER_PUSH_PREFILLED,
+                               bgra_out ? cam->push_bgra : nullptr, ids_out ? cam->push_ids : nullptr, cam->stream, 1,
+                               bgra_out ? &owner_bgra : nullptr, ids_out ? &owner_ids : nullptr);
+            if (rc) return rc;
+        }
+        RTB_CUDA(cudaStreamSynchronize(cam->stream));
+        return RTB_OK;
+    }
+
+    // ---- pageable caller buffers: ring of two device chunks; chunk k+1 renders while chunk k streams to the host ------------
     int chunk_frames = (int)std::max<size_t>(1, std::min<size_t>((size_t)num_frames, (size_t)(16u << 20) / (P * 4)));
     if (cam->ring_frames < chunk_frames) {
         for (int k = 0; k < 2; k++) {
@@ -1315,14 +1425,6 @@ int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32
         cam->ring_frames = chunk_frames;
     }
     chunk_frames = std::min(chunk_frames, cam->ring_frames);
-    // caller buffers that are already pinned receive the DMA directly
-    auto is_pinned = [](const void* p) {
-        if (!p) return false;
-        cudaPointerAttributes a;
-        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-        return a.type == cudaMemoryTypeHost;
-    };
-    const bool direct_bgra = is_pinned(bgra_out), direct_ids = is_pinned(ids_out);
     const int chunks = (num_frames + chunk_frames - 1) / chunk_frames;
     auto drain = [&](int k) -> int {  // staging -> caller memory for chunk k
         const int slot = k & 1, f0 = k * chunk_frames, nf = std::min(chunk_frames, num_frames - f0);
@@ -1432,6 +1534,23 @@ int rtb_measure_l2_read_bandwidth(size_t bytes, int iters, double* gb_per_s) {
     cudaFree(buf); cudaFree(sink);
     if (e != cudaSuccess) return fail(RTB_ERR_CUDA, std::string("measure_l2: ") + cudaGetErrorString(e));
     *gb_per_s = (double)n16 * 16.0 * iters / ((double)ms * 1e-3) / 1e9;
+    return RTB_OK;
+}
+
+int rtb_measure_host_fill_bandwidth(size_t bytes, int threads, double* gb_per_s) {
+    if (!gb_per_s || bytes < (1u << 20)) return fail(RTB_ERR_ARG, "measure_host_fill: bad argument");
+    uint32_t* buf = nullptr;
+    RTB_CUDA(cudaSetDevice(g_device));
+    RTB_CUDA(cudaMallocHost(&buf, bytes));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {  // the first pass also touches the pages
+        const auto t0 = std::chrono::steady_clock::now();
+        rtb::fill_words(buf, bytes / 4, 0x00f08200u + (uint32_t)rep, threads);
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (rep) best = std::max(best, (double)bytes / s / 1e9);
+    }
+    cudaFreeHost(buf);
+    *gb_per_s = best;
     return RTB_OK;
 }
 

@@ -7,11 +7,19 @@
 //     stable LSD radix sort (cub::DeviceRadixSort) over the ids fed in descending order gives exactly that;
 //   * breadth-first, one level per iteration: every node owns the same position range [l,r] in all six
 //     lists; split list = first strict maximum of key[r]-key[l] in the order x1,x0,y1,y0,z1,z0; the other
-//     five lists are stably partitioned by "position in the split list <= m" -- here one flag array, one
-//     device-wide exclusive scan (cub::DeviceScan) and one scatter per list and level, for all nodes of the
-//     level at once (positions of different nodes never mix because offsets are taken relative to l);
-//   * children are numbered in node order (exclusive scan over the level's interior flags), bounds come
-//     from the list ends, leaves take the x1 list's triangle.
+//     five lists are stably partitioned by "position in the split list <= m".
+// The split position is always the middle of the range, so the SHAPE of the tree -- how many nodes a level has, which
+// of them are leaves -- follows from n alone (range sizes of one level differ by at most one); only the choice of the
+// split list and the order inside the lists depend on the data.  The host therefore knows every level's extent in
+// advance and never reads anything back during the build.  A level is five launches for ALL its nodes and ALL six
+// lists at once:
+//     level_nodes_kernel   one thread per node: own bounds from the list ends, leaf or split list, children created;
+//     side_kernel          one thread per position of the split lists: one byte per triangle, "goes to the left child";
+//     one exclusive scan   (cub::DeviceScan, two launches) over n+1 six-component flag vectors computed on the fly:
+//                          component k of position i = the side byte of the element of list k at i;
+//     scatter_kernel       one thread per list position: the six stable partitions (offsets = scan differences
+//                          relative to the node's range start, so ranges never mix), node of position.
+// (Round 1: flag / scan / scatter / copy per list and two blocking 4-byte read-backs per level, ~35 launches per level.)
 // cub's radix sort and scan are library primitives used for the build only; the ray-cast hot path does not
 // touch them.
 #include <cub/device/device_radix_sort.cuh>
@@ -19,8 +27,13 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
+
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "rtb_host.hpp"
 
@@ -56,112 +69,128 @@ __global__ void sort_input_kernel(const float* __restrict__ key, int n, unsigned
     ukey[i] = u;
     ids[i] = t;
 }
-__global__ void rank_kernel(const int* __restrict__ order, int n, int* __restrict__ rank) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) rank[order[i]] = i;
-}
-
 struct Lists {
     const float* key;  // 6 x n
-    int* order;        // 6 x n (current)
-    int* rank;         // 6 x n
+    const int* order;  // 6 x n (the level's input order)
     int n;
 };
 __device__ __forceinline__ float key_at(const Lists& L, int k, int pos) { return L.key[(long long)k * L.n + L.order[(long long)k * L.n + pos]]; }
 
-// one thread per node of the level: leaf or split choice (Trixel.h:172-205)
-__global__ void level_nodes_kernel(Lists L, int level_begin, int count, const int* __restrict__ lo, const int* __restrict__ hi,
-                                   const int* __restrict__ parent, unsigned char* __restrict__ cut, int* __restrict__ tri,
-                                   int* __restrict__ interior /* count */) {
+// one thread per node of the level: the node's own bounds from the ends of its range in the six lists (Trixel.h:150,
+// 345-350), then leaf (Trixel.h:194-202) or split choice (Trixel.h:172-205) and the two children (Trixel.h:329-352).
+// child_scan == nullptr: every node of the level is interior, the children of the q-th node are 2q, 2q+1 of the next level.
+__global__ void level_nodes_kernel(Lists L, int level_begin, int count, int next_begin, const int* __restrict__ child_scan, int* __restrict__ lo,
+                                   int* __restrict__ hi, unsigned char* __restrict__ cut, int* __restrict__ tri, int* __restrict__ left,
+                                   float* __restrict__ bounds, int* __restrict__ rec) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= count) return;
     const int node = level_begin + q, l = lo[node], r = hi[node];
+    float a[6], b[6];
+    for (int k = 0; k < 6; k++) { a[k] = key_at(L, k, l); b[k] = key_at(L, k, r); }
+    float* B = bounds + 6ll * node;  // x0,x1,y0,y1,z0,z1
+    B[0] = a[3]; B[1] = b[0]; B[2] = a[4]; B[3] = b[1]; B[4] = a[5]; B[5] = b[2];
     if (r == l) {
-        cut[node] = node == 0 ? 5 : cut[parent[node]];  // Trixel.h:152,194
-        tri[node] = L.order[l];                          // x1 list, Trixel.h:202
-        interior[q] = 0;
+        tri[node] = L.order[l];  // x1 list, Trixel.h:202 (the split list is inherited: written by the parent)
+        left[node] = -1;
         return;
     }
     const int scan[6] = {0, 3, 1, 4, 2, 5};
-    float best = __fsub_rn(key_at(L, 0, r), key_at(L, 0, l));
+    float best = __fsub_rn(b[0], a[0]);
     int c = 0;
     for (int s = 1; s < 6; s++) {
         const int k = scan[s];
-        const float spread = __fsub_rn(key_at(L, k, r), key_at(L, k, l));
+        const float spread = __fsub_rn(b[k], a[k]);
         if (spread > best) { best = spread; c = k; }
     }
     cut[node] = (unsigned char)c;
     tri[node] = -1;
-    interior[q] = 1;
-}
-// one thread per list position: does the element go to the left child?  (Trixel.h:237-259)
-__global__ void flags_kernel(Lists L, int k, const int* __restrict__ node_of_pos, const int* __restrict__ lo, const int* __restrict__ hi,
-                             const unsigned char* __restrict__ cut, int* __restrict__ flag) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L.n) return;
-    const int node = node_of_pos[i], l = lo[node], r = hi[node];
-    int f = 0;
-    if (r > l && cut[node] != k) {
-        const int m = l + (r - l) / 2;
-        f = L.rank[(long long)cut[node] * L.n + L.order[(long long)k * L.n + i]] <= m;
-    }
-    flag[i] = f;
-}
-// stable partition of list k inside every node range, using the device-wide exclusive scan of the flags
-__global__ void scatter_kernel(Lists L, int k, const int* __restrict__ node_of_pos, const int* __restrict__ lo, const int* __restrict__ hi,
-                               const unsigned char* __restrict__ cut, const int* __restrict__ flag, const int* __restrict__ scan,
-                               int* __restrict__ order_out /* n, list k */) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L.n) return;
-    const int node = node_of_pos[i], l = lo[node], r = hi[node];
-    const int t = L.order[(long long)k * L.n + i];
-    int dst = i;
-    if (r > l && cut[node] != k) {
-        const int m = l + (r - l) / 2;
-        const int left_before = scan[i] - scan[l];
-        dst = flag[i] ? l + left_before : (m + 1) + ((i - l) - left_before);
-    }
-    order_out[dst] = t;
-    L.rank[(long long)k * L.n + t] = dst;
-}
-// one thread per node of the level: create the two children (Trixel.h:329-352)
-__global__ void children_kernel(Lists L, int level_begin, int count, int next_begin, const int* __restrict__ child_scan, int* __restrict__ lo,
-                                int* __restrict__ hi, int* __restrict__ parent, int* __restrict__ left, float* __restrict__ bounds,
-                                int* __restrict__ rec) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= count) return;
-    const int node = level_begin + q, l = lo[node], r = hi[node];
-    if (r == l) { left[node] = -1; return; }
     const int m = l + (r - l) / 2;
-    const int cl = next_begin + 2 * child_scan[q], cr = cl + 1;
+    const int cl = next_begin + 2 * (child_scan ? child_scan[q] : q), cr = cl + 1;
     left[node] = cl;
-    lo[cl] = l; hi[cl] = m; parent[cl] = node;
-    lo[cr] = m + 1; hi[cr] = r; parent[cr] = node;
+    lo[cl] = l; hi[cl] = m; cut[cl] = (unsigned char)c;
+    lo[cr] = m + 1; hi[cr] = r; cut[cr] = (unsigned char)c;
     // pre-order rank among interior nodes: the left subtree [l,m] holds m-l interior nodes and follows its parent directly
     rec[cl] = m > l ? rec[node] + 1 : -1;
     rec[cr] = r > m + 1 ? rec[node] + 1 + (m - l) : -1;
-    for (int c = 0; c < 2; c++) {
-        const int a = c ? m + 1 : l, b = c ? r : m;
-        float* B = bounds + 6ll * (c ? cr : cl);  // x0,x1,y0,y1,z0,z1 (Trixel.h:345-350)
-        B[0] = key_at(L, 3, a); B[1] = key_at(L, 0, b);
-        B[2] = key_at(L, 4, a); B[3] = key_at(L, 1, b);
-        B[4] = key_at(L, 5, a); B[5] = key_at(L, 2, b);
-    }
 }
-__global__ void reassign_kernel(int n, int* __restrict__ node_of_pos, const int* __restrict__ lo, const int* __restrict__ hi,
-                                const int* __restrict__ left) {
+
+// Six counters, one per list: the scan's value type.
+struct Six { int v[6]; };
+struct SixSum {
+    __host__ __device__ __forceinline__ Six operator()(const Six& x, const Six& y) const {
+        Six z;
+#pragma unroll
+        for (int k = 0; k < 6; k++) z.v[k] = x.v[k] + y.v[k];
+        return z;
+    }
+};
+// Which child every triangle of an interior node goes to (Trixel.h:237-259): its position in the node's split list is
+// <= m.  One byte per triangle, written from the split list's side -- a 1-byte scatter into an array that stays in L2 --
+// so that the five other lists can ask "left?" with a 1-byte gather instead of a 4-byte gather into a rank array per
+// list (the round-1 builder kept six rank arrays up to date: 6 random reads and 6 random writes per triangle and level).
+__global__ void side_kernel(int n, const int* __restrict__ node_of_pos, const int* __restrict__ lo, const int* __restrict__ hi,
+                            const unsigned char* __restrict__ cut, const int* __restrict__ order, unsigned char* __restrict__ side) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int node = node_of_pos[i], cl = left[node];
-    if (cl < 0) return;
-    const int l = lo[node], r = hi[node], m = l + (r - l) / 2;
-    node_of_pos[i] = i <= m ? cl : cl + 1;
+    const int node = node_of_pos[i], l = lo[node], r = hi[node];
+    if (r == l) return;
+    side[order[(long long)cut[node] * n + i]] = i <= l + (r - l) / 2 ? 1 : 0;
 }
-__global__ void root_bounds_kernel(Lists L, float* __restrict__ bounds) {
-    const int n = L.n;
-    bounds[0] = key_at(L, 3, 0); bounds[1] = key_at(L, 0, n - 1);
-    bounds[2] = key_at(L, 4, 0); bounds[3] = key_at(L, 1, n - 1);
-    bounds[4] = key_at(L, 5, 0); bounds[5] = key_at(L, 2, n - 1);
+// Input of the level's scan, computed where it is consumed: component k at position i is 1 iff the element of list k at
+// position i goes to the left child of its node.  Position n
+// (one past the end) is all zeros, so that scan[i+1] - scan[i] gives every position its own flags back.
+struct GoesLeft {
+    const int* node_of_pos; const int* lo; const int* hi; const unsigned char* cut; const int* order; const unsigned char* side; int n;
+    __host__ __device__ __forceinline__ Six operator()(int i) const {
+        Six f = {{0, 0, 0, 0, 0, 0}};
+        if (i >= n) return f;
+        const int node = node_of_pos[i], l = lo[node], r = hi[node];
+        if (r > l) {
+            const int c = cut[node];
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+                if (k != c) f.v[k] = side[order[(long long)k * n + i]];
+        }
+        return f;
+    }
+};
+struct IsInterior {
+    const int* lo; const int* hi; int level_begin;
+    __host__ __device__ __forceinline__ int operator()(int q) const { return hi[level_begin + q] > lo[level_begin + q] ? 1 : 0; }
+};
+
+// one thread per list position: stable partition of all six lists inside every node range, from the exclusive scan of
+// the GoesLeft vectors; positions of leaves stay where they are.  Also moves every position to its child node.
+__global__ void scatter_kernel(int n, const int* __restrict__ node_of_pos, const int* __restrict__ lo, const int* __restrict__ hi,
+                               const unsigned char* __restrict__ cut, const int* __restrict__ left, const Six* __restrict__ scan,
+                               const int* __restrict__ order, int* __restrict__ order_out, int* __restrict__ node_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int node = node_of_pos[i], l = lo[node], r = hi[node];
+    if (r == l) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) order_out[(long long)k * n + i] = order[(long long)k * n + i];
+        node_out[i] = node;
+        return;
+    }
+    const int c = cut[node], m = l + (r - l) / 2, cl = left[node];
+    const Six base = scan[l], mine = scan[i], next = scan[i + 1];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const int t = order[(long long)k * n + i];
+        int dst = i;
+        if (k != c) {
+            const int left_before = mine.v[k] - base.v[k];
+            dst = (next.v[k] - mine.v[k]) ? l + left_before : (m + 1) + ((i - l) - left_before);
+        }
+        order_out[(long long)k * n + dst] = t;
+    }
+    node_out[i] = i <= m ? cl : cl + 1;
+}
+__global__ void root_init_kernel(int n, int* __restrict__ lo, int* __restrict__ hi, unsigned char* __restrict__ cut, int* __restrict__ rec) {
+    lo[0] = 0; hi[0] = n - 1;
+    cut[0] = 5;               // a single-triangle mesh: the root is a leaf with Trixel.h:152's initial value
+    rec[0] = n > 1 ? 0 : -1;
 }
 // s1 = left child's max, s2 = right child's min on the split axis (Trixel.h:353-376)
 __global__ void split_planes_kernel(int num_nodes, const int* __restrict__ left, const unsigned char* __restrict__ cut,
@@ -216,6 +245,65 @@ done:
     return err;
 }
 
+namespace {
+// The shape of the tree from n alone.  The split position is the middle of the range (Trixel.h:206), so the range sizes of
+// one level take at most two consecutive values; a range of size k >= 2 leaves (k+1)/2 elements to its left child and
+// k/2 to its right one.  Levels are numbered breadth-first, children in the order of their parents (Trixel.h:329).
+struct LevelShape { int begin, count, interior; };
+std::vector<LevelShape> tree_shape(int n) {
+    std::vector<LevelShape> levels;
+    long long size[2] = {n, 0}, many[2] = {1, 0};  // two (range size, number of ranges) classes
+    int begin = 0;
+    for (;;) {
+        const long long count = many[0] + many[1];
+        long long interior = 0;
+        for (int k = 0; k < 2; k++) if (size[k] >= 2) interior += many[k];
+        levels.push_back({begin, (int)count, (int)interior});
+        if (interior == 0) break;
+        begin += (int)count;
+        long long nsize[4], nmany[4]; int classes = 0;
+        for (int k = 0; k < 2; k++) {
+            if (many[k] == 0 || size[k] < 2) continue;
+            const long long parts[2] = {(size[k] + 1) / 2, size[k] / 2};
+            for (long long part : parts) {
+                int at = 0;
+                while (at < classes && nsize[at] != part) at++;
+                if (at == classes) { nsize[classes] = part; nmany[classes] = 0; classes++; }
+                nmany[at] += many[k];
+            }
+        }
+        // (classes <= 2: sizes k and k+1 halve into at most two consecutive values)
+        size[0] = nsize[0]; many[0] = nmany[0];
+        size[1] = classes > 1 ? nsize[1] : 0; many[1] = classes > 1 ? nmany[1] : 0;
+        if (classes > 2) { levels.clear(); return levels; }  // cannot happen; the caller reports it
+    }
+    return levels;
+}
+
+// The work arrays (about 130 bytes per triangle) come from a stream-ordered pool OWNED BY THIS LIBRARY, one per device,
+// which keeps up to 2 GB between builds: mapping and unmapping gigabytes costs more than a ten-million-triangle build
+// (measured: up to 0.5 s).  The process's default pool and its release threshold are not touched.
+cudaMemPool_t build_pool(int device, std::string& err) {
+    static std::mutex lock;
+    static cudaMemPool_t pools[64] = {};
+    std::lock_guard<std::mutex> guard(lock);
+    if (device < 0 || device >= 64) { err = "build_tree_gpu: device index out of range"; return nullptr; }
+    if (!pools[device]) {
+        cudaMemPoolProps props;
+        std::memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaError_t e = cudaMemPoolCreate(&pools[device], &props);
+        unsigned long long keep = 2ull << 30;
+        if (e == cudaSuccess) e = cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &keep);
+        if (e != cudaSuccess) { err = std::string("build_tree_gpu: memory pool: ") + cudaGetErrorString(e); cudaGetLastError(); pools[device] = nullptr; }
+    }
+    return pools[device];
+}
+}  // namespace
+
 // Builds the tree of the triangle soup `d_points9` (device, 9 floats per triangle) on the current device and leaves
 // it there (`T`; release with free_device_tree).  Returns an empty string on success.
 std::string build_tree_gpu(const float* d_points9, int64_t n64, DeviceTree& T) {
@@ -225,119 +313,120 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, DeviceTree& T) {
     const int n = (int)n64;
     const int N = 2 * n - 1;
     const auto t_begin = clock::now();
-    auto t_sorted = t_begin;
+    const std::vector<LevelShape> levels = tree_shape(n);
+    if (levels.empty() || levels.back().begin + levels.back().count != N) return "build_tree_gpu: level shape does not add up";
 
     float *key = nullptr, *bounds = nullptr, *s1 = nullptr, *s2 = nullptr;
     unsigned *ukey_in = nullptr, *ukey_out = nullptr;
-    int *ids_in = nullptr, *order = nullptr, *order_tmp = nullptr, *rank = nullptr, *node_of_pos = nullptr, *flag = nullptr, *scan = nullptr;
-    int *lo = nullptr, *hi = nullptr, *parent = nullptr, *left = nullptr, *tri = nullptr, *interior = nullptr, *child_scan = nullptr, *rec = nullptr;
-    unsigned char* cut = nullptr;
+    int *ids_in = nullptr, *order[2] = {nullptr, nullptr}, *node_of_pos[2] = {nullptr, nullptr}, *child_scan = nullptr;
+    int *lo = nullptr, *hi = nullptr, *left = nullptr, *tri = nullptr, *rec = nullptr;
+    Six* scan = nullptr;
+    unsigned char *cut = nullptr, *side = nullptr;
     void* temp = nullptr;
     void *keep_base = nullptr, *work_base = nullptr;
     size_t temp_bytes = 0, need = 0;
-    Lists L{};
-    int level_begin = 0, level_end = 1;
-    int launches = 0;
+    int launches = 0, cur = 0, device = 0, max_count = 1;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    float sort_ms = 0.0f;
+    cudaMemPool_t pool = nullptr;
+    thrust::counting_iterator<int> counting(0);
+    double seconds_before_sort = 0.0;
 
-    // two allocations: the tree itself (kept, DeviceTree::arena) and the work arrays (freed at the end)
+    // two allocations: the tree itself (kept, DeviceTree::arena) and the work arrays (returned to the pool at the end)
     Arena keep, work;
     keep.reserve<float>(6 * (size_t)N); keep.reserve<int>((size_t)N); keep.reserve<int>((size_t)N); keep.reserve<int>((size_t)N);
     keep.reserve<unsigned char>((size_t)N); keep.reserve<float>((size_t)N); keep.reserve<float>((size_t)N);
-    cub::DeviceRadixSort::SortPairs(nullptr, need, ukey_in, ukey_out, ids_in, order, n);
+    for (const LevelShape& lv : levels) max_count = lv.count > max_count ? lv.count : max_count;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, ukey_in, ukey_out, ids_in, ids_in, n);
     temp_bytes = need;
-    cub::DeviceScan::ExclusiveSum(nullptr, need, flag, scan, n);
-    temp_bytes = temp_bytes > need ? temp_bytes : need;
-    work.reserve<float>(6 * (size_t)n); work.reserve<unsigned>((size_t)n); work.reserve<unsigned>((size_t)n); work.reserve<int>((size_t)n);
-    work.reserve<int>(6 * (size_t)n); work.reserve<int>((size_t)n); work.reserve<int>(6 * (size_t)n);
-    for (int k = 0; k < 5; k++) work.reserve<int>((size_t)n);  // node_of_pos, flag, scan, interior, child_scan
-    for (int k = 0; k < 3; k++) work.reserve<int>((size_t)N);  // lo, hi, parent
-    work.reserve<char>(temp_bytes);
-    RTB_BUILD_CUDA(cudaMalloc(&keep_base, keep.size));
     {
-        // The work arrays come from the device's stream-ordered pool, which is told to keep what it is given back:
-        // mapping and unmapping gigabytes costs more than a ten-million-triangle build (measured: up to 0.5 s).
-        int device = 0;
-        cudaMemPool_t pool = nullptr;
-        RTB_BUILD_CUDA(cudaGetDevice(&device));
-        RTB_BUILD_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-        unsigned long long keep_all = ~0ull;
-        RTB_BUILD_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
-        RTB_BUILD_CUDA(cudaMallocAsync(&work_base, work.size, (cudaStream_t)0));
+        GoesLeft src{};
+        thrust::transform_iterator<GoesLeft, thrust::counting_iterator<int>, Six> in(counting, src);
+        cub::DeviceScan::ExclusiveScan(nullptr, need, in, scan, SixSum(), Six{{0, 0, 0, 0, 0, 0}}, n + 1);
+        temp_bytes = temp_bytes > need ? temp_bytes : need;
+        IsInterior isrc{};
+        thrust::transform_iterator<IsInterior, thrust::counting_iterator<int>, int> iin(counting, isrc);
+        cub::DeviceScan::ExclusiveSum(nullptr, need, iin, child_scan, max_count);
+        temp_bytes = temp_bytes > need ? temp_bytes : need;
     }
+    work.reserve<float>(6 * (size_t)n); work.reserve<unsigned>((size_t)n); work.reserve<unsigned>((size_t)n); work.reserve<int>((size_t)n);
+    work.reserve<int>(6 * (size_t)n); work.reserve<int>(6 * (size_t)n); work.reserve<unsigned char>((size_t)n);  // order x2, side
+    work.reserve<int>((size_t)n); work.reserve<int>((size_t)n); work.reserve<int>((size_t)max_count);       // node_of_pos x2, child_scan
+    work.reserve<int>((size_t)N); work.reserve<int>((size_t)N);                                             // lo, hi
+    work.reserve<Six>((size_t)n + 1);
+    work.reserve<char>(temp_bytes);
+    RTB_BUILD_CUDA(cudaGetDevice(&device));
+    pool = build_pool(device, err);
+    if (!pool) goto done;
+    RTB_BUILD_CUDA(cudaMalloc(&keep_base, keep.size));
+    RTB_BUILD_CUDA(cudaMallocFromPoolAsync(&work_base, work.size, pool, (cudaStream_t)0));
+    RTB_BUILD_CUDA(cudaEventCreate(&ev[0]));
+    RTB_BUILD_CUDA(cudaEventCreate(&ev[1]));
     keep.base = (char*)keep_base; work.base = (char*)work_base;
     bounds = keep.take<float>(6 * (size_t)N); left = keep.take<int>((size_t)N); tri = keep.take<int>((size_t)N); rec = keep.take<int>((size_t)N);
     cut = keep.take<unsigned char>((size_t)N); s1 = keep.take<float>((size_t)N); s2 = keep.take<float>((size_t)N);
     key = work.take<float>(6 * (size_t)n); ukey_in = work.take<unsigned>((size_t)n); ukey_out = work.take<unsigned>((size_t)n);
-    ids_in = work.take<int>((size_t)n); order = work.take<int>(6 * (size_t)n); order_tmp = work.take<int>((size_t)n);
-    rank = work.take<int>(6 * (size_t)n); node_of_pos = work.take<int>((size_t)n); flag = work.take<int>((size_t)n); scan = work.take<int>((size_t)n);
-    interior = work.take<int>((size_t)n); child_scan = work.take<int>((size_t)n);
-    lo = work.take<int>((size_t)N); hi = work.take<int>((size_t)N); parent = work.take<int>((size_t)N);
+    ids_in = work.take<int>((size_t)n); order[0] = work.take<int>(6 * (size_t)n); order[1] = work.take<int>(6 * (size_t)n);
+    side = work.take<unsigned char>((size_t)n); node_of_pos[0] = work.take<int>((size_t)n); node_of_pos[1] = work.take<int>((size_t)n);
+    child_scan = work.take<int>((size_t)max_count);
+    lo = work.take<int>((size_t)N); hi = work.take<int>((size_t)N);
+    scan = work.take<Six>((size_t)n + 1);
     temp = work.take<char>(temp_bytes);
+    seconds_before_sort = std::chrono::duration<double>(clock::now() - t_begin).count();
 
     // ---- six sorted lists -----------------------------------------------------------------------------
+    RTB_BUILD_CUDA(cudaEventRecord(ev[0], (cudaStream_t)0));
     keys_kernel<<<blocks(n), 256>>>(d_points9, n, key); launches++;
     for (int k = 0; k < 6; k++) {
         sort_input_kernel<<<blocks(n), 256>>>(key + (size_t)k * n, n, ukey_in, ids_in); launches++;
         size_t tb = temp_bytes;
-        RTB_BUILD_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, ukey_in, ukey_out, ids_in, order + (size_t)k * n, n)); launches += 5;  // histogram + four onesweep passes
-        rank_kernel<<<blocks(n), 256>>>(order + (size_t)k * n, n, rank + (size_t)k * n); launches++;
+        RTB_BUILD_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, ukey_in, ukey_out, ids_in, order[0] + (size_t)k * n, n)); launches += 5;  // histogram + four onesweep passes
     }
-    RTB_BUILD_CUDA(cudaDeviceSynchronize());
-    t_sorted = clock::now();
+    RTB_BUILD_CUDA(cudaEventRecord(ev[1], (cudaStream_t)0));
 
-    // ---- level-synchronous partition --------------------------------------------------------------------
-    L.key = key; L.order = order; L.rank = rank; L.n = n;
-    RTB_BUILD_CUDA(cudaMemset(node_of_pos, 0, sizeof(int) * (size_t)n));
-    {
-        const int zero = 0, last = n - 1;
-        RTB_BUILD_CUDA(cudaMemcpy(lo, &zero, sizeof(int), cudaMemcpyHostToDevice));
-        RTB_BUILD_CUDA(cudaMemcpy(hi, &last, sizeof(int), cudaMemcpyHostToDevice));
-        RTB_BUILD_CUDA(cudaMemcpy(parent, &zero, sizeof(int), cudaMemcpyHostToDevice));
-        const int root_rec = n > 1 ? 0 : -1;
-        RTB_BUILD_CUDA(cudaMemcpy(rec, &root_rec, sizeof(int), cudaMemcpyHostToDevice));
-    }
-    root_bounds_kernel<<<1, 1>>>(L, bounds); launches++;
-    while (level_begin < level_end) {
-        const int count = level_end - level_begin;
-        level_nodes_kernel<<<blocks(count), 256>>>(L, level_begin, count, lo, hi, parent, cut, tri, interior); launches++;
-        size_t tb = temp_bytes;
-        RTB_BUILD_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, interior, child_scan, count)); launches += 2;
-        int last_flag = 0, last_scan = 0;
-        RTB_BUILD_CUDA(cudaMemcpy(&last_flag, interior + (count - 1), sizeof(int), cudaMemcpyDeviceToHost));
-        RTB_BUILD_CUDA(cudaMemcpy(&last_scan, child_scan + (count - 1), sizeof(int), cudaMemcpyDeviceToHost));
-        const int num_interior = last_flag + last_scan;
-        if (num_interior > 0) {
-            for (int k = 0; k < 6; k++) {
-                flags_kernel<<<blocks(n), 256>>>(L, k, node_of_pos, lo, hi, cut, flag); launches++;
-                tb = temp_bytes;
-                RTB_BUILD_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, flag, scan, n)); launches += 2;
-                scatter_kernel<<<blocks(n), 256>>>(L, k, node_of_pos, lo, hi, cut, flag, scan, order_tmp); launches++;
-                RTB_BUILD_CUDA(cudaMemcpyAsync(order + (size_t)k * n, order_tmp, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice));
-            }
+    // ---- level-synchronous partition: nothing is read back, the host knows every level's extent ---------------
+    RTB_BUILD_CUDA(cudaMemsetAsync(node_of_pos[0], 0, sizeof(int) * (size_t)n, (cudaStream_t)0));
+    root_init_kernel<<<1, 1>>>(n, lo, hi, cut, rec); launches++;
+    for (const LevelShape& lv : levels) {
+        const Lists L{key, order[cur], n};
+        const int next_begin = lv.begin + lv.count;
+        const bool mixed = lv.interior > 0 && lv.interior < lv.count;  // leaves among the level's nodes: children need a scan
+        if (mixed) {
+            thrust::transform_iterator<IsInterior, thrust::counting_iterator<int>, int> iin(counting, IsInterior{lo, hi, lv.begin});
+            size_t tb = temp_bytes;
+            RTB_BUILD_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, iin, child_scan, lv.count)); launches += 2;
         }
-        children_kernel<<<blocks(count), 256>>>(L, level_begin, count, level_end, child_scan, lo, hi, parent, left, bounds, rec); launches++;
-        reassign_kernel<<<blocks(n), 256>>>(n, node_of_pos, lo, hi, left); launches++;
-        level_begin = level_end;
-        level_end += 2 * num_interior;
+        level_nodes_kernel<<<blocks(lv.count), 256>>>(L, lv.begin, lv.count, next_begin, mixed ? child_scan : nullptr, lo, hi, cut, tri, left, bounds, rec);
+        launches++;
+        if (lv.interior == 0) break;
+        side_kernel<<<blocks(n), 256>>>(n, node_of_pos[cur], lo, hi, cut, order[cur], side); launches++;
+        {
+            thrust::transform_iterator<GoesLeft, thrust::counting_iterator<int>, Six> in(counting, GoesLeft{node_of_pos[cur], lo, hi, cut, order[cur], side, n});
+            size_t tb = temp_bytes;
+            RTB_BUILD_CUDA(cub::DeviceScan::ExclusiveScan(temp, tb, in, scan, SixSum(), Six{{0, 0, 0, 0, 0, 0}}, n + 1)); launches += 2;
+        }
+        scatter_kernel<<<blocks(n), 256>>>(n, node_of_pos[cur], lo, hi, cut, left, scan, order[cur], order[cur ^ 1], node_of_pos[cur ^ 1]);
+        launches++;
+        cur ^= 1;
     }
     split_planes_kernel<<<blocks(N), 256>>>(N, left, cut, bounds, s1, s2); launches++;
-    RTB_BUILD_CUDA(cudaDeviceSynchronize());
-    if (level_end != N) { err = "build_tree_gpu: node count mismatch"; goto done; }
-
-    // ---- the tree stays on the device ------------------------------------------------------------------
-    RTB_BUILD_CUDA(cudaMemcpy(T.root_bounds, bounds, sizeof(float) * 6, cudaMemcpyDeviceToHost));
+    RTB_BUILD_CUDA(cudaGetLastError());
+    // ---- the tree stays on the device; the root's box and triangle are all the host needs ----------------------------
+    RTB_BUILD_CUDA(cudaMemcpy(T.root_bounds, bounds, sizeof(float) * 6, cudaMemcpyDeviceToHost));  // (synchronises with everything above)
     RTB_BUILD_CUDA(cudaMemcpy(&T.root_tri, tri, sizeof(int), cudaMemcpyDeviceToHost));
+    RTB_BUILD_CUDA(cudaEventElapsedTime(&sort_ms, ev[0], ev[1]));
     T.num_tri = n; T.num_nodes = N;
     T.bounds = bounds; T.left = left; T.tri = tri; T.cut = cut; T.s1 = s1; T.s2 = s2; T.rec = rec;
     T.arena = keep_base;
     keep_base = nullptr;
-    T.seconds_sort = std::chrono::duration<double>(t_sorted - t_begin).count();
-    T.seconds_partition = std::chrono::duration<double>(clock::now() - t_sorted).count();
+    T.seconds_sort = seconds_before_sort + (double)sort_ms * 1e-3;  // allocation + keys + six sorts (device time)
+    T.seconds_partition = std::chrono::duration<double>(clock::now() - t_begin).count() - T.seconds_sort;
     T.launches = launches;
 
 done:
     if (work_base) cudaFreeAsync(work_base, (cudaStream_t)0);
     cudaFree(keep_base);
+    for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
     if (!err.empty()) cudaGetLastError();
     return err;
 }

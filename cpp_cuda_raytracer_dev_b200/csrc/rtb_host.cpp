@@ -10,6 +10,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 namespace rtb {
 
@@ -888,6 +891,30 @@ void Transform::matrix(float m[12]) const {
 }
 void Transform::set_matrix(const float m[12]) {
     for (int r = 0; r < 3; r++) { row[r].x = m[4 * r]; row[r].y = m[4 * r + 1]; row[r].z = m[4 * r + 2]; row[r].w = m[4 * r + 3]; }
+}
+
+
+// Fill `count` 32-bit words with `value` on `threads` host threads.  Streaming (non-temporal) stores where the platform
+// has them: the destination is a frame buffer that is written once and read later by somebody else, so there is no
+// point in first reading its cache lines in (which is what ordinary stores do) -- about half the memory traffic.
+void fill_words(uint32_t* dst, size_t count, uint32_t value, int threads) {
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    const size_t chunk = (size_t)1 << 18;  // 1 MB per task
+    const int64_t tasks = (int64_t)((count + chunk - 1) / chunk);
+    parallel_for(threads, tasks, 1, [&](int64_t task) {
+        uint32_t* p = dst + (size_t)task * chunk;
+        uint32_t* const end = dst + std::min(count, ((size_t)task + 1) * chunk);
+#if defined(__x86_64__)
+        while (p < end && ((uintptr_t)p & 15u)) *p++ = value;
+        const __m128i v = _mm_set1_epi32((int)value);
+        for (; p + 16 <= end; p += 16) {
+            _mm_stream_si128((__m128i*)p, v); _mm_stream_si128((__m128i*)(p + 4), v);
+            _mm_stream_si128((__m128i*)(p + 8), v); _mm_stream_si128((__m128i*)(p + 12), v);
+        }
+        _mm_sfence();
+#endif
+        while (p < end) *p++ = value;
+    });
 }
 
 }  // namespace rtb

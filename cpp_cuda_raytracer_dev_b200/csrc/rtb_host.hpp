@@ -65,6 +65,9 @@ std::string build_tree_gpu(const float* d_points9, int64_t num_tri, DeviceTree& 
 std::string download_tree(const DeviceTree& in, HostTree& out);
 void free_device_tree(DeviceTree& t);
 
+// host-side fill of a frame buffer (background pre-fill of the sweep's host frames), threads <= 0: all hardware threads
+void fill_words(uint32_t* dst, size_t count, uint32_t value, int threads);
+
 // ---- camera (Camera.cpp:5-67) ----------------------------------------------------------------
 struct CameraBasis {
     int32_t W = 0, H = 0;

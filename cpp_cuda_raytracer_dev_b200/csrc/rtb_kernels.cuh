@@ -66,6 +66,8 @@ struct RenderParams {
     int seg_frames[3], seg_shift[3];
     long long seg_items[3];
     int t_active, t_leaf;  // refill when <= t_active lanes still traverse; leaf step when >= t_leaf lanes wait at a leaf
+    int steal_mask;        // single-frame launches: a draining warp looks for lanes to share rays with every steal_mask + 1 iterations
+    int prefetch;          // single-frame launches: 1 = ask for both children's records as soon as a record arrives
     long long total_items; // work units: num_frames * my_tiles * (1024 >> unit_shift)
     long long frame_stride;  // output elements per frame: W*H (row-major) or my_tile_slots*1024 (tile-major)
     int tile_major;          // 1: compact tile-major output (the multi-GPU exchange format), 0: final row-major position
@@ -79,7 +81,11 @@ struct RenderParams {
     uint32_t* push_bgra[kMaxPushOwners];
     int32_t* push_ids[kMaxPushOwners];
     int push_owners;
-    int push_skip_background;  // the owner of push_* pre-filled the frames with background / -1: background-only units are not sent
+    int push_skip_background;  // 1: the owner of push_* pre-filled the frames with background / -1: background-only units are not
+                               // sent.  2: the owner's frame holds an earlier frame of this camera whose content lies inside
+                               // push_prev_rect and is background outside it: background-only units are sent only where they
+                               // overlap that rectangle (single-frame path into the camera's host frame, rtb_object_render)
+    int push_prev_rect[4];     // x0, y0, x1, y1 (inclusive)
     unsigned long long* work_counter;  // never reset: a launch hands out units work_base, work_base + 1, ... and every warp
     unsigned long long work_base;      // overshoots exactly once, so the host knows the counter's value after the launch
     unsigned long long* counters;  // [0] rays [1] interior nodes entered [2] nodes popped (reference sense) [3] triangle tests [4] hits
@@ -283,7 +289,9 @@ __global__ void l2_read_kernel(const uint4* __restrict__ buf, long long n16, int
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
 // Moller-Trumbore, Trixel.cu:98-145.  Returns true and updates best/id on acceptance.
-__device__ __forceinline__ bool moller_trumbore(const Ray& r, const float4* __restrict__ tris, int tri, float& best, int& id) {
+// `tie` (optional): raised when the test yields exactly the current best distance for a triangle other than the current
+// best one -- the reference keeps whichever it visited first, which only matters to callers that split a walk (STEAL).
+__device__ __forceinline__ bool moller_trumbore(const Ray& r, const float4* __restrict__ tris, int tri, float& best, int& id, bool* tie = nullptr) {
     const float4 a = ldg4(tris + 3ll * tri), b = ldg4(tris + 3ll * tri + 1), c = ldg4(tris + 3ll * tri + 2);
     // p = d x e2
     const float px = __fsub_rn(__fmul_rn(r.dy, b.z), __fmul_rn(r.dz, b.y));
@@ -305,6 +313,7 @@ __device__ __forceinline__ bool moller_trumbore(const Ray& r, const float4* __re
     // (w < d) && !(u < EPS || v < EPS || (u+v) > 1+EPS || w < EPS); 1+1e-16 == 1.0 in double
     const bool reject = (u < RTB_EPS_UP) || (v < RTB_EPS_UP) || (__fadd_rn(u, v) > 1.0f) || (w < RTB_EPS_UP);
     if ((w < best) && !reject) { best = w; id = tri; return true; }
+    if (tie && (w == best) && !reject && id >= 0 && id != tri) *tie = true;
     return false;
 }
 

@@ -21,6 +21,9 @@
 namespace rtb {
 
 constexpr int kStateEmpty = 0, kStateTraverse = 1, kStateDone = 2;
+// single-frame launches only (STEAL, see render_stream_kernel): a lane that finished a subtree it took over from another
+// lane and has not reported yet / a lane whose own walk is over while helpers still hold parts of its ray's stack
+constexpr int kStateHelperDone = 3, kStateWait = 4;
 
 __device__ __forceinline__ uint32_t compact_even_bits(uint32_t x) {
     x &= 0x55555555u;
@@ -171,14 +174,40 @@ __global__ void selftest_exact_kernel(uint64_t seed, long long count, unsigned l
 #endif
 // INLINE: single-frame launch whose frame record is P.frame0 (kernel parameter space) -- the per-frame path of the
 // reference's loop (Object::render, WinMain.cpp:212) then needs no upload before the launch.
+//
+// INLINE launches also share long rays between the lanes of a warp (STEAL).  A single frame has fewer rays than the GPU
+// has lanes, so it lasts as long as its longest ray: 300-400 dependent steps along the silhouette against ~40 for a ray
+// that hits the object squarely (measured, rtb_camera_counters_ex[7]).  Once a warp has no pixels left to fetch, its idle
+// lanes take over the BOTTOM entry of a busy lane's traversal stack -- the subtree that lane would have visited last --
+// together with a copy of the ray, walk it with the donor's current best distance as their bound, and report what they
+// found to the lane that owns the pixel.  The result is the reference's: the closest hit wins; the reference breaks exact
+// ties between different triangles by visit order (Trixel.cu:127: strict `<`), which a split walk does not know, so a
+// pixel that sees such a tie while its walk may be split is traced again by its owner alone, ties ignored (3_walls:
+// every hit is a three-way tie; elsewhere it practically never happens).  Ties are only looked for once the warp has
+// run out of pixels, because nothing is shared before that.
+#ifndef RTB_STEAL
+#define RTB_STEAL 1
+#endif
+#ifndef RTB_MIN_BLOCKS_INLINE
+#define RTB_MIN_BLOCKS_INLINE 6  // a single frame never fills the GPU: registers matter more than resident warps (80 instead of 64)
+#endif
 template <bool CULL, bool COUNT, bool PUSH, bool INLINE = false>
-__global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RTB_MIN_BLOCKS) render_stream_kernel(const RenderParams P) {
+__global__ void __launch_bounds__(kBlockThreads, INLINE ? RTB_MIN_BLOCKS_INLINE : PUSH ? RTB_MIN_BLOCKS_PUSH : RTB_MIN_BLOCKS)
+render_stream_kernel(const RenderParams P) {
+    constexpr bool STEAL = INLINE && (RTB_STEAL != 0);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanemask_lt = (1u << lane) - 1u;
+    __shared__ int s_helpers[STEAL ? kBlockThreads / 32 : 1][STEAL ? 32 : 1];  // per lane: helpers still out with parts of its ray
+    int sbase = 0;            // STEAL: index of the bottom entry of this lane's stack (entries below it were given away)
+    int owner = (int)lane;    // STEAL: the lane whose pixel this lane is working for
+    bool tie = false, solo = false;  // STEAL: owner saw an exact tie between lanes / traces its pixel again alone
+    int spin = 0, rounds = 0;
+    volatile int* const helpers = s_helpers[STEAL ? threadIdx.x >> 5 : 0];
+    if (STEAL) { helpers[lane] = 0; __syncwarp(); }
 #ifdef RTB_WARP_LOG  // development builds only (tools/warp_log.py): what every warp did and when, in nanoseconds
     unsigned long long wl_t0, wl_first_work = 0, wl_exhausted = 0;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(wl_t0));
-    unsigned wl_units = 0, wl_bg_units = 0, wl_iters = 0, wl_rays = 0;
+    unsigned wl_units = 0, wl_bg_units = 0, wl_iters = 0, wl_rays = 0, wl_steals = 0;
 #endif
     __shared__ int s_owed[PUSH ? kBlockThreads / 32 : 1][PUSH ? kPushSlots : 1];   // pixels of an open unit not yet written
     __shared__ int4 s_unit[PUSH ? kBlockThreads / 32 : 1][PUSH ? kPushSlots : 1];  // frame, tile slot, x and y offset inside the tile
@@ -234,11 +263,14 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
 #endif
             // ---- lanes that finished a node or leaf take the stack top ------------------------------
             if (want_pop) {
-                if (sp == 0) { state = kStateDone; want_pop = false; }
-                else {
+                if (sp == (STEAL ? sbase : 0)) {
+                    want_pop = false;
+                    if (!STEAL) state = kStateDone;
+                    else state = owner != (int)lane ? kStateHelperDone : (helpers[lane] != 0 ? kStateWait : kStateDone);
+                } else {
                     if (!culled(top_tmin)) { cur = top_ref; cur_tmin = top_tmin; cur_tmax = top_tmax; want_pop = false; }
                     sp--;
-                    if (sp > 0) { top_ref = stk_ref[sp - 1]; top_tmin = stk_tmin[sp - 1]; top_tmax = stk_tmax[sp - 1]; }
+                    if (sp > (STEAL ? sbase : 0)) { top_ref = stk_ref[sp - 1]; top_tmin = stk_tmin[sp - 1]; top_tmax = stk_tmax[sp - 1]; }
                 }
             }
             const bool ready = (state == kStateTraverse) & !want_pop;
@@ -249,7 +281,7 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                 // ---- leaf step: always intersected when popped (Trixel.cu:98) -----------------------
                 if (at_leaf) {
                     if (COUNT) { c_tris++; ray_steps++; }
-                    if (moller_trumbore(r, P.tris, (int)((unsigned)cur & kRefIndexMask), best, id)) set_cull_base();
+                    if (moller_trumbore(r, P.tris, (int)((unsigned)cur & kRefIndexMask), best, id, (STEAL && exhausted && !solo) ? &tie : nullptr)) set_cull_base();
                     want_pop = true;
                 }
             } else if (ready & !at_leaf) {
@@ -259,6 +291,16 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                 asm("mad.wide.u32 %0, %1, 64, %2;" : "=l"(rec) : "r"((unsigned)cur & kRefIndexMask), "l"(P.nodes));
                 const float4 q0 = ldg4(rec), q1 = ldg4(rec + 1), q2 = ldg4(rec + 2), q3 = ldg4(rec + 3);
                 const int lref = __float_as_int(q3.x), rref = __float_as_int(q3.y);
+                if (INLINE && P.prefetch) {
+                    // A single frame is bound by the LATENCY of its longest rays, not by throughput: a step is a record fetch
+                    // (L2 or DRAM) followed by a dependent chain of ~150 instructions that decides which record comes next.
+                    // Asking for both candidates now overlaps the next fetch with that chain.  (In the multi-frame kernel,
+                    // which is bound by issue slots, the same requests cost more than they return: DESIGN.md section 4.)
+                    const char* lp = reinterpret_cast<const char*>(lref < 0 ? (const void*)(P.tris + 3ll * ((unsigned)lref & kRefIndexMask)) : (const void*)(P.nodes + 4ll * ((unsigned)lref & kRefIndexMask)));
+                    const char* rp = reinterpret_cast<const char*>(rref < 0 ? (const void*)(P.tris + 3ll * ((unsigned)rref & kRefIndexMask)) : (const void*)(P.nodes + 4ll * ((unsigned)rref & kRefIndexMask)));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(lp));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(rp));
+                }
                 const float S1 = q3.z, S2 = q3.w;  // left child's max / right child's min on the split axis (Trixel.h:353-376)
                 const int axis = (lref >> kRefAxisShift) & 3;
                 // Split-axis components.  Trixel.cu:88-90 forms them as three-term sums with 0/1 flags,
@@ -292,7 +334,7 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                         const bool go_first = !culled(f_eff);
                         const bool go_second = visit_second & !culled(s_eff);
                         if (go_second) {
-                            if (sp > 0) { stk_ref[sp - 1] = top_ref; stk_tmin[sp - 1] = top_tmin; stk_tmax[sp - 1] = top_tmax; }
+                            if (sp > (STEAL ? sbase : 0)) { stk_ref[sp - 1] = top_ref; stk_tmin[sp - 1] = top_tmin; stk_tmax[sp - 1] = top_tmax; }
                             top_ref = left_first ? rref : lref; top_tmin = s_eff; top_tmax = left_first ? rtmax : ltmax;
                             sp++;
                             if (COUNT) ray_depth = max(ray_depth, sp);
@@ -309,7 +351,7 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                     const bool go_first = ((first < 0) | f_in) & !culled(f_tmin);
                     const bool go_second = visit_second & ((second < 0) | s_in) & !culled(s_tmin);
                     if (go_second) {
-                        if (sp > 0) { stk_ref[sp - 1] = top_ref; stk_tmin[sp - 1] = top_tmin; stk_tmax[sp - 1] = top_tmax; }
+                        if (sp > (STEAL ? sbase : 0)) { stk_ref[sp - 1] = top_ref; stk_tmin[sp - 1] = top_tmin; stk_tmax[sp - 1] = top_tmax; }
                         top_ref = second; top_tmin = s_tmin; top_tmax = s_tmax;
                         sp++;
                         if (COUNT) ray_depth = max(ray_depth, sp);
@@ -325,9 +367,21 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
                 }
             }
             m_trav = __ballot_sync(0xffffffffu, state == kStateTraverse);
+            if (STEAL && exhausted && m_trav != 0xffffffffu && (++spin & P.steal_mask) == 0) break;  // idle lanes: see below
         }
 
         // ================= retire: Phong + store for finished rays ===================================
+        if (STEAL && state == kStateDone && tie && !solo) {
+            // two lanes found different triangles at exactly the same distance: which one the reference keeps depends
+            // on its visit order, so the owner walks the whole ray again, alone
+            tie = false; solo = true;
+            best = P.draw_distance; id = -1; sp = 0; sbase = 0; want_pop = false;
+            set_cull_base();
+            cur = P.root_ref;
+            if (P.root_ref < 0) { cur_tmin = 0.0f; cur_tmax = 0.0f; }
+            else slab(r, P.root_box[0], P.root_box[1], P.root_box[2], P.root_box[3], P.root_box[4], P.root_box[5], cur_tmin, cur_tmax);
+            state = kStateTraverse;  // (it entered the root box the first time, so it does again)
+        }
         if (state == kStateDone) {
             uint32_t color = P.background;
             if (id >= 0) {
@@ -350,6 +404,7 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
             if (P.out_ids) RTB_PIXEL_STORE(P.out_ids + o, id);
             if (PUSH) atomicSub(&s_owed[wib][my_pslot], 1);
             state = kStateEmpty;
+            if (STEAL) { solo = false; tie = false; }
         }
         const unsigned m_empty = ~m_trav;
 
@@ -409,7 +464,11 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
 #ifdef RTB_WARP_LOG
                         wl_bg_units++;
 #endif
-                        if (PUSH && P.push_skip_background) continue;  // the frame's owner has pre-filled it: nothing to send
+                        if (PUSH && P.push_skip_background == 1) continue;  // the frame's owner has pre-filled it: nothing to send
+                        if (PUSH && P.push_skip_background == 2 &&
+                            (bx > P.push_prev_rect[2] || bx + (1 << wshift) - 1 < P.push_prev_rect[0] || by > P.push_prev_rect[3] ||
+                             by + (unit_pixels >> wshift) - 1 < P.push_prev_rect[1]))
+                            continue;  // background before, background now: the owner's frame already says so
                         const int owner = PUSH ? u_frame % P.push_owners : 0;
                         uint32_t* __restrict__ dc = PUSH ? P.push_bgra[owner] : P.out_bgra;
                         int32_t* __restrict__ di = PUSH ? P.push_ids[owner] : P.out_ids;
@@ -565,19 +624,88 @@ __global__ void __launch_bounds__(kBlockThreads, PUSH ? RTB_MIN_BLOCKS_PUSH : RT
             }
             blocked = blocked && open_mask == (1u << kPushSlots) - 1u;
         }
-        if (exhausted && m_trav == 0u) break;  // nothing in flight, nothing left to fetch
+        if (STEAL && exhausted) {
+            // ---- helpers report: the pixel's owner keeps the closer hit ------------------------------------------
+            unsigned m_rep = __ballot_sync(0xffffffffu, state == kStateHelperDone);
+            while (m_rep) {
+                const int src = __ffs(m_rep) - 1;
+                m_rep &= m_rep - 1u;
+                const int o = __shfl_sync(0xffffffffu, owner, src);
+                const float w = __shfl_sync(0xffffffffu, best, src);
+                const int t = __shfl_sync(0xffffffffu, id, src);
+                const bool t_tie = __shfl_sync(0xffffffffu, (int)tie, src) != 0;
+                if ((int)lane == o) {
+                    if (t >= 0) {
+                        if (w < best) { best = w; id = t; if (CULL) set_cull_base(); }
+                        else if (w == best && id >= 0 && id != t) tie = true;
+                    }
+                    tie |= t_tie;
+                    const int left = helpers[lane] - 1;
+                    helpers[lane] = left;
+                    if (state == kStateWait && left == 0) state = kStateDone;  // retired on the next round
+                }
+            }
+            if (state == kStateHelperDone) { state = kStateEmpty; owner = (int)lane; tie = false; }
+            // ---- idle lanes take over the bottom stack entries of busy lanes -------------------------------------
+            const unsigned m_idle = __ballot_sync(0xffffffffu, state == kStateEmpty);
+            const unsigned m_donor = __ballot_sync(0xffffffffu, state == kStateTraverse && sp > sbase && !solo);
+            if (m_idle != 0u && m_donor != 0u) {
+                const int pairs = min(__popc(m_idle), __popc(m_donor));
+                const int my_rank = state == kStateEmpty ? __popc(m_idle & lanemask_lt) : __popc(m_donor & lanemask_lt);
+                const bool helper = state == kStateEmpty && my_rank < pairs;
+                const bool donor = state == kStateTraverse && sp > sbase && !solo && my_rank < pairs;
+                // the entry a donor gives away: the bottom of its stack (in memory), or its only entry (the register top)
+                int e_ref = 0; float e_tmin = 0.0f, e_tmax = 0.0f;
+                if (donor) {
+                    while (CULL && sp - sbase >= 2 && culled(stk_tmin[sbase])) sbase++;  // dead entries: a pop would drop them too
+                    if (sp - sbase >= 2) { e_ref = stk_ref[sbase]; e_tmin = stk_tmin[sbase]; e_tmax = stk_tmax[sbase]; sbase++; }
+                    else { e_ref = top_ref; e_tmin = top_tmin; e_tmax = top_tmax; sp--; }
+                }
+                const int src = helper ? (int)__fns(m_donor, 0, my_rank + 1) : (int)lane;
+                const int n_ref = __shfl_sync(0xffffffffu, e_ref, src);
+                const float n_tmin = __shfl_sync(0xffffffffu, e_tmin, src), n_tmax = __shfl_sync(0xffffffffu, e_tmax, src);
+                const int n_owner = __shfl_sync(0xffffffffu, owner, src);
+                const float n_best = __shfl_sync(0xffffffffu, best, src), n_slack = __shfl_sync(0xffffffffu, slack_abs, src);
+                const int n_id = __shfl_sync(0xffffffffu, id, src);  // (kept to recognise ties with the donor's hit, see moller_trumbore)
+                Ray q;
+                q.dx = __shfl_sync(0xffffffffu, r.dx, src); q.dy = __shfl_sync(0xffffffffu, r.dy, src); q.dz = __shfl_sync(0xffffffffu, r.dz, src);
+                q.ix = __shfl_sync(0xffffffffu, r.ix, src); q.iy = __shfl_sync(0xffffffffu, r.iy, src); q.iz = __shfl_sync(0xffffffffu, r.iz, src);
+                q.fx = __shfl_sync(0xffffffffu, r.fx, src); q.fy = __shfl_sync(0xffffffffu, r.fy, src); q.fz = __shfl_sync(0xffffffffu, r.fz, src);
+                q.ox = __shfl_sync(0xffffffffu, r.ox, src); q.oy = __shfl_sync(0xffffffffu, r.oy, src); q.oz = __shfl_sync(0xffffffffu, r.oz, src);
+                if (helper) {
+                    r = q;
+                    best = n_best; slack_abs = n_slack; id = n_id; tie = false;
+                    set_cull_base();
+                    owner = n_owner;
+                    sp = 0; sbase = 0;
+                    cur = n_ref; cur_tmin = n_tmin; cur_tmax = n_tmax;
+                    want_pop = culled(n_tmin);  // the donor's best may have improved since the entry was pushed
+                    state = kStateTraverse;
+                    atomicAdd(&s_helpers[wib][n_owner], 1);
+#ifdef RTB_WARP_LOG
+                    wl_steals++;
+#endif
+                }
+                __syncwarp();
+            }
+            if (__ballot_sync(0xffffffffu, state != kStateEmpty) == 0u) break;  // nothing in flight, nothing left to fetch
+            // (a bound on the rounds of a draining warp -- orders of magnitude above any real walk -- so that a mistake in the
+            // sharing logic shows up as a wrong frame in the tests instead of a kernel that never ends)
+            if (++rounds > (1 << 22)) break;
+        } else if (exhausted && m_trav == 0u) break;  // nothing in flight, nothing left to fetch
     }
 #ifdef RTB_WARP_LOG
     {
         unsigned long long wl_t1;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(wl_t1));
         wl_rays = __reduce_add_sync(0xffffffffu, wl_rays);
+        wl_steals = __reduce_add_sync(0xffffffffu, wl_steals);
         if (lane == 0 && P.counters) {  // log lives behind the counters: 8 words per warp from counters[16]
             unsigned long long* L = P.counters + 16 + 8ull * ((unsigned long long)blockIdx.x * (kBlockThreads / 32) + wib);
             unsigned smid;
             asm("mov.u32 %0, %smid;" : "=r"(smid));
             L[0] = wl_t0; L[1] = wl_t1; L[2] = wl_first_work; L[3] = wl_exhausted;
-            L[4] = ((unsigned long long)wl_units << 32) | wl_bg_units; L[5] = ((unsigned long long)wl_iters << 32) | wl_rays; L[6] = smid; L[7] = 0;
+            L[4] = ((unsigned long long)wl_units << 32) | wl_bg_units; L[5] = ((unsigned long long)wl_iters << 32) | wl_rays; L[6] = smid; L[7] = ((unsigned long long)(unsigned)rounds << 32) | wl_steals;
         }
     }
 #endif

@@ -308,6 +308,10 @@ int rtb_selftest_exact(uint64_t seed, int64_t count, uint64_t out4[4]);
  * `bytes` (choose it well below the L2 size, e.g. 32 MB) by 8 blocks of 256 threads per SM; result in GB/s. */
 int rtb_measure_l2_read_bandwidth(size_t bytes, int iters, double* gb_per_s);
 
+/* What the host can take when IT writes a frame buffer: `bytes` of pinned memory filled by `threads` host threads
+ * (<= 0: all) with streaming stores, best of three passes.  The sweep's background pre-fill is bound by this, the frames
+ * that cross PCIe by the copy bandwidth (bench.py reports both). */
+int rtb_measure_host_fill_bandwidth(size_t bytes, int threads, double* gb_per_s);
 /* number of kernels this library has launched in this process (render, pack and fill kernels) */
 uint64_t rtb_launch_count(void);
 

@@ -1061,3 +1061,45 @@ def test_set_matrix_suspends_the_recurrence(gpu, orc):
     p.ref.transform(gpu.ROTATE_TRI_PY, *gpu.R_KEY_QUAT)
     p.check()
     p.close()
+
+
+def test_sweep_into_pinned_buffers_without_the_copy_engine(gpu, orc):
+    """rtb_render_sweep into pinned caller buffers: host threads pre-fill the background chunk by chunk, the kernel stores
+    every work unit that holds anything else straight into the buffers.  Same frames as the copy-engine path (knob off),
+    over several chunks, with either output alone, and the last frame against the oracle."""
+    import torch
+    W, H, F = 203, 117, 50   # ragged frame; 1 MB chunks hold 5 frames
+    pts = gpu.geodesic_mesh(14)
+    p = Pair(gpu, orc, pts, W, H)
+    ops = gpu.orbit_ops(F)
+    got = {}
+    try:
+        gpu.set_knob("sweep_chunk_mb", 1)
+        for direct in (1, 0):
+            gpu.set_knob("sweep_direct", direct)
+            p.cam.add_object(p.obj)  # restart the recurrence
+            hc = torch.full((F, W * H), 0x55, dtype=torch.int32).pin_memory(); hi = torch.full((F, W * H), 7, dtype=torch.int32).pin_memory()
+            p.obj.render_sweep(p.cam, ops, out_color=hc.numpy().view(np.uint32), out_ids=hi.numpy())
+            got[direct] = (hi.numpy().copy(), hc.numpy().copy())
+        gpu.set_knob("sweep_direct", 1)
+        assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1])
+        assert (got[1][0] >= 0).any() and (got[1][0] == -1).any()
+        # either output alone
+        p.cam.add_object(p.obj)
+        hi = torch.full((F, W * H), 7, dtype=torch.int32).pin_memory()
+        p.obj.render_sweep(p.cam, ops, want_color=False, out_ids=hi.numpy())
+        assert np.array_equal(hi.numpy(), got[1][0])
+        p.cam.add_object(p.obj)
+        hc = torch.full((F, W * H), 0x55, dtype=torch.int32).pin_memory()
+        p.obj.render_sweep(p.cam, ops, want_ids=False, out_color=hc.numpy().view(np.uint32))
+        assert np.array_equal(hc.numpy(), got[1][1])
+    finally:
+        gpu.set_knob("sweep_chunk_mb", 256); gpu.set_knob("sweep_direct", 1)
+    for k in range(F):  # the oracle follows the same ops
+        op = ops[k, 0]
+        if int(op[0]):
+            p.ref.transform(int(op[0]), *[float(v) for v in op[1:5]])
+    oids, obgra = p.ref.render()
+    assert np.array_equal(got[1][0][F - 1].astype(np.int64), oids)
+    assert channel_diff(got[1][1][F - 1].view(np.uint32), obgra).max(initial=0) <= COLOUR_TOL
+    p.close()

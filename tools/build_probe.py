@@ -5,7 +5,7 @@ import cpp_cuda_raytracer_dev_b200 as rtb
 rtb.set_device(0)
 for nu in [int(a) for a in (sys.argv[1:] or ["59", "209", "707"])]:
     pts = rtb.geodesic_mesh(nu)
-    for where, name in ((2, "gpu"), (2, "gpu"), (1, "host")):
+    for where, name in ((2, "gpu"), (2, "gpu"), (2, "gpu")) + (((1, "host"),) if nu <= 300 else ()):
         m = rtb.Trixel(pts)
         t = time.time(); m.create_kd(where=where); dt = time.time() - t
         cam = rtb.Camera(960, 540, **rtb.default_camera_args(960, 540)); obj = rtb.Object(m)

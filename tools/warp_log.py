@@ -22,6 +22,7 @@ for k in range(int(sys.argv[1]) if len(sys.argv) > 1 else 1):
     units, bg = (log[:, 4] >> np.uint64(32)).astype(np.int64), (log[:, 4] & np.uint64(0xffffffff)).astype(np.int64)
     iters, rays = (log[:, 5] >> np.uint64(32)).astype(np.int64), (log[:, 5] & np.uint64(0xffffffff)).astype(np.int64)
     sm = log[:, 6].astype(np.int64)
+    steals, rounds = (log[:, 7] & np.uint64(0xffffffff)).astype(np.int64), (log[:, 7] >> np.uint64(32)).astype(np.int64)
     dur = (t1 - t0) / 1e3
     print("warps that ran: %d; kernel span %.1f us (first start -> last end); starts spread over %.1f us" % (live.sum(), (t1[live].max() - base) / 1e3, (t0[live].max() - base) / 1e3))
     print("queue exhausted (first warp to see it) at %.1f us, last at %.1f us" % ((tx[tx > 0].min() - base) / 1e3, (tx[tx > 0].max() - base) / 1e3))
@@ -31,9 +32,12 @@ for k in range(int(sys.argv[1]) if len(sys.argv) > 1 else 1):
     print("duration of warps with rays: p50 %.1f  p90 %.1f  p99 %.1f  max %.1f us;  ns per iteration of the slowest 1%%: %.0f" % (
         np.percentile(dur[busy], 50), np.percentile(dur[busy], 90), np.percentile(dur[busy], 99), dur[busy].max(),
         1e3 * (dur[busy] / np.maximum(iters[busy], 1))[dur[busy] >= np.percentile(dur[busy], 99)].mean()))
+    print("subtrees handed over between lanes: %d in %d warps (max %d in one warp); drain rounds: max %d" % (steals.sum(), (steals > 0).sum(), steals.max(), rounds.max()))
+    ends = np.sort((t1[busy] - base) / 1e3)
+    print("end times of warps with rays: p10 %.1f p50 %.1f p90 %.1f p99 %.1f max %.1f us" % tuple(np.percentile(ends, q) for q in (10, 50, 90, 99, 100)))
     order = np.argsort(-dur)[:8]
     for w in order:
-        print("  warp %5d sm %3d: start %.1f first-work %.1f end %.1f us  units %d (bg %d) rays %d iters %d" % (
-            w, sm[w], (t0[w] - base) / 1e3, (tw[w] - base) / 1e3 if tw[w] else -1, (t1[w] - base) / 1e3, units[w], bg[w], rays[w], iters[w]))
+        print("  warp %5d sm %3d: start %.1f first-work %.1f exhausted %.1f end %.1f us  units %d (bg %d) rays %d iters %d steals %d rounds %d" % (
+            w, sm[w], (t0[w] - base) / 1e3, (tw[w] - base) / 1e3 if tw[w] else -1, (tx[w] - base) / 1e3 if tx[w] else -1, (t1[w] - base) / 1e3, units[w], bg[w], rays[w], iters[w], steals[w], rounds[w]))
     per_sm = np.bincount(sm[busy], weights=rays[busy].astype(np.float64), minlength=148)
     print("rays per SM: mean %.0f min %.0f max %.0f; slowest warps' SMs hold %s rays" % (per_sm.mean(), per_sm.min(), per_sm.max(), [int(per_sm[sm[w]]) for w in order[:4]]))
