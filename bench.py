@@ -541,7 +541,13 @@ def end_to_end(env, sc, K, Wm):
         copy_times.append(time.perf_counter() - t)
     copy_s = env.max_over_ranks(min(copy_times[1:]))
     return {"value": rays_total / total / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(F * 5 * 4), "d2h_bytes_per_step": int(F * P * 8),
-            "fps": K * env.world * F / total, "api": "rtb_render_sweep (host ops in, pinned host colour+id frames out)", "matches_device_run": same,
+            "fps": K * env.world * F / total,
+            "api": "rtb_render_sweep (host ops in, pinned host colour+id frames out): host threads pre-fill each chunk of frames with the background while "
+                   "the kernel traces the chunk before and stores every work unit that holds anything else straight into the caller's buffers over PCIe; "
+                   "RTB_SWEEP_DIRECT=0 selects the copy-engine path (device frames + cudaMemcpyAsync), which is what pageable buffers get",
+            "matches_device_run": same, "host_fill_gbs": rtb.measure_host_fill_bandwidth(256 << 20, 0) if env.rank == 0 else None,
+            "host_fill_note": "what this host's cores write into pinned memory with streaming stores (all usable cores, nothing else running): the ceiling of the "
+                              "pre-fill; d2h_bytes_per_step counts every byte of the frames delivered to host memory, whoever wrote it",
             "d2h_gbs": K * env.world * F * P * 8 / total / 1e9,
             "d2h_copy_only_gbs": env.world * F * P * 8 / copy_s / 1e9,
             "d2h_copy_only_note": "plain cudaMemcpyAsync of one step's frames (colour + ids) from device to the same pinned buffers, all ranks "
@@ -551,19 +557,28 @@ def end_to_end(env, sc, K, Wm):
 def frame_loop(env, sc):
     """The reference's own frame loop through the drop-in calls, one frame at a time (WinMain.cpp:187-237: Input::set_quat +
     Object::transform, Object::render, Camera::color_pixels(PHONG)); frame and ids in the camera's host buffers after every
-    iteration."""
+    iteration.  Measured twice: as shipped (frames rendered ahead while the steps repeat, which they do in this loop exactly as
+    with the reference's R key held down) and with the knob `lookahead` at 0 (every frame starts when it is asked for)."""
     rtb = env.rtb
     nloop = 300 if sc.P <= (1 << 20) else 30
-    for it in range(nloop + 10):
-        if it == 10:
-            t_loop = time.perf_counter()
-        sc.obj.transform(rtb.R_KEY_QUAT, rtb.ROTATE_TRI_PY)
-        sc.obj.render(sc.cam)
-        sc.cam.color_pixels(rtb.PHONG_COLOR_TAG)
-    t_loop = time.perf_counter() - t_loop
-    return {"fps": nloop / t_loop, "value": nloop * sc.P / t_loop / 1e6, "unit": "Mrays/s", "frames": nloop,
-            "api": "per frame: rtb_object_transform + rtb_object_render + rtb_camera_color_pixels(PHONG) (the reference's WinMain loop: "
-                   "frame + ids in host memory after every iteration, one synchronisation per frame)"}
+    out = {}
+    for name, look in (("fps", None), ("fps_no_lookahead", 0)):
+        if look is not None:
+            rtb.set_knob("lookahead", look)
+        for it in range(nloop + 10):
+            if it == 10:
+                t_loop = time.perf_counter()
+            sc.obj.transform(rtb.R_KEY_QUAT, rtb.ROTATE_TRI_PY)
+            sc.obj.render(sc.cam)
+            sc.cam.color_pixels(rtb.PHONG_COLOR_TAG)
+        out[name] = nloop / (time.perf_counter() - t_loop)
+    rtb.set_knob("lookahead", 2)
+    out.update({"value": out["fps"] * sc.P / 1e6, "unit": "Mrays/s", "frames": nloop,
+                "api": "per frame: rtb_object_transform + rtb_object_render + rtb_camera_color_pixels(PHONG) (the reference's WinMain loop: "
+                       "frame + ids in host memory after every iteration, one synchronisation per frame; the kernel stores the frame straight into "
+                       "a pinned host buffer, shares long rays between the lanes of a warp, and -- `fps` -- up to two predicted frames are in "
+                       "flight behind the current one while the transform steps repeat; `fps_no_lookahead`: knob lookahead = 0)"})
+    return out
 
 
 def scene_extension_leg(env, sc):

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -101,6 +102,31 @@ struct SceneArrays {
     int64_t num_tri = 0;
 };
 
+// Single-frame path (rtb_object_render -> rtb_camera_color_pixels): a frame is rendered into a SLOT -- a pinned host frame the
+// kernel stores into directly, a device staging area for its work units, a work counter, a stream and an event of its own --
+// so that frames can be in flight side by side.  A single 960x540 frame cannot fill a B200: it lasts as long as its longest
+// rays while most of the GPU idles.  When the caller's motion repeats (the same transform steps before
+// every render: the reference's key-held orbit, WinMain.cpp:186-213) the frames after the current one are rendered ahead, on
+// other slots' streams, in the shadow of the current frame's tail; a render call whose matrix equals the predicted one
+// bit for bit finds its frame already on the way.  A wrong guess costs idle-GPU work and is simply never looked at.
+constexpr int kFrameSlots = 4;
+struct FrameSlot {
+    uint32_t* h_bgra = nullptr;      // slot 0 uses the camera's own host frame
+    int32_t* h_ids = nullptr;
+    uint32_t* stage_bgra = nullptr;  // tile-major staging of one frame (device)
+    int32_t* stage_ids = nullptr;
+    unsigned long long* d_work = nullptr;
+    unsigned long long work_base = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    bool ready = false;        // allocated
+    bool in_flight = false;    // a launch into this slot has not been waited for yet
+    bool rect_valid = false;   // the host frame is background / -1 outside rect (the frame last stored there)
+    int rect[4] = {0, 0, -1, -1};
+    float m12[12] = {0};
+    uint32_t flags = 0;
+};
+
 struct rtb_camera {
     int device = 0;
     rtb::CameraBasis basis;
@@ -136,8 +162,12 @@ struct rtb_camera {
     // Single-frame path (rtb_object_render): the kernel stores the frame straight into h_bgra / h_ids (pinned, mapped),
     // and only where it can differ from what they hold -- host_rect is the pixel rectangle outside which the host frame
     // is known to be background / -1 (the root-box rectangle of the frame last stored there this way).
-    bool host_rect_valid = false;
-    int host_rect[4] = {0, 0, -1, -1};
+    FrameSlot slots[kFrameSlots];
+    int cur_slot = 0;                 // the slot whose host frame rtb_camera_host_color / _ids name
+    std::deque<int> ahead;            // slots rendering predicted frames, oldest first
+    rtb_object* ahead_obj = nullptr;  // ... of this object,
+    uint32_t ahead_flags = 0;         // ... with these render flags;
+    rtb::Transform ahead_xf;          // the recurrence's state after the last predicted frame
     bool device_frame_stale = false;  // the last frame went to the host only: d_bgra / d_ids hold an older one
 };
 
@@ -160,6 +190,11 @@ struct rtb_object {
     cudaEvent_t ev_upload = nullptr, ev_launch = nullptr;
     cudaStream_t last_stream = nullptr;
     bool upload_pending = false, launch_pending = false;
+    // the transform steps applied since the last single-frame render and before the one before it: when they repeat, the
+    // next frames are predictable (rtb_camera::ahead)
+    struct Step { uint8_t select; float v[4]; };
+    std::vector<Step> steps_now, steps_frame;
+    bool steps_repeat = false;
 };
 
 namespace {
@@ -186,6 +221,7 @@ struct Knobs {
     int t_active_inline = 30;   // single-frame launches: t_active (a warp that sees the empty queue early shares its long rays early)
     int steal_spin = 8;         // ... and how many iterations a draining warp runs between two looks for lanes to share with (power of two)
     int inline_prefetch = 1;    // ... and whether it asks for both children's records ahead of the decision
+    int lookahead = 2;          // single-frame path: predicted frames kept in flight behind the current one (0 = off)
     int sweep_chunk_mb = 256;   // ... and the size of the chunks (MB of host frames) in which fill and render alternate
     int l2_carve_mb = 0;  // persisting L2 carve-out in MB, 0 = the size of the window
 };
@@ -199,7 +235,7 @@ Knobs& knobs() {
         v.host_direct = env_int("RTB_HOST_DIRECT", v.host_direct); v.sweep_direct = env_int("RTB_SWEEP_DIRECT", v.sweep_direct);
         v.host_fill_threads = env_int("RTB_HOST_FILL_THREADS", v.host_fill_threads); v.sweep_chunk_mb = env_int("RTB_SWEEP_CHUNK_MB", v.sweep_chunk_mb);
         v.t_active_inline = env_int("RTB_T_ACTIVE_INLINE", v.t_active_inline); v.steal_spin = env_int("RTB_STEAL_SPIN", v.steal_spin);
-        v.inline_prefetch = env_int("RTB_INLINE_PREFETCH", v.inline_prefetch); v.l2_carve_mb = env_int("RTB_L2_CARVE_MB", v.l2_carve_mb);
+        v.inline_prefetch = env_int("RTB_INLINE_PREFETCH", v.inline_prefetch); v.lookahead = env_int("RTB_LOOKAHEAD", v.lookahead); v.l2_carve_mb = env_int("RTB_L2_CARVE_MB", v.l2_carve_mb);
         return v;
     }();
     return k;
@@ -358,7 +394,7 @@ bool order_frames(const rtb_object* o, const rtb_camera* c, int num_frames) {
 int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, const float* inline_record, int num_frames, int tile_first,
                   int tile_stride, uint32_t flags, uint32_t* d_bgra, int32_t* d_ids, cudaStream_t stream, int push_owners = 0,
                   uint32_t* const* push_bgra = nullptr, int32_t* const* push_ids = nullptr, const int* d_frame_order = nullptr,
-                  const int* push_prev_rect = nullptr) {
+                  const int* push_prev_rect = nullptr, const int* tile_window = nullptr, FrameSlot* slot = nullptr) {
     using namespace rtb;
     const SceneArrays* sc = o->scene;
     RenderParams P;
@@ -378,7 +414,15 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, const flo
     P.num_frames = num_frames;
     P.tiles_x = (b.W + kTile - 1) / kTile;
     const int tiles_y = (b.H + kTile - 1) / kTile;
-    const int tiles = P.tiles_x * tiles_y;
+    P.win_tx0 = 0; P.win_ty0 = 0; P.win_tw = P.tiles_x;
+    int win_th = tiles_y;
+    if (tile_window) {  // tx0, ty0, tx1, ty1 (inclusive); empty when tx1 < tx0
+        P.win_tx0 = std::max(0, tile_window[0]); P.win_ty0 = std::max(0, tile_window[1]);
+        P.win_tw = std::max(0, std::min(P.tiles_x - 1, tile_window[2]) - P.win_tx0 + 1);
+        win_th = std::max(0, std::min(tiles_y - 1, tile_window[3]) - P.win_ty0 + 1);
+        if (P.win_tw == 0 || win_th == 0) return RTB_OK;  // nothing can change
+    }
+    const int tiles = P.win_tw * win_th;
     if (tile_stride < 1 || tile_first < 0 || tile_first >= tile_stride) return fail(RTB_ERR_ARG, "render: bad tile_first/tile_stride");
     P.tile_first = tile_first; P.tile_stride = tile_stride;
     P.my_tiles = tile_first < tiles ? (tiles - tile_first + tile_stride - 1) / tile_stride : 0;
@@ -394,8 +438,8 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, const flo
     }
     P.tile_major = ((flags & RTB_RENDER_TILE_MAJOR) || push) ? 1 : 0;
     P.frame_stride = P.tile_major ? (long long)((tiles + tile_stride - 1) / tile_stride) * kTile * kTile : (long long)b.W * b.H;
-    P.work_counter = o->d_work;
-    P.work_base = o->work_base;
+    P.work_counter = slot ? slot->d_work : o->d_work;  // a slot's launches share nothing with the object's other launches
+    P.work_base = slot ? slot->work_base : o->work_base;
     P.counters = c->d_counters;
     P.cull_rel = 1e-5f;
     if (P.total_items == 0) return RTB_OK;
@@ -479,8 +523,10 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, const flo
         nattr = 1;
     }
     cfg.attrs = attr; cfg.numAttrs = nattr;
-    int rc = order_after_previous(o, stream);
-    if (rc) return rc;
+    if (!slot) {
+        const int rc = order_after_previous(o, stream);
+        if (rc) return rc;
+    }
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, P);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -488,10 +534,115 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, const flo
     }
     g_launches++;
     // every warp of the grid fetches until its first miss: the counter ends at base + units + warps
-    o->work_base += (unsigned long long)P.total_items + (unsigned long long)grid * (kBlockThreads / 32);
+    const unsigned long long handed_out = (unsigned long long)P.total_items + (unsigned long long)grid * (kBlockThreads / 32);
+    if (slot) {
+        slot->work_base += handed_out;
+        return RTB_OK;
+    }
+    o->work_base += handed_out;
     RTB_CUDA(cudaEventRecord(o->ev_launch, stream));
     o->launch_pending = true;
     o->last_stream = stream;
+    return RTB_OK;
+}
+
+// ---- frame slots of the single-frame path ---------------------------------------------------------------------------
+int ensure_slot(rtb_camera* c, int k) {
+    FrameSlot& s = c->slots[k];
+    if (s.ready) return RTB_OK;
+    const size_t P = (size_t)c->pixels, stage = (size_t)rtb_tile_major_elements(c, 1);
+    if (k == 0) { s.h_bgra = c->h_bgra; s.h_ids = c->h_ids; }
+    else {
+        if (!s.h_bgra) RTB_CUDA(cudaMallocHost(&s.h_bgra, 4 * P));
+        if (!s.h_ids) RTB_CUDA(cudaMallocHost(&s.h_ids, 4 * P));
+    }
+    if (!s.stage_bgra) RTB_CUDA(cudaMalloc(&s.stage_bgra, 4 * stage));
+    if (!s.stage_ids) RTB_CUDA(cudaMalloc(&s.stage_ids, 4 * stage));
+    if (!s.d_work) {
+        RTB_CUDA(cudaMalloc(&s.d_work, sizeof(unsigned long long)));
+        RTB_CUDA(cudaMemset(s.d_work, 0, sizeof(unsigned long long)));
+        s.work_base = 0;
+    }
+    if (!s.stream) RTB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    if (!s.done) RTB_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    s.rect_valid = false;  // nothing is known about a fresh host frame
+    s.ready = true;
+    return RTB_OK;
+}
+int wait_slot(FrameSlot& s) {
+    if (s.in_flight) {
+        RTB_CUDA(cudaEventSynchronize(s.done));
+        s.in_flight = false;
+    }
+    return RTB_OK;
+}
+// every frame in flight on the slots has landed and no prediction is outstanding
+int drain_slots(rtb_camera* c) {
+    c->ahead.clear();
+    c->ahead_obj = nullptr;
+    for (FrameSlot& s : c->slots) { const int rc = wait_slot(s); if (rc) return rc; }
+    return RTB_OK;
+}
+void free_slots(rtb_camera* c) {
+    for (int k = 0; k < kFrameSlots; k++) {
+        FrameSlot& s = c->slots[k];
+        if (s.in_flight && s.done) cudaEventSynchronize(s.done);
+        if (k != 0) { if (s.h_bgra) cudaFreeHost(s.h_bgra); if (s.h_ids) cudaFreeHost(s.h_ids); }
+        if (s.stage_bgra) cudaFree(s.stage_bgra);
+        if (s.stage_ids) cudaFree(s.stage_ids);
+        if (s.d_work) cudaFree(s.d_work);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.done) cudaEventDestroy(s.done);
+        s = FrameSlot();
+    }
+    c->ahead.clear();
+    c->cur_slot = 0;
+}
+// a slot that is neither the current frame's nor holds a predicted frame; one whose kernel has finished if there is one
+int pick_slot(rtb_camera* c, int keep) {
+    int pick = -1;
+    for (int k = 0; k < kFrameSlots; k++) {
+        if (k == keep || std::find(c->ahead.begin(), c->ahead.end(), k) != c->ahead.end()) continue;
+        FrameSlot& s = c->slots[k];
+        if (s.in_flight && s.done && cudaEventQuery(s.done) == cudaSuccess) s.in_flight = false;
+        if (!s.in_flight) return k;
+        if (pick < 0) pick = k;
+    }
+    cudaGetLastError();  // (cudaEventQuery's cudaErrorNotReady)
+    return pick;
+}
+// One frame with matrix m12 into slot k, on the slot's stream: the kernel stores finished work units straight into the
+// slot's pinned host frame, and only inside the window of tiles where that frame can differ from what it holds.
+int launch_into_slot(rtb_object* obj, rtb_camera* cam, int k, const float m12[12], uint32_t flags) {
+    int rc = ensure_slot(cam, k);
+    if (rc) return rc;
+    FrameSlot& s = cam->slots[k];
+    rc = wait_slot(s);  // (an abandoned prediction may still be running there)
+    if (rc) return rc;
+    float record[rtb::kFrameStride];
+    fill_frame_record(obj->scene, cam, m12, record);
+    int now[4], prev[4] = {0, 0, cam->basis.W - 1, cam->basis.H - 1};
+    std::memcpy(now, record + 12, sizeof now);
+    if (s.rect_valid) std::memcpy(prev, s.rect, sizeof prev);
+    // window = the tiles touched by either rectangle (an empty rectangle has x1 < x0)
+    const bool now_empty = now[2] < now[0] || now[3] < now[1], prev_empty = prev[2] < prev[0] || prev[3] < prev[1];
+    int win[4] = {0, 0, -1, -1};
+    if (!now_empty || !prev_empty) {
+        const int x0 = now_empty ? prev[0] : prev_empty ? now[0] : std::min(now[0], prev[0]), y0 = now_empty ? prev[1] : prev_empty ? now[1] : std::min(now[1], prev[1]);
+        const int x1 = now_empty ? prev[2] : prev_empty ? now[2] : std::max(now[2], prev[2]), y1 = now_empty ? prev[3] : prev_empty ? now[3] : std::max(now[3], prev[3]);
+        win[0] = x0 / rtb::kTile; win[1] = y0 / rtb::kTile; win[2] = x1 / rtb::kTile; win[3] = y1 / rtb::kTile;
+    }
+    uint32_t* owner_bgra = s.h_bgra;  // unified addressing: a pinned allocation has the same address on the device
+    int32_t* owner_ids = s.h_ids;
+    s.rect_valid = false;
+    rc = launch_render(obj, cam, nullptr, record, 1, 0, 1, flags, s.stage_bgra, s.stage_ids, s.stream, 1, &owner_bgra, &owner_ids, nullptr, prev, win, &s);
+    if (rc) return rc;
+    RTB_CUDA(cudaEventRecord(s.done, s.stream));
+    s.in_flight = true;
+    std::memcpy(s.rect, now, sizeof now);
+    s.rect_valid = true;
+    std::memcpy(s.m12, m12, sizeof s.m12);
+    s.flags = flags;
     return RTB_OK;
 }
 
@@ -509,6 +660,7 @@ void detach_object(rtb_object* o) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (o->launch_pending) { cudaEventSynchronize(o->ev_launch); o->launch_pending = false; }  // kernels still read the arrays
+    drain_slots(c);  // ... and so may frames in flight on the camera's slots (predictions included)
     c->objects.erase(std::remove(c->objects.begin(), c->objects.end(), o), c->objects.end());
     release_scene(c, o->scene);
     o->scene = nullptr;
@@ -559,6 +711,7 @@ int rtb_set_knob(const char* name, int value) {
     else if (n == "t_active_inline") k.t_active_inline = value;
     else if (n == "steal_spin") k.steal_spin = value;
     else if (n == "inline_prefetch") k.inline_prefetch = value;
+    else if (n == "lookahead") k.lookahead = value;
     else if (n == "l2_carve_mb") k.l2_carve_mb = value;
     else return fail(RTB_ERR_ARG, "set_knob: unknown knob " + n);
     return RTB_OK;
@@ -936,6 +1089,7 @@ int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj) {
 int rtb_camera_color_pixels(rtb_camera* cam, uint8_t tag) {
     if (!cam || !cam->d_bgra) return fail(RTB_ERR_CUDA, "color_pixels: camera has no device memory");
     RTB_CUDA(cudaSetDevice(cam->device));
+    bool enqueued = false;  // something was put on the camera's own stream by this call
     if (tag == RTB_SET_COLOR_TAG) {
         // Camera.cu:77-82: the reference's SET case fills the frame with the background and FALLS THROUGH into the
         // Phong pass, so what reaches the host is "background + shaded hits of the last render" -- the call exists to
@@ -951,23 +1105,42 @@ int rtb_camera_color_pixels(rtb_camera* cam, uint8_t tag) {
             g_launches += 2;
             RTB_CUDA(cudaGetLastError());
             cam->frame_on_host = false;
+            enqueued = true;
         }
     } else if (tag != RTB_PHONG_COLOR_TAG) {
         return fail(RTB_ERR_ARG, "color_pixels: unknown tag");
     }
     if (!cam->frame_on_host) {
-        cam->host_rect_valid = false;  // the host frame becomes a copy of the device frame: nothing is known about its background
+        // the host frame becomes a copy of the device frame: slot 0's buffer, about whose background nothing is known afterwards
+        const int rc = drain_slots(cam);
+        if (rc) return rc;
+        cam->cur_slot = 0;
+        cam->slots[0].rect_valid = false;
         RTB_CUDA(cudaMemcpyAsync(cam->h_bgra, cam->d_bgra, sizeof(uint32_t) * (size_t)cam->pixels, cudaMemcpyDeviceToHost, cam->stream));
         RTB_CUDA(cudaMemcpyAsync(cam->h_ids, cam->d_ids, sizeof(int32_t) * (size_t)cam->pixels, cudaMemcpyDeviceToHost, cam->stream));
+        enqueued = true;
     }
     // the one synchronisation of a frame: the reference's wrappers synchronise after every launch (Trixel.cu:234,
     // Camera.cu:83), but nothing can observe the frame before this call returns it
-    RTB_CUDA(cudaStreamSynchronize(cam->stream));
+    if (enqueued) RTB_CUDA(cudaStreamSynchronize(cam->stream));
+    {
+        const int rc = wait_slot(cam->slots[cam->cur_slot]);  // a frame stored by its kernel: complete when the slot's event has passed
+        if (rc) return rc;
+    }
     cam->frame_on_host = true;
     return RTB_OK;
 }
-const uint32_t* rtb_camera_host_color(const rtb_camera* cam) { return cam ? cam->h_bgra : nullptr; }
-const int32_t* rtb_camera_host_ids(const rtb_camera* cam) { return cam ? cam->h_ids : nullptr; }
+// (the frame of the last render lives in the current slot's pinned buffer; slot 0 is the camera's own)
+const uint32_t* rtb_camera_host_color(const rtb_camera* cam) {
+    if (!cam) return nullptr;
+    const FrameSlot& s = cam->slots[cam->cur_slot];
+    return s.h_bgra ? s.h_bgra : cam->h_bgra;
+}
+const int32_t* rtb_camera_host_ids(const rtb_camera* cam) {
+    if (!cam) return nullptr;
+    const FrameSlot& s = cam->slots[cam->cur_slot];
+    return s.h_ids ? s.h_ids : cam->h_ids;
+}
 
 static int read_counters(rtb_camera* cam, uint64_t* out, int count, int reset) {
     if (!cam || !cam->d_counters || !out) return fail(RTB_ERR_ARG, "counters: bad argument");
@@ -997,6 +1170,7 @@ void rtb_camera_destroy(rtb_camera* cam) {
     cudaSetDevice(cam->device);
     if (cam->stream) cudaStreamSynchronize(cam->stream);
     if (cam->copy_stream) cudaStreamSynchronize(cam->copy_stream);
+    free_slots(cam);
     dfree(cam->d_bgra); dfree(cam->d_ids); dfree(cam->d_counters); dfree(cam->push_bgra); dfree(cam->push_ids);
     if (cam->h_bgra) cudaFreeHost(cam->h_bgra);
     if (cam->h_ids) cudaFreeHost(cam->h_ids);
@@ -1031,6 +1205,8 @@ int rtb_object_transform_host(rtb_object* obj, const float xyzw[4], uint8_t sele
     if (obj->xf_overridden)
         return fail(RTB_ERR_STATE, "transform: the matrix was set with rtb_object_set_matrix; rtb_camera_add_object restarts the recurrence");
     if (!obj->xf.apply(select, xyzw[0], xyzw[1], xyzw[2], xyzw[3])) return fail(RTB_ERR_ARG, "transform: unknown selector");
+    if (obj->steps_now.size() < 16) obj->steps_now.push_back({select, {xyzw[0], xyzw[1], xyzw[2], xyzw[3]}});
+    else obj->steps_frame.clear();  // too many steps per frame to be worth predicting
     if (m12_out) obj->xf.matrix(m12_out);
     return RTB_OK;
 }
@@ -1097,8 +1273,24 @@ int ensure_push_staging(rtb_camera* cam, size_t need) {
 int render_current(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
     float m12[12], record[rtb::kFrameStride];
     obj->xf.matrix(m12);
+    // do the transform steps since the last render repeat the ones before it?  (the prediction of the frames ahead)
+    {
+        auto same = [](const std::vector<rtb_object::Step>& x, const std::vector<rtb_object::Step>& y) {
+            if (x.size() != y.size()) return false;
+            for (size_t k = 0; k < x.size(); k++)
+                if (x[k].select != y[k].select || std::memcmp(x[k].v, y[k].v, sizeof x[k].v) != 0) return false;
+            return true;
+        };
+        obj->steps_repeat = same(obj->steps_now, obj->steps_frame);
+        obj->steps_frame.swap(obj->steps_now);
+        obj->steps_now.clear();
+    }
     fill_frame_record(obj->scene, cam, m12, record);
     int rc;
+    if ((flags & RTB_RENDER_COUNTERS) || !knobs().host_direct) {
+        rc = drain_slots(cam);  // the frame goes through the device frame and the copy into slot 0's host frame
+        if (rc) return rc;
+    }
     if (flags & RTB_RENDER_COUNTERS) {  // the counting variants read their records from device memory
         rc = ensure_frames(obj, 1);
         if (rc) return rc;
@@ -1107,22 +1299,41 @@ int render_current(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
         if (!rc) rc = upload_frames(obj, 1, cam->stream);
         if (!rc) rc = launch_render(obj, cam, obj->d_frames, nullptr, 1, 0, 1, flags, cam->d_bgra, cam->d_ids, cam->stream);
     } else if (knobs().host_direct) {
-        // Straight into the camera's host frame: the warps store their finished work units as row segments into the pinned,
-        // mapped buffers (the peer-push variant with the host as the owner), so the frame crosses PCIe while the rest of
-        // it is still being traced and no copy follows the kernel.  Work units that hold nothing but background are
-        // stored only where the host frame may hold something else: inside the rectangle of the frame stored before.
-        rc = ensure_push_staging(cam, (size_t)rtb_tile_major_elements(cam, 1));
-        if (rc) return rc;
-        int prev[4] = {0, 0, cam->basis.W - 1, cam->basis.H - 1};
-        if (cam->host_rect_valid) std::memcpy(prev, cam->host_rect, sizeof prev);
-        uint32_t* owner_bgra = cam->h_bgra;  // unified addressing: a pinned allocation has the same address on the device
-        int32_t* owner_ids = cam->h_ids;
-        rc = launch_render(obj, cam, nullptr, record, 1, 0, 1, flags, cam->push_bgra, cam->push_ids, cam->stream, 1, &owner_bgra, &owner_ids, nullptr, prev);
-        if (rc) { cam->host_rect_valid = false; return rc; }
-        std::memcpy(cam->host_rect, record + 12, sizeof cam->host_rect);
-        cam->host_rect_valid = true;
+        // Straight into a host frame: the warps store their finished work units as row segments into a pinned, mapped buffer
+        // (the peer-push variant with the host as the owner), so the frame crosses PCIe while the rest of it is still being
+        // traced and no copy follows the kernel.  Work units that hold nothing but background are stored only where the
+        // host frame may hold something else: inside the rectangle of the frame stored there before.
+        const bool repeat = obj->steps_repeat;
+        int slot = -1;
+        if (!cam->ahead.empty() && cam->ahead_obj == obj && cam->ahead_flags == flags &&
+            std::memcmp(cam->slots[cam->ahead.front()].m12, m12, sizeof m12) == 0) {
+            slot = cam->ahead.front();  // predicted: this very frame is already on its way
+            cam->ahead.pop_front();
+        } else {
+            cam->ahead.clear();  // (wrong guesses finish on their own and are never looked at)
+            slot = knobs().lookahead > 0 ? pick_slot(cam, cam->cur_slot) : 0;
+            rc = launch_into_slot(obj, cam, slot, m12, flags);
+            if (rc) return rc;
+        }
+        cam->cur_slot = slot;
+        // frames ahead: only while the steps between two renders repeat, and never more than the free slots allow
+        const int depth = std::min(knobs().lookahead, kFrameSlots - 2);
+        if (depth > 0 && repeat && !obj->steps_frame.empty() && !obj->xf_overridden) {
+            rtb::Transform t = cam->ahead.empty() ? obj->xf : cam->ahead_xf;
+            while ((int)cam->ahead.size() < depth) {
+                for (const rtb_object::Step& st : obj->steps_frame) t.apply(st.select, st.v[0], st.v[1], st.v[2], st.v[3]);
+                float next12[12];
+                t.matrix(next12);
+                const int k = pick_slot(cam, cam->cur_slot);
+                if (k < 0) break;
+                rc = launch_into_slot(obj, cam, k, next12, flags);
+                if (rc) return rc;
+                cam->ahead.push_back(k);
+            }
+            cam->ahead_xf = t; cam->ahead_obj = obj; cam->ahead_flags = flags;
+        }
         cam->frame_rendered = true;
-        cam->frame_on_host = true;  // once the stream has drained, which is what rtb_camera_color_pixels waits for
+        cam->frame_on_host = true;  // once the slot's event has passed, which is what rtb_camera_color_pixels waits for
         cam->device_frame_stale = true;
         return RTB_OK;
     } else {

@@ -57,6 +57,10 @@ struct RenderParams {
                                        // with the kernel parameters (constant bank) instead of through device memory
     int num_frames;
     int tiles_x;           // tiles per image row
+    // the launch covers the tiles of the window [win_tx0, win_tx0 + win_tw) x [win_ty0, ...) only (the whole frame unless the
+    // caller knows that nothing outside can change, as the single-frame path into the host frame does); tile indices below
+    // count inside the window, row by row
+    int win_tx0, win_ty0, win_tw;
     int tile_first, tile_stride;
     int my_tiles;          // number of 32x32 tiles of one frame rendered by this launch
     int unit_shift;        // log2 pixels per work unit: 5..10, a Morton block of a 32x32 tile (first segment)

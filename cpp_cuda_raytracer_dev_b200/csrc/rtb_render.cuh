@@ -443,8 +443,8 @@ render_stream_kernel(const RenderParams P) {
                 u_slot = rem / units_per_tile;
                 const int tile = P.tile_first + u_slot * P.tile_stride;
                 u_base = (rem % units_per_tile) << u_shift;
-                u_x0 = (tile % P.tiles_x) * kTile;
-                u_y0 = (tile / P.tiles_x) * kTile;
+                u_x0 = (P.win_tx0 + tile % P.win_tw) * kTile;
+                u_y0 = (P.win_ty0 + tile / P.win_tw) * kTile;
                 if (INLINE) {
                     u_rx0 = __float_as_int(P.frame0[12]); u_ry0 = __float_as_int(P.frame0[13]);
                     u_rx1 = __float_as_int(P.frame0[14]); u_ry1 = __float_as_int(P.frame0[15]);
@@ -600,7 +600,7 @@ render_stream_kernel(const RenderParams P) {
                 d.z &= 0xff;
                 const int wshift = unit_wshift(dshift);  // a unit is a (1 << wshift) x (unit_pixels >> wshift) block of its tile
                 const int tile = P.tile_first + d.y * P.tile_stride;
-                const int bx = (tile % P.tiles_x) * kTile + d.z, by = (tile / P.tiles_x) * kTile + d.w;
+                const int bx = (P.win_tx0 + tile % P.win_tw) * kTile + d.z, by = (P.win_ty0 + tile / P.win_tw) * kTile + d.w;
                 const long long lbase = (long long)d.x * P.frame_stride + ((long long)d.y * kTile + d.w) * kTile + d.z;
                 const int owner = d.x % P.push_owners;
                 uint32_t* const pc = P.push_bgra[owner];

@@ -70,7 +70,14 @@ int rtb_set_device(int device);
  * this many lanes wait at a leaf), "tail5" / "tail6" (trailing frames of a launch handed out in 32- / 64-pixel units,
  * -1 = automatic), "reserve_sms" (SMs left free beside the persistent kernel), "l2_window" (persisting L2 window:
  * 0 off, 1 node records, 2 nodes + triangles; applied at the next rtb_camera_add_object), "l2_carve_mb" (persisting
- * carve-out in MB, 0 = the size of the window), "no_rect" (1: no root-box rectangle, every pixel is traced). */
+ * carve-out in MB, 0 = the size of the window), "no_rect" (1: no root-box rectangle, every pixel is traced),
+ * "frame_order" (1: a multi-frame launch works through its frames sorted by viewing direction), "host_direct" (1:
+ * rtb_object_render stores its frame straight into the camera's host buffers; 0: device frame + copy), "lookahead" (frames
+ * rendered ahead of the current one while the transform steps between two renders repeat, 0..2), "steal_spin" /
+ * "t_active_inline" / "inline_prefetch" (single-frame launches: iterations between two looks for lanes to share a long ray
+ * with, their t_active, child-record prefetch), "sweep_direct" (1: rtb_render_sweep into pinned buffers pre-fills the
+ * background on the host and lets the kernel store the rest), "host_fill_threads", "sweep_chunk_mb" (threads and chunk
+ * size of that pre-fill). */
 int rtb_set_knob(const char* name, int value);
 
 /* ---- mesh input -------------------------------------------------------------------------- */
@@ -145,7 +152,10 @@ int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj);
  * rendered frame (every render writes every pixel), or the plain background / ids -1 before the first render. */
 int rtb_camera_color_pixels(rtb_camera* cam, uint8_t color_tag_select);
 /* Camera::h_mem.h_color.c (Camera.cpp:79): W*H little-endian 0x00RRGGBB words, row 0 = bottom.
- * Library-owned pinned memory, valid until the next render / color_pixels on this camera. */
+ * Library-owned pinned memory holding the frame rtb_camera_color_pixels delivered last, valid until the next render on
+ * this camera.  The library rotates between a few such buffers (frames are stored into them by the render kernel itself,
+ * and predicted frames may be in flight behind the current one): read the pointer again after every color_pixels, as
+ * integration/rtb_seam.cpp does for Camera::h_mem.h_color.c. */
 const uint32_t* rtb_camera_host_color(const rtb_camera* cam);
 /* hit triangle id per pixel (-1 = miss): the reference keeps these in Camera::pixel_memory::d_rmi
  * (Camera.h:57) and never reads them back; here they come with every frame. */
@@ -182,9 +192,11 @@ void rtb_object_destroy(rtb_object* obj);
 
 /* Object::render(Camera*) -> Trixel::intersect_trixels -> intersect_trixels_device
  * (Object.cpp:10, Trixel.h:474, Trixel.cu:210).  One fused launch: ray generation, traversal,
- * Moller-Trumbore, Phong and background into the camera's device frame; follow with
- * rtb_camera_color_pixels(PHONG) to obtain it on the host, exactly like the reference's frame loop
- * (WinMain.cpp:212-213).  The call returns as soon as the kernel is queued (the reference's cudaDeviceSynchronize at
+ * Moller-Trumbore, Phong and background; the kernel stores the finished frame straight into one of the camera's pinned host
+ * buffers (with RTB_RENDER_COUNTERS, or the knob "host_direct" off: into the device frame, copied by color_pixels); follow
+ * with rtb_camera_color_pixels(PHONG) to obtain it, exactly like the reference's frame loop (WinMain.cpp:212-213).  While
+ * the transform steps between two renders repeat (a key held down), the next frames are rendered ahead on other streams
+ * and a render call whose matrix equals the predicted one bit for bit finds its frame already on the way.  The call returns as soon as the kernel is queued (the reference's cudaDeviceSynchronize at
  * Trixel.cu:234 cannot be observed before color_pixels delivers the frame); rtb_camera_color_pixels is the one
  * synchronisation of a frame, and launch errors surface there at the latest. */
 int rtb_object_render(rtb_object* obj, rtb_camera* cam, uint32_t flags);
@@ -220,8 +232,10 @@ int rtb_camera_render_scene_device_async(rtb_camera* cam, uint32_t flags, uint32
 
 /* Batched animation sweep (WinMain.cpp:174-239 with a key held down): for frame k = 0..num_frames-1
  * apply `steps_per_frame` transforms ops[k*steps_per_frame ...] (each 5 floats: select, x, y, z, w;
- * select 0 = no-op) and render.  The frames are rendered in chunks of about 16 MB of output per buffer, one persistent
- * launch per chunk; a finished chunk streams to the host while the next one renders (two chunks in flight).  The call
+ * select 0 = no-op) and render.  Pinned caller buffers: host threads pre-fill a chunk of frames (256 MB) with the background
+ * while the kernel traces the chunk before and stores every work unit that holds anything else straight into the buffers
+ * over PCIe -- no copy engine.  Pageable buffers: chunks of about 16 MB of output per buffer, one persistent launch per
+ * chunk; a finished chunk streams to the host while the next one renders (two chunks in flight).  The call
  * returns when every frame is in the caller's buffers.  bgra_out / ids_out are caller buffers of
  * num_frames*W*H elements (pageable or pinned; either may be NULL) -- the only interface here that
  * writes into caller memory.  The object's transform state advances as if the calls had been made

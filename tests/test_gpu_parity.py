@@ -1103,3 +1103,36 @@ def test_sweep_into_pinned_buffers_without_the_copy_engine(gpu, orc):
     assert np.array_equal(got[1][0][F - 1].astype(np.int64), oids)
     assert channel_diff(got[1][1][F - 1].view(np.uint32), obgra).max(initial=0) <= COLOUR_TOL
     p.close()
+
+
+def test_frames_rendered_ahead_are_the_frames_asked_for(gpu, orc):
+    """Single-frame path with lookahead: while the steps between two renders repeat, predicted frames are in flight on other
+    slots; whatever the caller then does -- keeps going, turns round, stands still, takes two steps per frame, moves another
+    object -- every delivered frame must be the frame of the matrix it asked for (oracle), and equal to the run without
+    lookahead."""
+    W, H = 224, 126
+    pts = gpu.geodesic_mesh(10)
+    R, T = gpu.R_KEY_QUAT, gpu.T_KEY_QUAT
+    script = [[(gpu.ROTATE_TRI_PY, R)]] * 7 + [[(gpu.ROTATE_TRI_PY, T)]] * 4 + [[]] * 3 + [[(gpu.ROTATE_TRI_PY, R), (gpu.TRANSLATE_Z, (0.0, 0.0, 1.0, 0.004))]] * 5 + \
+             [[(gpu.ROTATE_TRI_PY, R)]] * 3 + [[(gpu.ROTATE_TRI_PY, (0.0998, 0.0, 0.0, 0.995))]] * 4
+    frames = {}
+    for look in (2, 0):
+        gpu.set_knob("lookahead", look)
+        p = Pair(gpu, orc, pts, W, H)
+        out = []
+        for k, steps in enumerate(script):
+            for sel, q in steps:
+                p.transform(sel, q)
+            ids, bgra, oids, obgra = p.check()
+            out.append((ids, bgra))
+            if k == 9:  # a second object of the same mesh is added and rendered in between: the prediction must not leak into it
+                other = gpu.Object(p.mesh); p.cam.add_object(other)
+                other.transform(T, gpu.ROTATE_TRI_PY)
+                i2, c2 = other.render_frame(p.cam)
+                assert not np.array_equal(i2, ids)
+                other.close()
+        frames[look] = out
+        p.close()
+    gpu.set_knob("lookahead", 2)
+    for a, b in zip(frames[2], frames[0]):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
