@@ -188,13 +188,16 @@ __global__ void selftest_exact_kernel(uint64_t seed, long long count, unsigned l
 #ifndef RTB_STEAL
 #define RTB_STEAL 1
 #endif
+#ifndef RTB_STEAL_ALL
+#define RTB_STEAL_ALL 0  // 1: multi-frame launches share long rays too, when their queue has run dry (the tail of a launch)
+#endif
 #ifndef RTB_MIN_BLOCKS_INLINE
 #define RTB_MIN_BLOCKS_INLINE 6  // a single frame never fills the GPU: registers matter more than resident warps (80 instead of 64)
 #endif
 template <bool CULL, bool COUNT, bool PUSH, bool INLINE = false>
 __global__ void __launch_bounds__(kBlockThreads, INLINE ? RTB_MIN_BLOCKS_INLINE : PUSH ? RTB_MIN_BLOCKS_PUSH : RTB_MIN_BLOCKS)
 render_stream_kernel(const RenderParams P) {
-    constexpr bool STEAL = INLINE && (RTB_STEAL != 0);
+    constexpr bool STEAL = (INLINE || (RTB_STEAL_ALL != 0 && !COUNT)) && (RTB_STEAL != 0);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanemask_lt = (1u << lane) - 1u;
     __shared__ int s_helpers[STEAL ? kBlockThreads / 32 : 1][STEAL ? 32 : 1];  // per lane: helpers still out with parts of its ray

@@ -196,8 +196,9 @@ void rtb_object_destroy(rtb_object* obj);
  * buffers (with RTB_RENDER_COUNTERS, or the knob "host_direct" off: into the device frame, copied by color_pixels); follow
  * with rtb_camera_color_pixels(PHONG) to obtain it, exactly like the reference's frame loop (WinMain.cpp:212-213).  While
  * the transform steps between two renders repeat (a key held down), the next frames are rendered ahead on other streams
- * and a render call whose matrix equals the predicted one bit for bit finds its frame already on the way.  The call returns as soon as the kernel is queued (the reference's cudaDeviceSynchronize at
- * Trixel.cu:234 cannot be observed before color_pixels delivers the frame); rtb_camera_color_pixels is the one
+ * and a render call whose matrix equals the predicted one bit for bit finds its frame already on the way.  The call
+ * returns as soon as the kernel is queued (the reference's cudaDeviceSynchronize at Trixel.cu:234 cannot be observed
+ * before color_pixels delivers the frame); rtb_camera_color_pixels is the one
  * synchronisation of a frame, and launch errors surface there at the latest. */
 int rtb_object_render(rtb_object* obj, rtb_camera* cam, uint32_t flags);
 /* = rtb_object_render + rtb_camera_color_pixels(PHONG) with one synchronisation; the frame and the
