@@ -412,6 +412,7 @@ def kernel_only(env, sc, K, Wm, shard="frames", exchange="push", sample_clocks=T
     region_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(total_steps)]
     gather_done = [None, None]
+    allreduce_done = [None]
     sampler = ClockSampler(env.local) if sample_clocks else None
     launches0 = 0
     for step in range(total_steps):
@@ -435,10 +436,18 @@ def kernel_only(env, sc, K, Wm, shard="frames", exchange="push", sample_clocks=T
                 obj.render_frames_push_striped_async(cam, my_mats(step), push_ptrs[2 * slot], push_ptrs[2 * slot + 1], stream.cuda_stream,
                                                      tile_first=rank, tile_stride=world, flags=rtb.RENDER_PUSH_PREFILLED)
                 ev[step][1].record(stream)
-                # the NEXT step's frames of this owner are pre-filled with background before this step's all-reduce lets any
-                # rank start pushing into them: work units that hold nothing but background then never cross NVLink
-                cam.fill_frames_device_async(owned, my_bufs[2 * (slot ^ 1)].ptr, my_bufs[2 * (slot ^ 1) + 1].ptr, stream.cuda_stream)
+                # The NEXT step's frames of this owner are pre-filled with background before this step's all-reduce lets any
+                # rank start pushing into them: work units that hold nothing but background then never cross NVLink.  The
+                # fill is queued on a second stream BEHIND the render kernel: the other slot has been free since the previous
+                # step's all-reduce, and the fill's blocks move in as the persistent kernel's blocks leave -- it runs in the
+                # shadow of the launch's tail (the latency of its longest rays) instead of after it.
+                if allreduce_done[0] is not None:
+                    side.wait_event(allreduce_done[0])
+                cam.fill_frames_device_async(owned, my_bufs[2 * (slot ^ 1)].ptr, my_bufs[2 * (slot ^ 1) + 1].ptr, side.cuda_stream)
+                fill_done = torch.cuda.Event(); fill_done.record(side)
+                stream.wait_event(fill_done)
                 dist.all_reduce(push_flag)  # completes when every rank's kernel has: the step's frames are whole on their owners
+                allreduce_done[0] = torch.cuda.Event(); allreduce_done[0].record(stream)
             else:
                 obj.render_frames_device_async(cam, my_mats(step), d_col[slot].data_ptr(), d_ids[slot].data_ptr(), stream.cuda_stream,
                                                tile_first=rank if tiles_mode else 0, tile_stride=world if tiles_mode else 1,
