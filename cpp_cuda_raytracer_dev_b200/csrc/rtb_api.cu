@@ -162,12 +162,16 @@ struct rtb_camera {
     // Single-frame path (rtb_object_render): the kernel stores the frame straight into h_bgra / h_ids (pinned, mapped),
     // and only where it can differ from what they hold -- host_rect is the pixel rectangle outside which the host frame
     // is known to be background / -1 (the root-box rectangle of the frame last stored there this way).
+    FrameSlot sweep_lane[2];          // rtb_render_sweep into pinned buffers: two streams with their own staging and work counter, so
+    size_t sweep_lane_elements = 0;   // that the tail of one chunk's launch overlaps the start of the next (only stream, d_work, stage_* used)
     FrameSlot slots[kFrameSlots];
     int cur_slot = 0;                 // the slot whose host frame rtb_camera_host_color / _ids name
     std::deque<int> ahead;            // slots rendering predicted frames, oldest first
     rtb_object* ahead_obj = nullptr;  // ... of this object,
     uint32_t ahead_flags = 0;         // ... with these render flags;
     rtb::Transform ahead_xf;          // the recurrence's state after the last predicted frame
+    int ahead_misses = 0;             // predictions dropped in a row (a caller that alternates objects or jitters: stop guessing)
+    int ahead_pause = 0;              // renders left before guessing is tried again
     bool device_frame_stale = false;  // the last frame went to the host only: d_bgra / d_ids hold an older one
 };
 
@@ -222,7 +226,7 @@ struct Knobs {
     int steal_spin = 8;         // ... and how many iterations a draining warp runs between two looks for lanes to share with (power of two)
     int inline_prefetch = 1;    // ... and whether it asks for both children's records ahead of the decision
     int lookahead = 2;          // single-frame path: predicted frames kept in flight behind the current one (0 = off)
-    int sweep_chunk_mb = 256;   // ... and the size of the chunks (MB of host frames) in which fill and render alternate
+    int sweep_chunk_mb = 256;   // ... and the largest size of the chunks (MB of host frames) in which fill and render alternate
     int l2_carve_mb = 0;  // persisting L2 carve-out in MB, 0 = the size of the window
 };
 Knobs& knobs() {
@@ -595,8 +599,42 @@ void free_slots(rtb_camera* c) {
         if (s.done) cudaEventDestroy(s.done);
         s = FrameSlot();
     }
+    for (FrameSlot& s : c->sweep_lane) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        if (s.stage_bgra) cudaFree(s.stage_bgra);
+        if (s.stage_ids) cudaFree(s.stage_ids);
+        if (s.d_work) cudaFree(s.d_work);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        s = FrameSlot();
+    }
+    c->sweep_lane_elements = 0;
     c->ahead.clear();
     c->cur_slot = 0;
+}
+// the two lanes of a host-direct sweep hold at least `elements` staging elements per array
+int ensure_sweep_lanes(rtb_camera* c, size_t elements) {
+    for (FrameSlot& s : c->sweep_lane) {
+        if (!s.stream) RTB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        if (!s.d_work) {
+            RTB_CUDA(cudaMalloc(&s.d_work, sizeof(unsigned long long)));
+            RTB_CUDA(cudaMemset(s.d_work, 0, sizeof(unsigned long long)));
+            s.work_base = 0;
+        }
+    }
+    if (c->sweep_lane_elements >= elements) return RTB_OK;
+    for (FrameSlot& s : c->sweep_lane) {
+        RTB_CUDA(cudaStreamSynchronize(s.stream));
+        if (s.stage_bgra) cudaFree(s.stage_bgra);
+        if (s.stage_ids) cudaFree(s.stage_ids);
+        s.stage_bgra = nullptr; s.stage_ids = nullptr;
+    }
+    c->sweep_lane_elements = 0;
+    for (FrameSlot& s : c->sweep_lane) {
+        RTB_CUDA(cudaMalloc(&s.stage_bgra, 4 * elements));
+        RTB_CUDA(cudaMalloc(&s.stage_ids, 4 * elements));
+    }
+    c->sweep_lane_elements = elements;
+    return RTB_OK;
 }
 // a slot that is neither the current frame's nor holds a predicted frame; one whose kernel has finished if there is one
 int pick_slot(rtb_camera* c, int keep) {
@@ -1309,7 +1347,9 @@ int render_current(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
             std::memcmp(cam->slots[cam->ahead.front()].m12, m12, sizeof m12) == 0) {
             slot = cam->ahead.front();  // predicted: this very frame is already on its way
             cam->ahead.pop_front();
+            cam->ahead_misses = 0;
         } else {
+            if (!cam->ahead.empty() && ++cam->ahead_misses >= 2) { cam->ahead_pause = 32; cam->ahead_misses = 0; }
             cam->ahead.clear();  // (wrong guesses finish on their own and are never looked at)
             slot = knobs().lookahead > 0 ? pick_slot(cam, cam->cur_slot) : 0;
             rc = launch_into_slot(obj, cam, slot, m12, flags);
@@ -1318,7 +1358,8 @@ int render_current(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
         cam->cur_slot = slot;
         // frames ahead: only while the steps between two renders repeat, and never more than the free slots allow
         const int depth = std::min(knobs().lookahead, kFrameSlots - 2);
-        if (depth > 0 && repeat && !obj->steps_frame.empty() && !obj->xf_overridden) {
+        if (cam->ahead_pause > 0) cam->ahead_pause--;
+        if (depth > 0 && repeat && cam->ahead_pause == 0 && !obj->steps_frame.empty() && !obj->xf_overridden) {
             rtb::Transform t = cam->ahead.empty() ? obj->xf : cam->ahead_xf;
             while ((int)cam->ahead.size() < depth) {
                 for (const rtb_object::Step& st : obj->steps_frame) t.apply(st.select, st.v[0], st.v[1], st.v[2], st.v[3]);
@@ -1600,23 +1641,37 @@ int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32
     // the frames: 128-byte row stores over PCIe).  What crosses the bus is the picture, not the wallpaper.
     if (knobs().sweep_direct && !(flags & RTB_RENDER_COUNTERS) && (bgra_out || ids_out) && (!bgra_out || direct_bgra) && (!ids_out || direct_ids)) {
         const size_t frame_bytes = 4 * P * ((bgra_out ? 1u : 0u) + (ids_out ? 1u : 0u));
-        const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)num_frames, ((size_t)std::max(1, knobs().sweep_chunk_mb) << 20) / frame_bytes));
-        rc = ensure_push_staging(cam, (size_t)chunk * (size_t)rtb_tile_major_elements(cam, 1));
+        // Chunks grow from 32 MB to the knob's size (256 MB): the first fill is the only one the GPU cannot hide behind, so it
+        // is small; afterwards fill k+1 and launch k run side by side and a launch's fixed cost wants large chunks.
+        const size_t cap_bytes = (size_t)std::max(1, knobs().sweep_chunk_mb) << 20;
+        const int cap = (int)std::max<size_t>(1, std::min<size_t>((size_t)num_frames, cap_bytes / frame_bytes));
+        int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)cap, std::min<size_t>(cap_bytes / 8, (size_t)32 << 20) / frame_bytes));
+        rc = ensure_sweep_lanes(cam, (size_t)cap * (size_t)rtb_tile_major_elements(cam, 1));
         if (rc) return rc;
+        for (FrameSlot& lane : cam->sweep_lane) RTB_CUDA(cudaStreamWaitEvent(lane.stream, obj->ev_upload, 0));  // the frame records
         const rtb::CameraBasis& b = cam->basis;
         const uint32_t bg = ((uint32_t)b.background[3] << 24) | ((uint32_t)b.background[0] << 16) | ((uint32_t)b.background[1] << 8) | b.background[2];
         const int threads = host_fill_threads();
-        for (int f0 = 0; f0 < num_frames; f0 += chunk) {
-            const int nf = std::min(chunk, num_frames - f0);
-            if (bgra_out) rtb::fill_words(bgra_out + (size_t)f0 * P, (size_t)nf * P, bg, threads);
-            if (ids_out) rtb::fill_words(reinterpret_cast<uint32_t*>(ids_out) + (size_t)f0 * P, (size_t)nf * P, 0xffffffffu, threads);
+        int turn = 0;
+        const int first_chunk = chunk;
+        for (int f0 = 0; f0 < num_frames;) {
+            FrameSlot& lane = cam->sweep_lane[turn];  // chunks alternate between two streams: a launch's tail (the latency of its
+            turn ^= 1;                                // longest rays) runs beside the next chunk instead of in front of it
+            // ... and they shrink again towards the end: what the call waits for after its last fill is the last launch
+            const int left = num_frames - f0;
+            const int nf = std::min(chunk, left > 2 * first_chunk ? (left + 1) / 2 : left);
+            rtb::fill_words2(bgra_out ? bgra_out + (size_t)f0 * P : nullptr, bg, ids_out ? reinterpret_cast<uint32_t*>(ids_out) + (size_t)f0 * P : nullptr,
+                             0xffffffffu, (size_t)nf * P, threads);
             uint32_t* owner_bgra = bgra_out ? static_cast<uint32_t*>(dev_bgra) + (size_t)f0 * P : nullptr;
             int32_t* owner_ids = ids_out ? static_cast<int32_t*>(dev_ids) + (size_t)f0 * P : nullptr;
             rc = launch_render(obj, cam, obj->d_frames + rtb::kFrameStride * (size_t)f0, nullptr, nf, 0, 1, flags | RTB_RENDER_PUSH_PREFILLED,
-                               bgra_out ? cam->push_bgra : nullptr, ids_out ? cam->push_ids : nullptr, cam->stream, 1,
-                               bgra_out ? &owner_bgra : nullptr, ids_out ? &owner_ids : nullptr);
+                               bgra_out ? lane.stage_bgra : nullptr, ids_out ? lane.stage_ids : nullptr, lane.stream, 1,
+                               bgra_out ? &owner_bgra : nullptr, ids_out ? &owner_ids : nullptr, nullptr, nullptr, nullptr, &lane);
             if (rc) return rc;
+            f0 += nf;
+            chunk = std::min(cap, chunk * 2);
         }
+        for (FrameSlot& lane : cam->sweep_lane) RTB_CUDA(cudaStreamSynchronize(lane.stream));
         RTB_CUDA(cudaStreamSynchronize(cam->stream));
         return RTB_OK;
     }
@@ -1750,17 +1805,29 @@ int rtb_measure_l2_read_bandwidth(size_t bytes, int iters, double* gb_per_s) {
 
 int rtb_measure_host_fill_bandwidth(size_t bytes, int threads, double* gb_per_s) {
     if (!gb_per_s || bytes < (1u << 20)) return fail(RTB_ERR_ARG, "measure_host_fill: bad argument");
+    // pinned memory where a device exists (that is what the sweep fills); plain memory otherwise, so that the host-side
+    // machinery can be exercised without a GPU
     uint32_t* buf = nullptr;
-    RTB_CUDA(cudaSetDevice(g_device));
-    RTB_CUDA(cudaMallocHost(&buf, bytes));
+    bool pinned = cudaSetDevice(g_device) == cudaSuccess && cudaMallocHost(&buf, bytes) == cudaSuccess;
+    if (!pinned) {
+        cudaGetLastError();
+        buf = static_cast<uint32_t*>(std::malloc(bytes));
+        if (!buf) return fail(RTB_ERR_NOMEM, "measure_host_fill: out of host memory");
+    }
     double best = 0.0;
+    bool ok = true;
+    const size_t words = bytes / 4;
     for (int rep = 0; rep < 4; rep++) {  // the first pass also touches the pages
+        const uint32_t value = 0x00f08200u + (uint32_t)rep;
         const auto t0 = std::chrono::steady_clock::now();
-        rtb::fill_words(buf, bytes / 4, 0x00f08200u + (uint32_t)rep, threads);
+        rtb::fill_words(buf + (rep & 1), words - 3, value, threads);  // (odd starts: the unaligned head and tail paths)
         const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (rep) best = std::max(best, (double)bytes / s / 1e9);
+        for (size_t k = (size_t)(rep & 1); k < (size_t)(rep & 1) + words - 3; k += 4099) ok = ok && buf[k] == value;
+        ok = ok && buf[(rep & 1) + words - 4] == value;
     }
-    cudaFreeHost(buf);
+    if (pinned) cudaFreeHost(buf); else std::free(buf);
+    if (!ok) return fail(RTB_ERR_STATE, "measure_host_fill: the filled buffer does not hold the value");
     *gb_per_s = best;
     return RTB_OK;
 }

@@ -9,6 +9,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #if defined(__x86_64__)
 #include <emmintrin.h>
@@ -897,24 +900,95 @@ void Transform::set_matrix(const float m[12]) {
 // Fill `count` 32-bit words with `value` on `threads` host threads.  Streaming (non-temporal) stores where the platform
 // has them: the destination is a frame buffer that is written once and read later by somebody else, so there is no
 // point in first reading its cache lines in (which is what ordinary stores do) -- about half the memory traffic.
-void fill_words(uint32_t* dst, size_t count, uint32_t value, int threads) {
+namespace {
+inline void fill_range(uint32_t* p, uint32_t* const end, uint32_t value) {
+#if defined(__x86_64__)
+    while (p < end && ((uintptr_t)p & 15u)) *p++ = value;
+    const __m128i v = _mm_set1_epi32((int)value);
+    for (; p + 16 <= end; p += 16) {
+        _mm_stream_si128((__m128i*)p, v); _mm_stream_si128((__m128i*)(p + 4), v);
+        _mm_stream_si128((__m128i*)(p + 8), v); _mm_stream_si128((__m128i*)(p + 12), v);
+    }
+    _mm_sfence();
+#endif
+    while (p < end) *p++ = value;
+}
+}  // namespace
+// The fills of a sweep come back to back, a few hundred megabytes each, so their threads are kept: a small pool that
+// lives as long as the process (workers sleep on a condition variable between jobs; a job is a range of task indices
+// handed out by an atomic counter, the calling thread works too).  Starting a dozen threads per call cost 10-15 % of a
+// 256 MB fill.
+namespace {
+class FillPool {
+public:
+    void run(int threads, int64_t tasks, const std::function<void(int64_t)>& body) {
+        std::lock_guard<std::mutex> one_job_at_a_time(job_lock_);
+        const int helpers = (int)std::min<int64_t>(std::max(0, threads - 1), std::max<int64_t>(0, tasks - 1));
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            while ((int)workers_.size() < helpers) workers_.emplace_back([this, id = (int)workers_.size()] { work(id); });
+            body_ = &body; tasks_ = tasks; next_.store(0); active_ = helpers; wanted_ = helpers; generation_++;
+        }
+        wake_.notify_all();
+        drain();
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return active_ == 0; });
+        body_ = nullptr;
+    }
+private:
+    void drain() {
+        for (;;) {
+            const int64_t t = next_.fetch_add(1);
+            if (t >= tasks_) return;
+            (*body_)(t);
+        }
+    }
+    void work(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                wake_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (id >= wanted_) continue;  // this job wants fewer helpers than the pool holds
+            }
+            drain();
+            std::unique_lock<std::mutex> lk(m_);
+            if (--active_ == 0) done_.notify_one();
+        }
+    }
+    std::mutex job_lock_, m_;
+    std::condition_variable wake_, done_;
+    std::vector<std::thread> workers_;  // never joined: they sleep until the process ends
+    const std::function<void(int64_t)>* body_ = nullptr;
+    int64_t tasks_ = 0;
+    std::atomic<int64_t> next_{0};
+    int active_ = 0, wanted_ = 0;
+    uint64_t generation_ = 0;
+};
+FillPool& fill_pool() {
+    static FillPool* pool = new FillPool();  // intentionally leaked: its sleeping workers must not be torn down by static destructors
+    return *pool;
+}
+}  // namespace
+// two buffers in one parallel region (either may be null): the colour and the id frames of a chunk of a sweep
+void fill_words2(uint32_t* a, uint32_t value_a, uint32_t* b, uint32_t value_b, size_t count, int threads) {
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
     const size_t chunk = (size_t)1 << 18;  // 1 MB per task
-    const int64_t tasks = (int64_t)((count + chunk - 1) / chunk);
-    parallel_for(threads, tasks, 1, [&](int64_t task) {
-        uint32_t* p = dst + (size_t)task * chunk;
-        uint32_t* const end = dst + std::min(count, ((size_t)task + 1) * chunk);
-#if defined(__x86_64__)
-        while (p < end && ((uintptr_t)p & 15u)) *p++ = value;
-        const __m128i v = _mm_set1_epi32((int)value);
-        for (; p + 16 <= end; p += 16) {
-            _mm_stream_si128((__m128i*)p, v); _mm_stream_si128((__m128i*)(p + 4), v);
-            _mm_stream_si128((__m128i*)(p + 8), v); _mm_stream_si128((__m128i*)(p + 12), v);
-        }
-        _mm_sfence();
-#endif
-        while (p < end) *p++ = value;
-    });
+    const int64_t per = (int64_t)((count + chunk - 1) / chunk);
+    const int64_t tasks = per * ((a ? 1 : 0) + (b ? 1 : 0));
+    const std::function<void(int64_t)> body = [&](int64_t task) {
+        const bool second = a ? task >= per : true;
+        uint32_t* const base = second ? b : a;
+        const size_t t = (size_t)(second && a ? task - per : task);
+        fill_range(base + t * chunk, base + std::min(count, (t + 1) * chunk), second ? value_b : value_a);
+    };
+    if (tasks <= 1 || threads <= 1) {
+        for (int64_t t = 0; t < tasks; t++) body(t);
+        return;
+    }
+    fill_pool().run(threads, tasks, body);
 }
+void fill_words(uint32_t* dst, size_t count, uint32_t value, int threads) { fill_words2(dst, value, nullptr, 0, count, threads); }
 
 }  // namespace rtb

@@ -67,6 +67,7 @@ void free_device_tree(DeviceTree& t);
 
 // host-side fill of a frame buffer (background pre-fill of the sweep's host frames), threads <= 0: all hardware threads
 void fill_words(uint32_t* dst, size_t count, uint32_t value, int threads);
+void fill_words2(uint32_t* a, uint32_t value_a, uint32_t* b, uint32_t value_b, size_t count, int threads);  // either may be null
 
 // ---- camera (Camera.cpp:5-67) ----------------------------------------------------------------
 struct CameraBasis {

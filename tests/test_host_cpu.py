@@ -374,3 +374,13 @@ def test_reference_arm_standin_mesh_is_the_products_standin_mesh(rtb):
         assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), kw
     big_a, big_b = rtb.geodesic_mesh(209), standin.geodesic_mesh(209)     # the dragon-sized stand-in of the headline bench
     assert np.array_equal(big_a.view(np.uint32), big_b.view(np.uint32))
+
+
+def test_host_fill_machinery_without_a_gpu(rtb):
+    """The sweep's background pre-fill (rtb::fill_words: streaming stores on a persistent thread pool) through its probe:
+    repeated jobs with changing thread counts, unaligned heads and tails, contents checked inside the library."""
+    for threads in (1, 3, 8, 2, 0, 5):
+        gbs = rtb.measure_host_fill_bandwidth((1 << 20) + 4096 * (threads + 1), threads)
+        assert gbs > 0.0
+    with pytest.raises(rtb.RtbError):
+        rtb.measure_host_fill_bandwidth(1000, 1)
