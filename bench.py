@@ -55,8 +55,9 @@ WORKLOADS = {
 }
 # tiles mode (N > 1) renders N x this many frames per step (weak scaling)
 # (a launch ends with the latency of its longest rays, ~0.3 ms that no number of GPUs shortens: a step must be long enough for
-# that tail not to dominate what is being measured -- at 4K, N x 18 frames = 2.2 ms per GPU and step at N = 8)
-TILES_FRAMES = {"dragon_orbit_960x540": 60, "dragon_closeup_960x540": 60, "happy_orbit_3840x2160": 18, "bunny_960x540": 60, "synthetic10m_7680x4320": 1}
+# that tail not to dominate what is being measured -- at 4K, N x 24 frames per step: the 360-frame sweep of configs[3] in 15 / N
+# steps; measured at N = 8: 84 % with N x 18 frames, 80 % at N = 2 with N x 6)
+TILES_FRAMES = {"dragon_orbit_960x540": 60, "dragon_closeup_960x540": 60, "happy_orbit_3840x2160": 24, "bunny_960x540": 60, "synthetic10m_7680x4320": 1}
 # the other configurations of BASELINE.json, measured beside the headline in the default N=1 run: (steps, warm-up steps)
 EXTRA_WORKLOADS = {"bunny_960x540": (3, 3), "dragon_closeup_960x540": (3, 3), "happy_orbit_3840x2160": (5, 3), "synthetic10m_7680x4320": (5, 3)}
 README_FPS = 100.0  # /root/reference/README.md:19 (Stanford Dragon, 960x540, unnamed GPU)

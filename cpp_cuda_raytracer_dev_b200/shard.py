@@ -3,8 +3,8 @@
 Every pixel of every frame is independent and the scene is read-only, so
 the path shards with no data-path collective: the scene is replicated on every rank, a single frame
 is split into interleaved 32x32 image tiles (tile t belongs to rank t % world), an animation sweep is
-split into blocks of consecutive frames, and the only exchange is the gather of finished tiles /
-frames to rank 0.  The functions here define who renders what and how rank 0 reassembles it; they
+split into blocks of consecutive frames, and the only exchange is the delivery of finished tiles to the
+rank that owns the frame (frame f -> rank f % world in the fused peer push; rank 0 in the NCCL gather).  The functions here define who renders what and how rank 0 reassembles it; they
 are shared by bench.py (NCCL) and tests/test_multi_cpu.py (gloo).
 """
 import numpy as np
@@ -32,6 +32,17 @@ def frame_block(step, rank, world, frames_per_step):
     """Global frame indices of the block rank `rank` renders in step `step` of a sweep."""
     first = (step * world + rank) * frames_per_step
     return first, first + frames_per_step
+
+
+def frame_owner(frame, world):
+    """Striped ownership of the fused tile exchange: frame `frame` of a step is assembled on rank frame % world, as that
+    rank's frame frame // world (rtb_render_frames_push_striped_async, RenderParams::push_owners)."""
+    return frame % world, frame // world
+
+
+def owned_frames(rank, world, frames_per_step):
+    """Frames of a step of `frames_per_step` frames that rank `rank` owns, in the order of its local frame index."""
+    return list(range(rank, frames_per_step, world))
 
 
 def compose_tiles(parts, W, H):

@@ -65,6 +65,25 @@ def _worker(rank, port, result_path):
         sweep = torch.cat(got).numpy()
         for f in range(WORLD * FRAMES):
             ok &= np.array_equal(sweep[f], scene.render(m12=mats[f])[0])
+
+    # ---- a step sharded by tiles with STRIPED frame ownership (the fused peer push: frame f is assembled on rank f % world) --
+    step = 5  # frames per step: ownership 3 + 2
+    mine_tiles = [np.where(mask, scene.render(m12=mats[f])[0], -7).astype(np.int64) for f in range(step)]  # this rank's tiles of every frame
+    owned = {}
+    for f in range(step):
+        owner, local = shard.frame_owner(f, WORLD)
+        parts = [torch.empty(W * H, dtype=torch.int64) for _ in range(WORLD)] if rank == owner else None
+        dist.gather(torch.from_numpy(mine_tiles[f]), parts, dst=owner)  # (the GPU path stores straight into the owner's frame instead)
+        if rank == owner:
+            owned[local] = shard.compose_tiles([t.numpy() for t in parts], W, H)
+    mine_owned = shard.owned_frames(rank, WORLD, step)
+    ok_striped = sorted(owned) == list(range(len(mine_owned)))
+    for local, f in enumerate(mine_owned):
+        ok_striped &= np.array_equal(owned[local], scene.render(m12=mats[f])[0])
+    flag = torch.tensor([1 if ok_striped else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every owner holds exactly its frames, whole
+    if rank == 0:
+        ok &= bool(int(flag[0]))
         with open(result_path, "w") as fh:
             fh.write("ok" if ok else "mismatch")
     dist.barrier()
@@ -88,5 +107,9 @@ def test_tile_partition_covers_every_pixel_once():
             counts = [int(shard.tile_mask(w, h, r, world).sum()) for r in range(world)]
             if w * h > 100000:
                 assert max(counts) - min(counts) <= 0.05 * max(counts)   # balanced to within a few tiles
+    for world in (1, 2, 3, 8):
+        seen = sorted(f for r in range(world) for f in shard.owned_frames(r, world, 19))
+        assert seen == list(range(19))
+        assert all(shard.frame_owner(f, world) == (r, k) for r in range(world) for k, f in enumerate(shard.owned_frames(r, world, 19)))
     blocks = [shard.frame_block(s, r, 4, 60) for s in range(3) for r in range(4)]
     assert blocks == [(k * 60, k * 60 + 60) for k in range(12)]
