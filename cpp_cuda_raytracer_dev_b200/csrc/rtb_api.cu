@@ -1120,6 +1120,7 @@ int rtb_camera_add_object(rtb_camera* cam, rtb_object* obj) {
     obj->xf.reset(cam->basis.pos);
     obj->xf_ready = true;
     obj->xf_overridden = false;
+    obj->steps_now.clear(); obj->steps_frame.clear(); obj->steps_repeat = false;  // the recurrence starts over: nothing to predict from
     return RTB_OK;
     });
 }
@@ -1323,11 +1324,11 @@ int render_current(rtb_object* obj, rtb_camera* cam, uint32_t flags) {
         obj->steps_frame.swap(obj->steps_now);
         obj->steps_now.clear();
     }
-    fill_frame_record(obj->scene, cam, m12, record);
     int rc;
     if ((flags & RTB_RENDER_COUNTERS) || !knobs().host_direct) {
         rc = drain_slots(cam);  // the frame goes through the device frame and the copy into slot 0's host frame
         if (rc) return rc;
+        fill_frame_record(obj->scene, cam, m12, record);
     }
     if (flags & RTB_RENDER_COUNTERS) {  // the counting variants read their records from device memory
         rc = ensure_frames(obj, 1);
