@@ -15,13 +15,15 @@
 // lists at once:
 //     level_nodes_kernel   one thread per node: own bounds from the list ends, leaf or split list, children created;
 //     side_kernel          one thread per position of the split lists: one byte per triangle, "goes to the left child";
-//     one exclusive scan   (cub::DeviceScan, two launches) over n+1 six-component flag vectors computed on the fly:
-//                          component k of position i = the side byte of the element of list k at i;
-//     scatter_kernel       one thread per list position: the six stable partitions (offsets = scan differences
+//     flags_kernel         one thread per position: its six "goes left" flags and their exclusive prefixes inside a
+//                          512-position block, packed into one 64-bit word; the block's six totals;
+//     block_scan_kernel    the totals become block bases (one 1024-thread block per list);
+//     scatter_kernel       one thread per list position: the six stable partitions (offsets = prefix differences
 //                          relative to the node's range start, so ranges never mix), node of position.
 // (Round 1: flag / scan / scatter / copy per list and two blocking 4-byte read-backs per level, ~35 launches per level.)
 // cub's radix sort and scan are library primitives used for the build only; the ray-cast hot path does not
 // touch them.
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
@@ -114,16 +116,15 @@ __global__ void level_nodes_kernel(Lists L, int level_begin, int count, int next
     rec[cr] = r > m + 1 ? rec[node] + 1 + (m - l) : -1;
 }
 
-// Six counters, one per list: the scan's value type.
-struct Six { int v[6]; };
-struct SixSum {
-    __host__ __device__ __forceinline__ Six operator()(const Six& x, const Six& y) const {
-        Six z;
-#pragma unroll
-        for (int k = 0; k < 6; k++) z.v[k] = x.v[k] + y.v[k];
-        return z;
-    }
-};
+// ---- the level's six stable partitions ------------------------------------------------------------------------------------
+// What position i needs in order to move is, per list k, (a) whether its element goes left and (b) how many elements of its
+// node's range before it go left = prefix_k(i) - prefix_k(l), l = the range's start.  A device-wide scan of six-component
+// vectors gave that (first round-2 version: cub::DeviceScan over a 24-byte type with the gathers inside its load phase, half
+// of the build's time).  Here the prefix is split at 512-position blocks: flags_kernel packs, for every position, its six
+// flags and its six IN-BLOCK exclusive prefixes (6 x 9 bits) into one 64-bit word and leaves the six block totals behind;
+// block_scan_kernel turns the totals into block bases (a few thousand numbers); scatter_kernel reads two packed words (its
+// own and its range start's) and two bases per list.  8 bytes per position and level instead of 24 + 72.
+constexpr int kPartBlock = 512;  // positions per block: in-block prefixes fit 9 bits
 // Which child every triangle of an interior node goes to (Trixel.h:237-259): its position in the node's split list is
 // <= m.  One byte per triangle, written from the split list's side -- a 1-byte scatter into an array that stays in L2 --
 // so that the five other lists can ask "left?" with a 1-byte gather instead of a 4-byte gather into a rank array per
@@ -136,34 +137,67 @@ __global__ void side_kernel(int n, const int* __restrict__ node_of_pos, const in
     if (r == l) return;
     side[order[(long long)cut[node] * n + i]] = i <= l + (r - l) / 2 ? 1 : 0;
 }
-// Input of the level's scan, computed where it is consumed: component k at position i is 1 iff the element of list k at
-// position i goes to the left child of its node.  Position n
-// (one past the end) is all zeros, so that scan[i+1] - scan[i] gives every position its own flags back.
-struct GoesLeft {
-    const int* node_of_pos; const int* lo; const int* hi; const unsigned char* cut; const int* order; const unsigned char* side; int n;
-    __host__ __device__ __forceinline__ Six operator()(int i) const {
-        Six f = {{0, 0, 0, 0, 0, 0}};
-        if (i >= n) return f;
+struct IsInterior {
+    const int* lo; const int* hi; int level_begin;
+    __host__ __device__ __forceinline__ int operator()(int q) const { return hi[level_begin + q] > lo[level_begin + q] ? 1 : 0; }
+};
+__global__ void __launch_bounds__(kPartBlock) flags_kernel(int n, const int* __restrict__ node_of_pos, const int* __restrict__ lo, const int* __restrict__ hi,
+                                                           const unsigned char* __restrict__ cut, const int* __restrict__ order,
+                                                           const unsigned char* __restrict__ side, unsigned long long* __restrict__ packed,
+                                                           int* __restrict__ block_sums /* 6 x nblocks */, int nblocks) {
+    __shared__ int wsum[6][kPartBlock / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blockIdx.x * kPartBlock + tid;
+    unsigned f = 0;  // bit k: the element of list k at position i goes to the left child (Trixel.h:237-259)
+    if (i < n) {
         const int node = node_of_pos[i], l = lo[node], r = hi[node];
         if (r > l) {
             const int c = cut[node];
 #pragma unroll
             for (int k = 0; k < 6; k++)
-                if (k != c) f.v[k] = side[order[(long long)k * n + i]];
+                if (k != c) f |= (unsigned)side[order[(long long)k * n + i]] << k;
         }
-        return f;
     }
-};
-struct IsInterior {
-    const int* lo; const int* hi; int level_begin;
-    __host__ __device__ __forceinline__ int operator()(int q) const { return hi[level_begin + q] > lo[level_begin + q] ? 1 : 0; }
-};
-
-// one thread per list position: stable partition of all six lists inside every node range, from the exclusive scan of
-// the GoesLeft vectors; positions of leaves stay where they are.  Also moves every position to its child node.
+    unsigned long long word = (unsigned long long)f << 54;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const unsigned b = __ballot_sync(0xffffffffu, (f >> k) & 1u);
+        word |= (unsigned long long)__popc(b & ((1u << lane) - 1u)) << (9 * k);
+        if (lane == 0) wsum[k][warp] = __popc(b);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        int before = 0;
+        for (int w = 0; w < warp; w++) before += wsum[k][w];
+        word += (unsigned long long)before << (9 * k);  // (<= 511: no carry into the next field)
+    }
+    if (i < n) packed[i] = word;
+    if (tid < 6) {
+        int total = 0;
+        for (int w = 0; w < kPartBlock / 32; w++) total += wsum[tid][w];
+        block_sums[(long long)tid * nblocks + blockIdx.x] = total;
+    }
+}
+// exclusive scan of each list's block totals, in place: one block of 1024 threads per list
+__global__ void __launch_bounds__(1024) block_scan_kernel(int* __restrict__ block_sums, int nblocks) {
+    typedef cub::BlockScan<int, 1024> Scan;
+    __shared__ typename Scan::TempStorage temp;
+    int* a = block_sums + (long long)blockIdx.x * nblocks;
+    const int per = (nblocks + 1023) / 1024;
+    const int begin = min(nblocks, (int)threadIdx.x * per), end = min(nblocks, begin + per);
+    int sum = 0;
+    for (int j = begin; j < end; j++) sum += a[j];
+    int base;
+    Scan(temp).ExclusiveSum(sum, base);
+    for (int j = begin; j < end; j++) { const int v = a[j]; a[j] = base; base += v; }
+}
+// one thread per list position: stable partition of all six lists inside every node range; positions of leaves stay where
+// they are.  Also moves every position to its child node.
 __global__ void scatter_kernel(int n, const int* __restrict__ node_of_pos, const int* __restrict__ lo, const int* __restrict__ hi,
-                               const unsigned char* __restrict__ cut, const int* __restrict__ left, const Six* __restrict__ scan,
-                               const int* __restrict__ order, int* __restrict__ order_out, int* __restrict__ node_out) {
+                               const unsigned char* __restrict__ cut, const int* __restrict__ left, const unsigned long long* __restrict__ packed,
+                               const int* __restrict__ block_base, int nblocks, const int* __restrict__ order, int* __restrict__ order_out,
+                               int* __restrict__ node_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int node = node_of_pos[i], l = lo[node], r = hi[node];
@@ -174,14 +208,17 @@ __global__ void scatter_kernel(int n, const int* __restrict__ node_of_pos, const
         return;
     }
     const int c = cut[node], m = l + (r - l) / 2, cl = left[node];
-    const Six base = scan[l], mine = scan[i], next = scan[i + 1];
+    const unsigned long long wi = packed[i], wl = packed[l];
+    const int bi = i / kPartBlock, bl = l / kPartBlock;
 #pragma unroll
     for (int k = 0; k < 6; k++) {
         const int t = order[(long long)k * n + i];
         int dst = i;
         if (k != c) {
-            const int left_before = mine.v[k] - base.v[k];
-            dst = (next.v[k] - mine.v[k]) ? l + left_before : (m + 1) + ((i - l) - left_before);
+            const int before_i = block_base[(long long)k * nblocks + bi] + (int)((wi >> (9 * k)) & 511u);
+            const int before_l = block_base[(long long)k * nblocks + bl] + (int)((wl >> (9 * k)) & 511u);
+            const int left_before = before_i - before_l;
+            dst = ((wi >> (54 + k)) & 1u) ? l + left_before : (m + 1) + ((i - l) - left_before);
         }
         order_out[(long long)k * n + dst] = t;
     }
@@ -312,6 +349,7 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, DeviceTree& T) {
     if (n64 <= 0 || n64 > 0x1fffffff) return "build_tree_gpu: bad triangle count";
     const int n = (int)n64;
     const int N = 2 * n - 1;
+    const int nblocks = (n + kPartBlock - 1) / kPartBlock;
     const auto t_begin = clock::now();
     const std::vector<LevelShape> levels = tree_shape(n);
     if (levels.empty() || levels.back().begin + levels.back().count != N) return "build_tree_gpu: level shape does not add up";
@@ -320,7 +358,8 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, DeviceTree& T) {
     unsigned *ukey_in = nullptr, *ukey_out = nullptr;
     int *ids_in = nullptr, *order[2] = {nullptr, nullptr}, *node_of_pos[2] = {nullptr, nullptr}, *child_scan = nullptr;
     int *lo = nullptr, *hi = nullptr, *left = nullptr, *tri = nullptr, *rec = nullptr;
-    Six* scan = nullptr;
+    unsigned long long* packed = nullptr;
+    int* block_sums = nullptr;
     unsigned char *cut = nullptr, *side = nullptr;
     void* temp = nullptr;
     void *keep_base = nullptr, *work_base = nullptr;
@@ -340,10 +379,6 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, DeviceTree& T) {
     cub::DeviceRadixSort::SortPairs(nullptr, need, ukey_in, ukey_out, ids_in, ids_in, n);
     temp_bytes = need;
     {
-        GoesLeft src{};
-        thrust::transform_iterator<GoesLeft, thrust::counting_iterator<int>, Six> in(counting, src);
-        cub::DeviceScan::ExclusiveScan(nullptr, need, in, scan, SixSum(), Six{{0, 0, 0, 0, 0, 0}}, n + 1);
-        temp_bytes = temp_bytes > need ? temp_bytes : need;
         IsInterior isrc{};
         thrust::transform_iterator<IsInterior, thrust::counting_iterator<int>, int> iin(counting, isrc);
         cub::DeviceScan::ExclusiveSum(nullptr, need, iin, child_scan, max_count);
@@ -353,7 +388,7 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, DeviceTree& T) {
     work.reserve<int>(6 * (size_t)n); work.reserve<int>(6 * (size_t)n); work.reserve<unsigned char>((size_t)n);  // order x2, side
     work.reserve<int>((size_t)n); work.reserve<int>((size_t)n); work.reserve<int>((size_t)max_count);       // node_of_pos x2, child_scan
     work.reserve<int>((size_t)N); work.reserve<int>((size_t)N);                                             // lo, hi
-    work.reserve<Six>((size_t)n + 1);
+    work.reserve<unsigned long long>((size_t)n); work.reserve<int>(6 * (size_t)nblocks);
     work.reserve<char>(temp_bytes);
     RTB_BUILD_CUDA(cudaGetDevice(&device));
     pool = build_pool(device, err);
@@ -370,7 +405,7 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, DeviceTree& T) {
     side = work.take<unsigned char>((size_t)n); node_of_pos[0] = work.take<int>((size_t)n); node_of_pos[1] = work.take<int>((size_t)n);
     child_scan = work.take<int>((size_t)max_count);
     lo = work.take<int>((size_t)N); hi = work.take<int>((size_t)N);
-    scan = work.take<Six>((size_t)n + 1);
+    packed = work.take<unsigned long long>((size_t)n); block_sums = work.take<int>(6 * (size_t)nblocks);
     temp = work.take<char>(temp_bytes);
     seconds_before_sort = std::chrono::duration<double>(clock::now() - t_begin).count();
 
@@ -400,12 +435,9 @@ std::string build_tree_gpu(const float* d_points9, int64_t n64, DeviceTree& T) {
         launches++;
         if (lv.interior == 0) break;
         side_kernel<<<blocks(n), 256>>>(n, node_of_pos[cur], lo, hi, cut, order[cur], side); launches++;
-        {
-            thrust::transform_iterator<GoesLeft, thrust::counting_iterator<int>, Six> in(counting, GoesLeft{node_of_pos[cur], lo, hi, cut, order[cur], side, n});
-            size_t tb = temp_bytes;
-            RTB_BUILD_CUDA(cub::DeviceScan::ExclusiveScan(temp, tb, in, scan, SixSum(), Six{{0, 0, 0, 0, 0, 0}}, n + 1)); launches += 2;
-        }
-        scatter_kernel<<<blocks(n), 256>>>(n, node_of_pos[cur], lo, hi, cut, left, scan, order[cur], order[cur ^ 1], node_of_pos[cur ^ 1]);
+        flags_kernel<<<nblocks, kPartBlock>>>(n, node_of_pos[cur], lo, hi, cut, order[cur], side, packed, block_sums, nblocks); launches++;
+        block_scan_kernel<<<6, 1024>>>(block_sums, nblocks); launches++;
+        scatter_kernel<<<blocks(n), 256>>>(n, node_of_pos[cur], lo, hi, cut, left, packed, block_sums, nblocks, order[cur], order[cur ^ 1], node_of_pos[cur ^ 1]);
         launches++;
         cur ^= 1;
     }
