@@ -212,8 +212,8 @@ int env_int(const char* name, int dflt) {
 // so that a launch costs no getenv; tests and the tuning tools change them through rtb_set_knob.
 struct Knobs {
     int unit_shift = 0;   // log2 pixels per work unit (5..10), 0 = chosen from the launch size
-    int t_active = 12;    // refill when no more than this many lanes still traverse
-    int t_leaf = 8;       // leaf step when at least this many lanes wait at a leaf
+    int t_active = 4;     // refill when no more than this many lanes still traverse   } re-tuned in round 2 with view-ordered frames
+    int t_leaf = 4;       // leaf step when at least this many lanes wait at a leaf    } (12 / 8 before: DESIGN.md section 4)
     int tail5 = -1, tail6 = -1;  // trailing frames of a launch in 32- / 64-pixel units, -1 = automatic
     int reserve_sms = 0;  // SMs left free beside the persistent kernel
     int l2_window = 1;    // persisting L2 window: 0 off, 1 node records, 2 nodes + triangles (takes effect at add_object)
@@ -470,7 +470,9 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, const flo
     const long long warps_total = (long long)c->sm_count * per_sm * (kBlockThreads / 32);
     // work unit: Morton block of 2^shift pixels; small launches get small units so every warp has work
     const long long pixels = (long long)num_frames * P.my_tiles * kTile * kTile;
-    int shift = 7;  // measured on the dragon stand-in: 128-pixel units beat 32, 64, 256 and 1024
+    // measured on the dragon stand-in: 256-pixel units for launches that give every warp a hundred of them or more (600 frames at
+    // 960x540, 36 at 4K), 128-pixel units below that (60-frame launches: 1.41 vs 1.59 ms), smaller ones for small launches
+    int shift = (pixels >> 8) >= warps_total * 128 ? 8 : 7;
     while (shift > 5 && (pixels >> shift) < warps_total * 4) shift--;
     const Knobs& K = knobs();
     P.unit_shift = std::min(10, std::max(5, K.unit_shift > 0 ? K.unit_shift : shift));
@@ -487,7 +489,7 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, const flo
     // dragon stand-in (60 frames): see DESIGN.md.  RTB_TAIL6 / RTB_TAIL5 = number of trailing frames in 64- / 32-pixel units.
     {
         int t5 = 0, t6 = 0;
-        if (P.unit_shift > 5 && num_frames >= 8) t5 = std::max(1, num_frames / 20);  // measured: 3 of 60 frames; a 64-pixel segment adds nothing
+        if (P.unit_shift > 5 && num_frames >= 8) t5 = std::min(8, std::max(1, num_frames / 20));  // measured: 3 of 60 frames, 0-16 of 600 alike; a 64-pixel segment adds nothing
         const int e5 = K.tail5, e6 = K.tail6;
         t5 = std::min(num_frames, std::max(0, e5 >= 0 ? e5 : t5));
         t6 = std::min(num_frames - t5, std::max(0, e6 >= 0 ? e6 : t6));
