@@ -54,10 +54,11 @@ WORKLOADS = {
     "synthetic10m_7680x4320": (None, 0, 707, 7680, 4320, 4, 0),
 }
 # tiles mode (N > 1) renders N x this many frames per step (weak scaling)
-# (a launch ends with the latency of its longest rays, ~0.3 ms that no number of GPUs shortens: a step must be long enough for
-# that tail not to dominate what is being measured -- at 4K, N x 24 frames per step: the 360-frame sweep of configs[3] in 15 / N
-# steps; measured at N = 8: 84 % with N x 18 frames, 80 % at N = 2 with N x 6)
-TILES_FRAMES = {"dragon_orbit_960x540": 60, "dragon_closeup_960x540": 60, "happy_orbit_3840x2160": 24, "bunny_960x540": 60, "synthetic10m_7680x4320": 1}
+# (a launch ends with the latency of its longest rays, ~0.3 ms that no number of GPUs shortens, and a step with an exchange ends
+# with an all-reduce that waits for the slowest rank: a step must be long enough for that not to dominate what is measured.  At
+# 4K a step is N x 36 frames -- every rank renders as many pixels per step as in frames mode, where a step is 36 frames per rank.
+# Measured at N = 8 with N x 6 / 18 / 24 frames: 64 % (round 1) / 84 % / 86 % before the single-GPU kernel's re-tune, 81 % after.)
+TILES_FRAMES = {"dragon_orbit_960x540": 60, "dragon_closeup_960x540": 60, "happy_orbit_3840x2160": 36, "bunny_960x540": 60, "synthetic10m_7680x4320": 1}
 # the other configurations of BASELINE.json, measured beside the headline in the default N=1 run: (steps, warm-up steps)
 EXTRA_WORKLOADS = {"bunny_960x540": (3, 3), "dragon_closeup_960x540": (3, 3), "happy_orbit_3840x2160": (5, 3), "synthetic10m_7680x4320": (5, 3)}
 README_FPS = 100.0  # /root/reference/README.md:19 (Stanford Dragon, 960x540, unnamed GPU)
@@ -434,18 +435,18 @@ def kernel_only(env, sc, K, Wm, shard="frames", exchange="push", sample_clocks=T
                 compose(slot)
             ev[step][0].record(stream)
             if push_mode:
-                obj.render_frames_push_striped_async(cam, my_mats(step), push_ptrs[2 * slot], push_ptrs[2 * slot + 1], stream.cuda_stream,
-                                                     tile_first=rank, tile_stride=world, flags=rtb.RENDER_PUSH_PREFILLED)
-                ev[step][1].record(stream)
                 # The NEXT step's frames of this owner are pre-filled with background before this step's all-reduce lets any
                 # rank start pushing into them: work units that hold nothing but background then never cross NVLink.  The
-                # fill is queued on a second stream BEHIND the render kernel: the other slot has been free since the previous
-                # step's all-reduce, and the fill's blocks move in as the persistent kernel's blocks leave -- it runs in the
-                # shadow of the launch's tail (the latency of its longest rays) instead of after it.
+                # other slot has been free since the previous step's all-reduce, so the fill -- a few thread blocks per SM on
+                # a second stream, queued IN FRONT of the persistent render kernel -- runs beside this step's rendering.
                 if allreduce_done[0] is not None:
                     side.wait_event(allreduce_done[0])
                 cam.fill_frames_device_async(owned, my_bufs[2 * (slot ^ 1)].ptr, my_bufs[2 * (slot ^ 1) + 1].ptr, side.cuda_stream)
                 fill_done = torch.cuda.Event(); fill_done.record(side)
+                ev[step][0].record(stream)  # (again: the kernel's event pair starts after the fill has been queued)
+                obj.render_frames_push_striped_async(cam, my_mats(step), push_ptrs[2 * slot], push_ptrs[2 * slot + 1], stream.cuda_stream,
+                                                     tile_first=rank, tile_stride=world, flags=rtb.RENDER_PUSH_PREFILLED)
+                ev[step][1].record(stream)
                 stream.wait_event(fill_done)
                 dist.all_reduce(push_flag)  # completes when every rank's kernel has: the step's frames are whole on their owners
                 allreduce_done[0] = torch.cuda.Event(); allreduce_done[0].record(stream)

@@ -225,6 +225,7 @@ struct Knobs {
     int t_active_inline = 30;   // single-frame launches: t_active (a warp that sees the empty queue early shares its long rays early)
     int steal_spin = 8;         // ... and how many iterations a draining warp runs between two looks for lanes to share with (power of two)
     int inline_prefetch = 1;    // ... and whether it asks for both children's records ahead of the decision
+    int fill_ctas_per_sm = 2;   // rtb_fill_frames_device_async: thread blocks per SM of the fill kernel (it is meant to run beside a render)
     int lookahead = 2;          // single-frame path: predicted frames kept in flight behind the current one (0 = off)
     int sweep_chunk_mb = 256;   // ... and the largest size of the chunks (MB of host frames) in which fill and render alternate
     int l2_carve_mb = 0;  // persisting L2 carve-out in MB, 0 = the size of the window
@@ -239,7 +240,8 @@ Knobs& knobs() {
         v.host_direct = env_int("RTB_HOST_DIRECT", v.host_direct); v.sweep_direct = env_int("RTB_SWEEP_DIRECT", v.sweep_direct);
         v.host_fill_threads = env_int("RTB_HOST_FILL_THREADS", v.host_fill_threads); v.sweep_chunk_mb = env_int("RTB_SWEEP_CHUNK_MB", v.sweep_chunk_mb);
         v.t_active_inline = env_int("RTB_T_ACTIVE_INLINE", v.t_active_inline); v.steal_spin = env_int("RTB_STEAL_SPIN", v.steal_spin);
-        v.inline_prefetch = env_int("RTB_INLINE_PREFETCH", v.inline_prefetch); v.lookahead = env_int("RTB_LOOKAHEAD", v.lookahead); v.l2_carve_mb = env_int("RTB_L2_CARVE_MB", v.l2_carve_mb);
+        v.inline_prefetch = env_int("RTB_INLINE_PREFETCH", v.inline_prefetch); v.lookahead = env_int("RTB_LOOKAHEAD", v.lookahead);
+        v.fill_ctas_per_sm = env_int("RTB_FILL_CTAS_PER_SM", v.fill_ctas_per_sm); v.l2_carve_mb = env_int("RTB_L2_CARVE_MB", v.l2_carve_mb);
         return v;
     }();
     return k;
@@ -472,6 +474,7 @@ int launch_render(rtb_object* o, rtb_camera* c, const float* d_frames, const flo
     const long long pixels = (long long)num_frames * P.my_tiles * kTile * kTile;
     // measured on the dragon stand-in: 256-pixel units for launches that give every warp a hundred of them or more (600 frames at
     // 960x540, 36 at 4K), 128-pixel units below that (60-frame launches: 1.41 vs 1.59 ms), smaller ones for small launches
+    // (the same holds for the push variant in tile mode: tools/push_tune.py)
     int shift = (pixels >> 8) >= warps_total * 128 ? 8 : 7;
     while (shift > 5 && (pixels >> shift) < warps_total * 4) shift--;
     const Knobs& K = knobs();
@@ -752,6 +755,7 @@ int rtb_set_knob(const char* name, int value) {
     else if (n == "steal_spin") k.steal_spin = value;
     else if (n == "inline_prefetch") k.inline_prefetch = value;
     else if (n == "lookahead") k.lookahead = value;
+    else if (n == "fill_ctas_per_sm") k.fill_ctas_per_sm = value;
     else if (n == "l2_carve_mb") k.l2_carve_mb = value;
     else return fail(RTB_ERR_ARG, "set_knob: unknown knob " + n);
     return RTB_OK;
@@ -1550,9 +1554,12 @@ int rtb_fill_frames_device_async(rtb_camera* cam, int32_t num_frames, uint32_t* 
     const rtb::CameraBasis& b = cam->basis;
     const uint32_t bg = ((uint32_t)b.background[3] << 24) | ((uint32_t)b.background[0] << 16) | ((uint32_t)b.background[1] << 8) | b.background[2];
     const long long count = (long long)num_frames * cam->pixels;
-    const unsigned grid = (unsigned)std::min<long long>((count + 255) / 256, 148ll * 64);
-    if (d_frame_bgra) { rtb::fill_kernel<<<grid, 256, 0, s>>>(d_frame_bgra, count, bg); g_launches++; }
-    if (d_frame_ids) { rtb::fill_ids_kernel<<<grid, 256, 0, s>>>(d_frame_ids, count, -1); g_launches++; }
+    // A few blocks per SM (knob fill_ctas_per_sm, default 2): queued in front of a persistent render launch on another stream,
+    // the fill then runs beside it -- it takes two of the SM's thread-block slots for its duration instead of the whole GPU
+    // for half a millisecond -- which is how bench.py's tile mode pre-fills the next step's frames.
+    const unsigned grid = (unsigned)std::min<long long>((count / 4 + 511) / 512, (long long)std::max(1, cam->sm_count) * std::max(1, knobs().fill_ctas_per_sm));
+    rtb::fill_frames_kernel<<<std::max(1u, grid), 512, 0, s>>>(d_frame_bgra, d_frame_ids, count, bg);
+    g_launches++;
     RTB_CUDA(cudaGetLastError());
     return RTB_OK;
 }

@@ -264,6 +264,25 @@ __global__ void compose_tiles_kernel(ComposeParts parts, int world, int W, int H
     }
 }
 
+// Both frame arrays of a block of frames in one grid-stride kernel with 16-byte stores (either array may be null): meant to
+// run BESIDE the persistent render kernel on a few blocks per SM (rtb_fill_frames_device_async), not to own the GPU.
+__global__ void fill_frames_kernel(uint32_t* __restrict__ bgra, int32_t* __restrict__ ids, long long n, uint32_t background) {
+    const long long stride = (long long)gridDim.x * blockDim.x, first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec = (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(bgra) | reinterpret_cast<uintptr_t>(ids)) & 15u) == 0;
+    if (vec) {
+        const uint4 b4 = make_uint4(background, background, background, background);
+        const int4 i4 = make_int4(-1, -1, -1, -1);
+        for (long long i = first; i < (n >> 2); i += stride) {
+            if (bgra) reinterpret_cast<uint4*>(bgra)[i] = b4;
+            if (ids) reinterpret_cast<int4*>(ids)[i] = i4;
+        }
+    } else {
+        for (long long i = first; i < n; i += stride) {
+            if (bgra) bgra[i] = background;
+            if (ids) ids[i] = -1;
+        }
+    }
+}
 __global__ void fill_kernel(uint32_t* __restrict__ out, long long n, uint32_t value) {  // grid-stride
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = value;
 }
