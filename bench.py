@@ -721,7 +721,7 @@ def run_ours(args):
 
     # ---- N > 1, sweep sharded by frames: the path's one real exchange measured beside it -- the 4K configuration split by
     # tiles, finished work units pushed by the render kernel into the frames' owners (striped) over NVLink ------------------
-    tiles = None
+    tiles = frames_4k = None
     if world > 1 and args.shard == "frames" and not args.no_tiles_leg:
         tw = "happy_orbit_3840x2160"
         ts = Scene(env, tw, TILES_FRAMES[tw])
@@ -756,6 +756,11 @@ def run_ours(args):
                  "exchange": "fused into the render kernel: finished 32x4-pixel work units stored as 128-byte rows into the frame's owner "
                              "(frame f -> rank f % N) over NVLink peer memory; one 4-byte all-reduce per step is the only collective",
                  "scaling": "strong (one step's frames split by tiles over N GPUs against the same frames on one GPU)"}
+        # the same 4K configuration sharded by FRAMES (36 per rank and step, no collective): BASELINE.json's "near-linear 8-GPU scaling
+        # at 4K" in the driver's own record; its N=1 figure is workloads.happy_orbit_3840x2160.value of the N=1 line
+        f4 = kernel_only(env, ts, 3, 3, shard="frames", sample_clocks=False)
+        frames_4k = {"workload": tw, "resolution": [ts.W, ts.H], "frames_per_rank_and_step": ts.F, "value": f4["value"], "unit": "Mrays/s", "fps": f4["fps"],
+                     "ms_per_step": f4["ms_per_step"], "per_gpu_value": f4["value"] / world, "scaling": "weak (blocks of frames per rank, no collective)"}
         ts.close()
 
     if rank != 0:
@@ -817,7 +822,7 @@ def run_ours(args):
                        (64.0 * (n_tri - 1) + 48.0 * n_tri) / 1e6, F * P * 8 / 1e6),
                    "fps": head["fps"], "fps_vs_readme_100fps": head["fps"] / README_FPS, "tree_build_s": build_total, "cpu_affinity": env.numa},
         "e2e": e2e, "gpu_launches": head["launches"], "clocks": head["clocks"], "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu,
-        "reference_classes_over_librtb": ref_seam, "frame_loop": loop, "tiles": tiles, "workloads": others, "scene_extension": scene_ext,
+        "reference_classes_over_librtb": ref_seam, "frame_loop": loop, "tiles": tiles, "frames_4k": frames_4k, "workloads": others, "scene_extension": scene_ext,
         "kernel_ms": {"mean": float(np.mean(kernel_ms)), "min": float(np.min(kernel_ms)), "max": float(np.max(kernel_ms))},
     }
     print(json.dumps(line))
