@@ -36,7 +36,7 @@ EXPORTS = [
     "rtb_camera_counters", "rtb_camera_counters_ex", "rtb_camera_destroy", "rtb_object_create", "rtb_object_transform", "rtb_object_get_matrix",
     "rtb_object_set_matrix", "rtb_object_destroy", "rtb_object_render", "rtb_render_frame", "rtb_camera_set_lights", "rtb_camera_set_shadows", "rtb_camera_set_sample_rate", "rtb_camera_object_id_base",
     "rtb_camera_render_scene", "rtb_camera_render_scene_device_async", "rtb_render_sweep",
-    "rtb_render_frames_device_async", "rtb_render_frames_push_async", "rtb_render_frames_push_striped_async", "rtb_fill_frames_device_async", "rtb_peer_alloc", "rtb_peer_free", "rtb_peer_export", "rtb_peer_open", "rtb_peer_close", "rtb_peer_read", "rtb_object_transform_host", "rtb_transform_sequence_host", "rtb_device_props", "rtb_launch_count", "rtb_tile_major_elements", "rtb_compose_tiles_device_async", "rtb_selftest_exact", "rtb_measure_l2_read_bandwidth", "rtb_measure_host_fill_bandwidth",
+    "rtb_render_frames_device_async", "rtb_render_frames_push_async", "rtb_render_frames_push_striped_async", "rtb_fill_frames_device_async", "rtb_peer_alloc", "rtb_peer_free", "rtb_peer_export", "rtb_peer_open", "rtb_peer_close", "rtb_peer_read", "rtb_object_transform_host", "rtb_transform_sequence_host", "rtb_device_props", "rtb_launch_count", "rtb_tile_major_elements", "rtb_compose_tiles_device_async", "rtb_selftest_exact", "rtb_measure_l2_read_bandwidth", "rtb_measure_host_fill_bandwidth", "rtb_host_alloc", "rtb_host_free",
 ]
 
 
@@ -112,6 +112,8 @@ def _load():
     L.rtb_fill_frames_device_async.argtypes = [vp, C.c_int32, vp, vp, vp]
     L.rtb_measure_l2_read_bandwidth.argtypes = [C.c_size_t, C.c_int, C.POINTER(C.c_double)]
     L.rtb_measure_host_fill_bandwidth.argtypes = [C.c_size_t, C.c_int, C.POINTER(C.c_double)]
+    L.rtb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.rtb_host_free.argtypes = [vp]
     L.rtb_peer_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.rtb_peer_free.argtypes = [vp]
     L.rtb_peer_export.argtypes = [vp, vp]

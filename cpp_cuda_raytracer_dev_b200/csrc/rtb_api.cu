@@ -1735,6 +1735,17 @@ int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32
     return RTB_OK;
 }
 
+int rtb_host_alloc(size_t bytes, void** ptr) {
+    if (!ptr || bytes == 0) return fail(RTB_ERR_ARG, "host_alloc: bad argument");
+    RTB_CUDA(cudaSetDevice(g_device));
+    RTB_CUDA(cudaMallocHost(ptr, bytes));
+    return RTB_OK;
+}
+int rtb_host_free(void* ptr) {
+    if (ptr) RTB_CUDA(cudaFreeHost(ptr));
+    return RTB_OK;
+}
+
 int64_t rtb_tile_major_elements(const rtb_camera* cam, int32_t tile_stride) {
     if (!cam || tile_stride < 1) return 0;
     const int tiles = ((cam->basis.W + rtb::kTile - 1) / rtb::kTile) * ((cam->basis.H + rtb::kTile - 1) / rtb::kTile);

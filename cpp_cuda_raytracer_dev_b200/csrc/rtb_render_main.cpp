@@ -114,14 +114,23 @@ int main(int argc, char** argv) {
     if (sweep) {
         std::vector<float> ops(5 * (size_t)frames);
         for (int f = 0; f < frames; f++) { ops[5 * f] = f ? (float)ROTATE_TRI_PY : 0.0f; std::memcpy(&ops[5 * f + 1], quat, sizeof quat); }
-        std::vector<uint32_t> colors((size_t)frames * W * H);
-        std::vector<int32_t> ids((size_t)frames * W * H);
-        if (rtb_render_sweep(obj1->handle, main_cam->handle, frames, 1, ops.data(), RTB_RENDER_DEFAULT, colors.data(), ids.data()) != 0) {
+        // pinned buffers: the sweep then pre-fills the background on the host and the kernel stores the rest (no copy engine)
+        const size_t words = (size_t)frames * W * H;
+        void *colors_mem = nullptr, *ids_mem = nullptr;
+        if (rtb_host_alloc(4 * words, &colors_mem) != 0 || rtb_host_alloc(4 * words, &ids_mem) != 0) {
+            std::fprintf(stderr, "host_alloc: %s\n", rtb_last_error());
+            return 1;
+        }
+        uint32_t* colors = static_cast<uint32_t*>(colors_mem);
+        int32_t* ids = static_cast<int32_t*>(ids_mem);
+        t0 = now_s();
+        if (rtb_render_sweep(obj1->handle, main_cam->handle, frames, 1, ops.data(), RTB_RENDER_DEFAULT, colors, ids) != 0) {
             std::fprintf(stderr, "render_sweep: %s\n", rtb_last_error());
             return 1;
         }
         const double dt = now_s() - t0;
-        for (int f = 0; f < frames; f++) present(f, colors.data() + (size_t)f * W * H, ids.data() + (size_t)f * W * H);
+        for (int f = 0; f < frames; f++) present(f, colors + (size_t)f * W * H, ids + (size_t)f * W * H);
+        rtb_host_free(colors_mem); rtb_host_free(ids_mem);
         std::printf("Resolution: %d x %d\nFPS: %f (sweep of %d frames, %.1f Mrays/s)\n", W, H, frames / dt, frames, frames * (double)W * H / dt / 1e6);
     } else {
         main_cam->color_pixels(SET_COLOR_TAG);

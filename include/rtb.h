@@ -243,6 +243,12 @@ int rtb_camera_render_scene_device_async(rtb_camera* cam, uint32_t flags, uint32
  * one by one; the camera's single-frame buffers (rtb_camera_host_color / _ids) are left untouched. */
 int rtb_render_sweep(rtb_object* obj, rtb_camera* cam, int32_t num_frames, int32_t steps_per_frame,
                      const float* ops5, uint32_t flags, uint32_t* bgra_out, int32_t* ids_out);
+/* Pinned (page-locked, device-mapped) host memory for rtb_render_sweep's output buffers, for callers without the CUDA
+ * headers: buffers from here take the sweep's fast path (background pre-filled by host threads, the rest stored by the
+ * kernel); pageable buffers take the copy-engine path.  Release with rtb_host_free. */
+int rtb_host_alloc(size_t bytes, void** ptr);
+int rtb_host_free(void* ptr);
+
 
 /* Device-resident variant for callers that own device memory and a stream (multi-GPU gather,
  * kernel-only timing): renders frames m12[f] (12 floats each), f in [0,num_frames), restricted to
